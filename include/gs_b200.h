@@ -1,0 +1,195 @@
+/*
+ * gs_b200.h — C ABI of the B200 (sm_100a) ground-segmentation hot path.
+ *
+ * This is the drop-in boundary for ONE path of matigolias/GroundSegmentationROSNode:
+ *     point cloud -> range image -> angle image -> ground mask -> point cloud
+ * (reference call stack: src/alfa_gs.cpp:175-244, the hw==0 branch of
+ * Alfa_GS::process_pointcloud; two-node packaging: src/cloud2range_node.cpp:381-480 and
+ * src/range2cloud_node.cpp:36-99).
+ *
+ * The reference has no FFI for this path: its only accelerator seam is the `hw` switch in
+ * Alfa_GS::process_pointcloud (src/alfa_gs.cpp:97,175) that routes stages to an FPGA through
+ * AlfaNode's store/read helpers (lib/alfa_node.h:102-149).  The entry points below are what a
+ * GPU back end bound at that seam needs; each cites the reference member it replaces.  Plain
+ * pointers and sizes only — no C++/torch/OpenCV/PCL types cross this boundary.
+ *
+ * Conventions
+ *   - images are row-major, row 0 = highest beam (src/alfa_gs.cpp:275); u16 range pixels,
+ *     0 = empty, otherwise 1 + 65534 * (range - min_range) / (max_range - min_range);
+ *   - a point record is `stride` bytes with float x,y,z at byte offsets 0,4,8
+ *     (pcl::PointXYZI = 16 B, pcl::PointXYZRGB = 32 B);
+ *   - every function returns GS_OK or an error code and never throws / aborts;
+ *     gs_last_error() gives the message of the last failure on that context;
+ *   - a context is used by one host thread at a time; one context per GPU; contexts are
+ *     independent (the reference runs the path on one ros::spin thread, src/alfa_node.cpp:387).
+ *   - there is NO CPU fallback: without a CUDA device gs_create() fails with GS_ECUDA.
+ */
+#ifndef GS_B200_H
+#define GS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GS_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------- */
+#define GS_OK 0
+#define GS_EINVAL 1 /* bad argument / window size / shape (reference: std::logic_error, ROS_ASSERT) */
+#define GS_ECUDA 2  /* CUDA runtime failure, message in gs_last_error()                           */
+#define GS_ENOMEM 3
+#define GS_ESTATE 4
+
+/* ---- policies ------------------------------------------------------- */
+/* which packaging of the pipeline the formulas follow */
+#define GS_VARIANT_ALFA_GS 0     /* src/alfa_gs.cpp (the executable CMake builds)              */
+#define GS_VARIANT_CLOUD2RANGE 1 /* src/cloud2range_node.cpp + src/range2cloud_node.cpp        */
+/* which return owns a pixel when several points project to it */
+#define GS_PIXEL_LAST 0    /* reference: plain overwrite in input order (alfa_gs.cpp:291)      */
+#define GS_PIXEL_NEAREST 1 /* north-star variant: smallest range, ties -> lowest index         */
+/* what happens to col == n_cols (alfa_gs.cpp:277 leaves it un-wrapped) */
+#define GS_COL_FLAT_ALIAS 0 /* reference: lands on flat index row*W+W = (row+1, 0); dropped past the end */
+#define GS_COL_WRAP 1       /* intended behaviour: col % n_cols                                */
+/* angle-image smoothing before the ground search */
+#define GS_SMOOTH_NONE 0 /* alfa_gs.cpp:212-220: the moving average result is discarded        */
+#define GS_SMOOTH_SG 1   /* cloud2range_node.cpp:470: Savitzky-Golay, window = window_size     */
+
+/*
+ * Parameters — the constants of Alfa_GS::Alfa_GS (src/alfa_gs.cpp:16-38) and
+ * Cloud2RangeNode::Cloud2RangeNode (src/cloud2range_node.cpp:281-300).
+ * Derived values (n_cols, d_azimuth, d_altitude; alfa_gs.cpp:48-50) are recomputed by
+ * gs_create()/gs_set_params() — unlike Alfa_GS::UpdateSegmentationSettings
+ * (alfa_gs.cpp:1122-1136), which forgets to.
+ */
+typedef struct gs_params {
+    int32_t n_beams;     /* H, image rows                                   */
+    int32_t rpm;         /* rotations per minute                            */
+    int32_t sample_freq; /* firings per second; n_cols = sample_freq*60/rpm */
+    double min_angle;    /* rad, lowest beam altitude                       */
+    double max_angle;    /* rad, highest beam altitude                      */
+    double min_range;    /* m                                               */
+    double max_range;    /* m                                               */
+    double ground_angle_threshold; /* rad (alfa_gs.cpp:18)                  */
+    double start_angle_threshold;  /* rad (alfa_gs.cpp:20)                  */
+    int32_t window_size;  /* 5,7,9,11: SG window and dilation kernel source (alfa_gs.cpp:16) */
+    int32_t erase_ground; /* 1: output keeps non-ground; 0: keeps ground (alfa_gs.cpp:38,753) */
+    int32_t variant;      /* GS_VARIANT_*      */
+    int32_t pixel_policy; /* GS_PIXEL_*        */
+    int32_t col_policy;   /* GS_COL_*          */
+    int32_t smoothing;    /* GS_SMOOTH_*       */
+    int32_t repair_gaps;  /* 0 (default) / 1: typed RepairGaps before the angle image (cloud2range_node.cpp:468) */
+    int32_t reserved;
+} gs_params;
+
+/* values the reference derives in its constructors, plus the integer cut-offs of appendix A.3/A.4 */
+typedef struct gs_derived {
+    int32_t n_rows, n_cols;
+    double d_azimuth, d_altitude;
+    int32_t k_ground;     /* edge  <=> |angle difference| <= k_ground (label.cpp:90,99)       */
+    int32_t s_start;      /* seed accepted <=> angle <= s_start       (alfa_gs.cpp:733)       */
+    int32_t n_dilate;     /* number of vertical taps of the effective structuring element      */
+    int32_t dilate_off[2];/* dilated(r,c) = OR_k L(r + dilate_off[k], c) (alfa_gs.cpp:747-750) */
+} gs_derived;
+
+/* sensor presets taken from the reference's own parameter blocks */
+#define GS_PRESET_ALFA_GS_DEFAULT 0 /* alfa_gs.cpp:16-38: HDL-64E, 64 x 1800                  */
+#define GS_PRESET_VLP16 1           /* cloud2range_node.cpp:66-86: 16 x 1800                  */
+#define GS_PRESET_HDL64E_2048 2     /* alfa_gs.cpp:16-38 with sample_freq 20480: 64 x 2048    */
+#define GS_PRESET_OS1_128 3         /* cloud2range_node.cpp:281-300, beams x2: 128 x 2048     */
+#define GS_PRESET_CLOUD2RANGE_DEFAULT 4 /* cloud2range_node.cpp:281-300: OS1-64, 64 x 2000, cloud2range variant, SG-7 */
+#define GS_PRESET_HDL32 5           /* cloud2range_node.cpp:122-135: 32 x 1800                */
+
+typedef struct gs_ctx gs_ctx;
+
+/* counters filled by the last call on a context */
+typedef struct gs_stats {
+    uint64_t kernel_launches;   /* CUDA kernels launched by this context since creation           */
+    uint64_t near_edge_project; /* points whose altitude/azimuth lies within 1e-5 rad of a cell edge */
+    uint64_t near_edge_angle;   /* pixels whose inclination angle lies within 1e-5 rad of a centi-radian edge */
+    uint64_t dropped_points;    /* points skipped by range/altitude gates or falling outside the image */
+    uint64_t slow_path_points;  /* points that took the double-precision re-check in the projection */
+} gs_stats;
+
+/* ---- parameters --------------------------------------------------------------------------- */
+int gs_abi_version(void);
+int gs_default_params(int preset, gs_params* out);
+/* alfa_gs.cpp:48-50 (+ thresholds, dilation taps).  GS_EINVAL on a bad window / shape. */
+int gs_derive(const gs_params* p, gs_derived* out);
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* replaces Alfa_GS::Alfa_GS (alfa_gs.cpp:12-93): parameters, derived values, LUTs, device scratch */
+int gs_create(const gs_params* p, int device, gs_ctx** out);
+void gs_destroy(gs_ctx* ctx);
+/* replaces Alfa_GS::UpdateSegmentationSettings (alfa_gs.cpp:1122-1136) */
+int gs_set_params(gs_ctx* ctx, const gs_params* p);
+int gs_get_params(const gs_ctx* ctx, gs_params* out);
+int gs_get_derived(const gs_ctx* ctx, gs_derived* out);
+/* all work of the context is enqueued on this cudaStream_t (0 = the context's own stream) */
+int gs_set_stream(gs_ctx* ctx, void* cuda_stream);
+/* frames processed per wave by the batch calls (scratch = chunk * ~20 B/pixel, kept L2 resident) */
+int gs_set_chunk_frames(gs_ctx* ctx, int frames);
+int gs_get_stats(gs_ctx* ctx, gs_stats* out);
+const char* gs_last_error(const gs_ctx* ctx);
+
+/* ---- stage API: one frame, HOST buffers (copies included) ---------------------------------- */
+/* Alfa_GS::CreateRangeImage (alfa_gs.cpp:247-298) / Cloud2RangeNode::CloudCb projection
+ * (cloud2range_node.cpp:396-455), chosen by params.variant.  range_out: n_rows*n_cols u16. */
+int gs_project(gs_ctx* ctx, const void* points, size_t n_points, size_t stride_bytes,
+               uint16_t* range_out);
+/* Alfa_GS::CreateAngleImg (alfa_gs.cpp:335-386) */
+int gs_angle_image(gs_ctx* ctx, const uint16_t* range, uint16_t* angle_out);
+/* Alfa_GS::SavitskyGolaySmoothing (alfa_gs.cpp:705-713); window in {5,7,9,11} else GS_EINVAL
+ * (reference: std::logic_error, alfa_gs.cpp:642-649) */
+int gs_smooth(gs_ctx* ctx, const uint16_t* angle, int window, uint16_t* smoothed_out);
+/* typed Alfa_GS::RepairGaps (alfa_gs.cpp:300-333) on encoded u16 depths */
+int gs_repair_gaps(gs_ctx* ctx, const uint16_t* range, int step, float depth_threshold,
+                   uint16_t* repaired_out);
+/* Alfa_GS::EraseBFS (alfa_gs.cpp:715-766) incl. Label::LabelOneComponent (Labeler/label.cpp:48-104),
+ * GetUniformKernel + cv::dilate (alfa_gs.cpp:747-750).  labels_out (n_rows*n_cols u8, may be NULL)
+ * receives the Labeler's label image before dilation.  Even kernel_size-2 -> GS_EINVAL
+ * (reference: std::logic_error, alfa_gs.cpp:631-633). */
+int gs_erase_ground(gs_ctx* ctx, const uint16_t* range, const uint16_t* angle,
+                    double ground_angle_threshold, double start_angle_threshold, int kernel_size,
+                    uint16_t* res_out, uint8_t* labels_out);
+/* Label::LabelOneComponent (Labeler/label.cpp:48-104) on an existing label image (in/out, u8):
+ * labels the 4-connected component of (row,col) under the angle threshold; already labelled
+ * pixels are barriers, empty pixels are labelled but not expanded. */
+int gs_label_one_component(gs_ctx* ctx, int label, int row, int col, float angle_threshold,
+                           const uint16_t* range, const uint16_t* angle, uint8_t* label_image);
+/* The Labeler driven as an all-components CCL (north-star kernel 4): components of the non-zero
+ * pixels of `image` under the angle threshold `beta` (rad).  labels_out: int32 per pixel = smallest
+ * flat index of the pixel's component (canonical relabelling), -1 for empty pixels. */
+int gs_label_components(gs_ctx* ctx, const uint16_t* image, const uint16_t* angle, double beta,
+                        int32_t* labels_out, int32_t* n_components_out);
+/* Alfa_GS::CameraCb (alfa_gs.cpp:997-1074) / Range2CloudNode::CameraCb (range2cloud_node.cpp:36-99,
+ * double range) chosen by params.variant.  xyz4_out: up to n_rows*n_cols records {x,y,z,1.0f},
+ * row-major order of the surviving pixels. */
+int gs_backproject(gs_ctx* ctx, const uint16_t* image, float* xyz4_out, uint32_t* n_out);
+/* Alfa_GS::process_pointcloud, hw==0 branch (alfa_gs.cpp:175-244) / Cloud2RangeNode::CloudCb +
+ * Range2CloudNode::CameraCb.  Any output pointer may be NULL. */
+int gs_process_frame(gs_ctx* ctx, const void* points, size_t n_points, size_t stride_bytes,
+                     uint16_t* range_out, uint16_t* angle_out, uint16_t* no_ground_out,
+                     float* xyz4_out, uint32_t* n_out);
+
+/* ---- batch API: frames are independent (alfa_gs.cpp:196-239 holds no cross-frame state) ---- */
+/* DEVICE buffers.  points: packed 16-byte XYZI records of all frames; offsets (HOST, n_frames+1
+ * entries, in points) delimit frames.  no_ground_out: n_frames * P u16;  xyz4_out: n_frames * P
+ * float4 slabs (frame f starts at f*P records);  counts_out: n_frames u32 (device).
+ * range_out / angle_out may be NULL.  Asynchronous on the context's stream. */
+int gs_process_batch_device(gs_ctx* ctx, const float* d_points_xyzi, const int64_t* h_offsets,
+                            int n_frames, uint16_t* d_range_out, uint16_t* d_angle_out,
+                            uint16_t* d_no_ground_out, float* d_xyz4_out, uint32_t* d_counts_out);
+/* HOST buffers (pinned recommended): the same, with the host<->device copies done inside,
+ * overlapped with compute over chunks.  Synchronous: outputs are complete on return. */
+int gs_process_batch_host(gs_ctx* ctx, const float* h_points_xyzi, const int64_t* h_offsets,
+                          int n_frames, uint16_t* h_no_ground_out, float* h_xyz4_out,
+                          uint32_t* h_counts_out);
+int gs_synchronize(gs_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GS_B200_H */

@@ -1,0 +1,2 @@
+// empty shim: lib/utils.h includes <pcl/point_types.h> but uses nothing from it (oracle/_ref build only)
+#pragma once
