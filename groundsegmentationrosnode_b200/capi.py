@@ -1,0 +1,265 @@
+"""ctypes binding of libgs_b200.so (include/gs_b200.h) — the only way Python reaches the CUDA path.
+
+The library is built in-tree by `groundsegmentationrosnode_b200/csrc/build.py` (nvcc, sm_100a).  There is
+no fallback: a missing library raises ImportError-like RuntimeError at load time, and a missing GPU makes
+`Context()` raise `GsError(GS_ECUDA)`.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .params import (GS_ECUDA, GS_EINVAL, GS_OK, GsDerived, GsParams, GsStats)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgs_b200.so")
+
+GS_OPT_COLLECT_STATS = 1
+GS_OPT_FORCE_STAGED = 2
+
+# every symbol include/gs_b200.h declares (tests check that the library exports all of them)
+EXPORTS = [
+    "gs_abi_version", "gs_default_params", "gs_derive", "gs_create", "gs_destroy", "gs_set_params", "gs_get_params",
+    "gs_get_derived", "gs_set_stream", "gs_set_chunk_frames", "gs_set_option", "gs_get_stats", "gs_reset_stats",
+    "gs_last_error", "gs_project", "gs_angle_image", "gs_smooth", "gs_repair_gaps", "gs_erase_ground",
+    "gs_label_one_component", "gs_label_components", "gs_backproject", "gs_process_frame", "gs_process_batch_device",
+    "gs_process_batch_host", "gs_synchronize",
+]
+
+
+class GsError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("gs_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+_lib = None
+
+
+def load(build_if_missing=False):
+    """dlopen the C-ABI library.  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if build_if_missing:
+            from .csrc import build as _b
+
+            _b.build()
+        else:
+            raise RuntimeError("%s is missing: run `python groundsegmentationrosnode_b200/csrc/build.py` "
+                               "(there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u16p, u8p, f32p, i32p, i64p = (C.c_void_p,) * 6
+    L.gs_abi_version.restype = C.c_int
+    L.gs_default_params.argtypes = [C.c_int, C.POINTER(GsParams)]
+    L.gs_derive.argtypes = [C.POINTER(GsParams), C.POINTER(GsDerived)]
+    L.gs_create.argtypes = [C.POINTER(GsParams), C.c_int, C.POINTER(C.c_void_p)]
+    L.gs_destroy.argtypes = [C.c_void_p]
+    L.gs_destroy.restype = None
+    L.gs_set_params.argtypes = [C.c_void_p, C.POINTER(GsParams)]
+    L.gs_get_params.argtypes = [C.c_void_p, C.POINTER(GsParams)]
+    L.gs_get_derived.argtypes = [C.c_void_p, C.POINTER(GsDerived)]
+    L.gs_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.gs_set_chunk_frames.argtypes = [C.c_void_p, C.c_int]
+    L.gs_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.gs_get_stats.argtypes = [C.c_void_p, C.POINTER(GsStats)]
+    L.gs_reset_stats.argtypes = [C.c_void_p]
+    L.gs_last_error.argtypes = [C.c_void_p]
+    L.gs_last_error.restype = C.c_char_p
+    L.gs_project.argtypes = [C.c_void_p, vp, C.c_size_t, C.c_size_t, u16p]
+    L.gs_angle_image.argtypes = [C.c_void_p, u16p, u16p]
+    L.gs_smooth.argtypes = [C.c_void_p, u16p, C.c_int, u16p]
+    L.gs_repair_gaps.argtypes = [C.c_void_p, u16p, C.c_int, C.c_float, u16p]
+    L.gs_erase_ground.argtypes = [C.c_void_p, u16p, u16p, C.c_double, C.c_double, C.c_int, u16p, u8p]
+    L.gs_label_one_component.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, u16p, u16p, u8p]
+    L.gs_label_components.argtypes = [C.c_void_p, u16p, u16p, C.c_double, i32p, C.POINTER(C.c_int32)]
+    L.gs_backproject.argtypes = [C.c_void_p, u16p, f32p, C.POINTER(C.c_uint32)]
+    L.gs_process_frame.argtypes = [C.c_void_p, vp, C.c_size_t, C.c_size_t, u16p, u16p, u16p, f32p, C.POINTER(C.c_uint32)]
+    L.gs_process_batch_device.argtypes = [C.c_void_p, vp, i64p, C.c_int, vp, vp, vp, vp, vp]
+    L.gs_process_batch_host.argtypes = [C.c_void_p, vp, i64p, C.c_int, vp, vp, C.c_uint64, i64p]
+    L.gs_synchronize.argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+def default_params(preset):
+    p = GsParams()
+    rc = load().gs_default_params(preset, C.byref(p))
+    if rc != GS_OK:
+        raise GsError(rc, "unknown preset %r" % (preset,))
+    return p
+
+
+def derive(p):
+    d = GsDerived()
+    rc = load().gs_derive(C.byref(p), C.byref(d))
+    if rc != GS_OK:
+        raise GsError(rc, "invalid parameters")
+    return d
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _u16(img, shape):
+    a = np.ascontiguousarray(img, dtype=np.uint16)
+    if a.shape != tuple(shape):
+        raise GsError(GS_EINVAL, "image shape %r != %r" % (a.shape, tuple(shape)))
+    return a
+
+
+class Context:
+    """One gs_ctx: parameters, LUTs, device scratch and a stream on one GPU."""
+
+    def __init__(self, params, device=0):
+        self._L = load()
+        h = C.c_void_p()
+        rc = self._L.gs_create(C.byref(params), device, C.byref(h))
+        if rc != GS_OK:
+            raise GsError(rc, "gs_create failed (%s)" % ("no usable CUDA device" if rc == GS_ECUDA else "invalid parameters"))
+        self._h = h
+        self.params = self.get_params()
+        self.derived = self.get_derived()
+        self.shape = (self.derived.n_rows, self.derived.n_cols)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.gs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != GS_OK:
+            raise GsError(rc, self._L.gs_last_error(self._h).decode())
+
+    # ---- configuration
+    def set_params(self, params):
+        self._ck(self._L.gs_set_params(self._h, C.byref(params)))
+        self.params = self.get_params()
+        self.derived = self.get_derived()
+        self.shape = (self.derived.n_rows, self.derived.n_cols)
+
+    def get_params(self):
+        p = GsParams()
+        self._ck(self._L.gs_get_params(self._h, C.byref(p)))
+        return p
+
+    def get_derived(self):
+        d = GsDerived()
+        self._ck(self._L.gs_get_derived(self._h, C.byref(d)))
+        return d
+
+    def set_stream(self, cuda_stream_handle):
+        self._ck(self._L.gs_set_stream(self._h, C.c_void_p(cuda_stream_handle)))
+
+    def set_chunk_frames(self, n):
+        self._ck(self._L.gs_set_chunk_frames(self._h, n))
+
+    def set_option(self, opt, value):
+        self._ck(self._L.gs_set_option(self._h, opt, int(value)))
+
+    def stats(self):
+        s = GsStats()
+        self._ck(self._L.gs_get_stats(self._h, C.byref(s)))
+        return s
+
+    def reset_stats(self):
+        self._ck(self._L.gs_reset_stats(self._h))
+
+    def synchronize(self):
+        self._ck(self._L.gs_synchronize(self._h))
+
+    # ---- stage API (host numpy in / out)
+    def project(self, points):
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        out = np.empty(self.shape, np.uint16)
+        self._ck(self._L.gs_project(self._h, _ptr(pts), pts.shape[0], pts.strides[0] if pts.shape[0] else 16, _ptr(out)))
+        return out
+
+    def angle_image(self, range_image):
+        out = np.empty(self.shape, np.uint16)
+        self._ck(self._L.gs_angle_image(self._h, _ptr(_u16(range_image, self.shape)), _ptr(out)))
+        return out
+
+    def smooth(self, angle_image, window):
+        out = np.empty(self.shape, np.uint16)
+        self._ck(self._L.gs_smooth(self._h, _ptr(_u16(angle_image, self.shape)), window, _ptr(out)))
+        return out
+
+    def repair_gaps(self, range_image, step=5, depth_threshold=1.0):
+        out = np.empty(self.shape, np.uint16)
+        self._ck(self._L.gs_repair_gaps(self._h, _ptr(_u16(range_image, self.shape)), step, depth_threshold, _ptr(out)))
+        return out
+
+    def erase_ground(self, range_image, angle_image, ground_thr=None, start_thr=None, kernel_size=None):
+        p = self.params
+        res = np.empty(self.shape, np.uint16)
+        lab = np.empty(self.shape, np.uint8)
+        self._ck(self._L.gs_erase_ground(self._h, _ptr(_u16(range_image, self.shape)), _ptr(_u16(angle_image, self.shape)),
+                                         p.ground_angle_threshold if ground_thr is None else ground_thr,
+                                         p.start_angle_threshold if start_thr is None else start_thr,
+                                         p.window_size if kernel_size is None else kernel_size, _ptr(res), _ptr(lab)))
+        return res, lab
+
+    def label_one_component(self, label, row, col, thr, range_image, angle_image, label_image):
+        lab = np.ascontiguousarray(label_image, dtype=np.uint8).copy()
+        self._ck(self._L.gs_label_one_component(self._h, label, row, col, thr, _ptr(_u16(range_image, self.shape)),
+                                                _ptr(_u16(angle_image, self.shape)), _ptr(lab)))
+        return lab
+
+    def label_components(self, image, angle_image, beta):
+        out = np.empty(self.shape, np.int32)
+        n = C.c_int32(0)
+        self._ck(self._L.gs_label_components(self._h, _ptr(_u16(image, self.shape)), _ptr(_u16(angle_image, self.shape)), beta,
+                                             _ptr(out), C.byref(n)))
+        return out, n.value
+
+    def backproject(self, image):
+        H, W = self.shape
+        xyz = np.empty((H * W, 4), np.float32)
+        n = C.c_uint32(0)
+        self._ck(self._L.gs_backproject(self._h, _ptr(_u16(image, self.shape)), _ptr(xyz), C.byref(n)))
+        return xyz[: n.value].copy()
+
+    def process_frame(self, points):
+        """-> dict(range, angle, no_ground, xyz)"""
+        H, W = self.shape
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        rng, ang, res = (np.empty((H, W), np.uint16) for _ in range(3))
+        xyz = np.empty((H * W, 4), np.float32)
+        n = C.c_uint32(0)
+        self._ck(self._L.gs_process_frame(self._h, _ptr(pts), pts.shape[0], pts.strides[0] if pts.shape[0] else 16, _ptr(rng),
+                                          _ptr(ang), _ptr(res), _ptr(xyz), C.byref(n)))
+        return dict(range=rng, angle=ang, no_ground=res, xyz=xyz[: n.value].copy())
+
+    # ---- batch API
+    def process_batch_device(self, d_points, h_offsets, n_frames, d_range=0, d_angle=0, d_no_ground=0, d_xyz4=0, d_counts=0):
+        """Raw device pointers (ints).  Asynchronous on the context's stream."""
+        offs = np.ascontiguousarray(h_offsets, dtype=np.int64)
+        self._ck(self._L.gs_process_batch_device(self._h, C.c_void_p(d_points), _ptr(offs), n_frames, C.c_void_p(d_range or None),
+                                                 C.c_void_p(d_angle or None), C.c_void_p(d_no_ground or None),
+                                                 C.c_void_p(d_xyz4 or None), C.c_void_p(d_counts or None)))
+
+    def process_batch_host(self, h_points, h_offsets, no_ground_out=None, xyz4_out=None, out_offsets=None):
+        """numpy (ideally pinned) buffers; returns (no_ground_out, xyz4_out, out_offsets)."""
+        offs = np.ascontiguousarray(h_offsets, dtype=np.int64)
+        n_frames = len(offs) - 1
+        if out_offsets is None:
+            out_offsets = np.zeros(n_frames + 1, np.int64)
+        cap = 0 if xyz4_out is None else xyz4_out.shape[0]
+        self._ck(self._L.gs_process_batch_host(self._h, _ptr(h_points), _ptr(offs), n_frames, _ptr(no_ground_out), _ptr(xyz4_out), cap,
+                                               _ptr(out_offsets)))
+        return no_ground_out, xyz4_out, out_offsets

@@ -1,0 +1,909 @@
+// gs_capi.cu — context and C ABI (include/gs_b200.h) over the kernels of gs_kernels.cu / gs_fused.cu.
+//
+// Nothing here computes on the CPU except parameter derivation and the per-row / per-column lookup
+// tables (the reference's constructor work, src/alfa_gs.cpp:16-63).  There is no CPU fallback: every
+// entry point that produces image or cloud data launches CUDA kernels and fails with GS_ECUDA when no
+// device is usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "gs_internal.h"
+
+using namespace gs;
+
+// ------------------------------------------------------------------------------------------------
+// parameter derivation (host; reference constructor arithmetic)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// Label::LabelOneComponent compares an integer-valued double with `float thr * 100` evaluated in float
+// (Labeler/label.cpp:99, label.h:41):  diff < T  <=>  diff <= ceil(T) - 1.
+int edge_cutoff(double thr) {
+    const float t = static_cast<float>(thr);
+    const float T = t * 100;
+    return static_cast<int>(std::ceil(static_cast<double>(T))) - 1;
+}
+// EraseBFS seed gate (alfa_gs.cpp:733): rejected when angle > start * 100 (double).
+int seed_cutoff(double start) { return static_cast<int>(std::floor(start * 100)); }
+
+// Effective structuring element of cv::dilate(label, dilated, GetUniformKernel(ks, CV_8U)) (alfa_gs.cpp:630-639,
+// 747-750).  GetUniformKernel stores two `float 1.0f` (bytes 00 00 80 3F) at byte offsets 0 and ks-1 of a ks-byte
+// column and halves it with u8 rounding, so kernel byte i is non-zero exactly where the overlaid float bytes are:
+// offsets 2,3 (from the first store; the second store's non-zero bytes fall at ks+1, ks+2, outside the kernel).
+// For ks == 3 the second store (offset 2) overwrites byte 2 with 0x00 and byte 3 is outside: the kernel is all
+// zero and OpenCV dilates with the single tap at kernel coordinate (0,0).  Pinned against OpenCV 4.13 in tests/golden.
+int dilation_taps(int kernel_size_arg, int off[2]) {
+    const int ks = std::max(kernel_size_arg - 2, 3);
+    std::vector<unsigned char> buf(static_cast<size_t>(ks) + 3, 0);
+    const float one = 1.0f;
+    std::memcpy(&buf[0], &one, 4);
+    std::memcpy(&buf[ks - 1], &one, 4);
+    int n = 0;
+    for (int i = 0; i < ks; ++i) {
+        const int halved = static_cast<int>(std::nearbyint(buf[i] / 2.0));
+        if (halved != 0 && n < 2) off[n++] = i - ks / 2;
+    }
+    if (n == 0) off[n++] = -(ks / 2);
+    if (n == 1) off[1] = off[0];
+    return n;
+}
+
+bool sg_taps(int ws, SgTaps* out) {
+    static const float k5[] = {-3, 12, 17, 12, -3};
+    static const float k7[] = {-2, 3, 6, 7, 6, 3, -2};
+    static const float k9[] = {-21, 14, 39, 54, 59, 54, 39, 14, -21};
+    static const float k11[] = {-36, 9, 44, 69, 84, 89, 84, 69, 44, 9, -36};
+    const float* src;
+    float norm;
+    switch (ws) {  // alfa_gs.cpp:653-699
+        case 5: src = k5; norm = 35.0f; break;
+        case 7: src = k7; norm = 21.0f; break;
+        case 9: src = k9; norm = 231.0f; break;
+        case 11: src = k11; norm = 429.0f; break;
+        default: return false;  // alfa_gs.cpp:645-649: std::logic_error("bad window size")
+    }
+    // `kernel /= norm` on a CV_32F Mat = convertTo(alpha = 1/norm): tap = numerator * (float)(1.0 / norm)
+    const float alpha = static_cast<float>(1.0 / static_cast<double>(norm));
+    for (int i = 0; i < ws; ++i) out->t[i] = src[i] * alpha;
+    out->ws = ws;
+    return true;
+}
+
+int derive(const gs_params* p, gs_derived* d) {
+    if (!p || !d) return GS_EINVAL;
+    if (p->n_beams < 2 || p->n_beams > 1024 || p->rpm <= 0 || p->sample_freq <= 0) return GS_EINVAL;
+    const long long w = static_cast<long long>(p->sample_freq) * 60 / p->rpm;  // alfa_gs.cpp:48 (int division)
+    if (w < 1 || w > 32767) return GS_EINVAL;                                   // Label::WrapCols takes int16_t (label.h:40)
+    if (!(p->max_angle > p->min_angle) || !(p->max_range > p->min_range)) return GS_EINVAL;
+    if (p->window_size < 3 || std::max(p->window_size - 2, 3) % 2 == 0) return GS_EINVAL;  // alfa_gs.cpp:631-633
+    if (p->smoothing == GS_SMOOTH_SG) {
+        SgTaps t;
+        if (!sg_taps(p->window_size, &t)) return GS_EINVAL;
+    }
+    if (p->variant != GS_VARIANT_ALFA_GS && p->variant != GS_VARIANT_CLOUD2RANGE) return GS_EINVAL;
+    d->n_rows = p->n_beams;
+    d->n_cols = static_cast<int>(w);
+    d->d_azimuth = 360.0 / d->n_cols / 180 * M_PI;                       // alfa_gs.cpp:49, utils.h:54
+    d->d_altitude = (p->max_angle - p->min_angle) / (p->n_beams - 1);    // alfa_gs.cpp:50
+    d->k_ground = edge_cutoff(p->ground_angle_threshold);
+    d->s_start = seed_cutoff(p->start_angle_threshold);
+    d->n_dilate = dilation_taps(p->window_size, d->dilate_off);
+    return GS_OK;
+}
+
+gs_params make_params(int n_beams, int sample_freq, double min_angle, double max_angle, double min_range, double max_range,
+                      double ground, int window, int variant, int smoothing) {
+    gs_params p;
+    std::memset(&p, 0, sizeof(p));
+    p.n_beams = n_beams;
+    p.rpm = 600;
+    p.sample_freq = sample_freq;
+    p.min_angle = min_angle;
+    p.max_angle = max_angle;
+    p.min_range = min_range;
+    p.max_range = max_range;
+    p.ground_angle_threshold = ground;
+    p.start_angle_threshold = 0.523598;
+    p.window_size = window;
+    p.erase_ground = 1;
+    p.variant = variant;
+    p.pixel_policy = GS_PIXEL_LAST;
+    p.col_policy = GS_COL_FLAT_ALIAS;
+    p.smoothing = smoothing;
+    return p;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct gs_ctx {
+    int device = 0;
+    gs_params params;
+    gs_derived der;
+    KParams kp;
+    Luts lut;
+    SgTaps sg;
+    void* lut_block = nullptr;  // one device allocation behind all LUTs
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    Scratch sc;
+    int chunk_frames = 0;  // 0 = automatic
+    Counters* d_cnt = nullptr;
+    Counters* h_cnt = nullptr;  // pinned
+    unsigned long long n_launches = 0;
+    bool collect_stats = false;
+    // single-frame staging (stage API)
+    void* d_points = nullptr;
+    size_t d_points_cap = 0;
+    uint16_t *d_a = nullptr, *d_b = nullptr, *d_c = nullptr;  // P u16 each
+    uint8_t* d_lab = nullptr;                                   // P u8
+    int32_t* d_lab32 = nullptr;                                 // P i32
+    float* d_xyz = nullptr;                                     // P float4
+    // batch staging (host batch API): two slots
+    float* d_in[2] = {nullptr, nullptr};
+    size_t d_in_cap[2] = {0, 0};
+    uint16_t* d_res[2] = {nullptr, nullptr};
+    float* d_cloud[2] = {nullptr, nullptr};
+    unsigned* d_counts[2] = {nullptr, nullptr};
+    unsigned* h_counts[2] = {nullptr, nullptr};  // pinned
+    int slot_frames = 0;
+    long long* d_offsets = nullptr;
+    size_t d_offsets_cap = 0;
+    FusedState fused;
+    std::string err;
+};
+
+namespace {
+
+int fail(gs_ctx* c, int code, const char* fmt, ...) {
+    if (c) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        c->err = buf;
+    }
+    return code;
+}
+
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        const cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? GS_ENOMEM : GS_ECUDA, \
+                                           "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+Launch launch_of(gs_ctx* c) { return Launch{c->stream, &c->n_launches}; }
+
+void free_scratch(Scratch& s) {
+    cudaFree(s.keys); cudaFree(s.range); cudaFree(s.angle); cudaFree(s.angle2); cudaFree(s.parent); cudaFree(s.label);
+    cudaFree(s.seed_row); cudaFree(s.eseed); cudaFree(s.rowcount); cudaFree(s.res); cudaFree(s.counts);
+    s = Scratch();
+}
+
+int ensure_scratch(gs_ctx* ctx, int frames) {
+    Scratch& s = ctx->sc;
+    const size_t P = ctx->kp.P;
+    if (s.frames >= frames && s.P == P && s.W == ctx->kp.W && s.H == ctx->kp.H) return GS_OK;
+    free_scratch(s);
+    const size_t n = static_cast<size_t>(frames) * P;
+    CU(cudaMalloc(&s.keys, n * 8));
+    CU(cudaMemsetAsync(s.keys, 0, n * 8, ctx->stream));
+    CU(cudaMalloc(&s.range, n * 2));
+    CU(cudaMalloc(&s.angle, n * 2));
+    CU(cudaMalloc(&s.angle2, n * 2));
+    CU(cudaMalloc(&s.parent, (n + 4) * 4));
+    CU(cudaMalloc(&s.label, n));
+    CU(cudaMalloc(&s.res, n * 2));
+    CU(cudaMalloc(&s.seed_row, static_cast<size_t>(frames) * ctx->kp.W * 4));
+    CU(cudaMalloc(&s.eseed, static_cast<size_t>(frames) * ctx->kp.W));
+    CU(cudaMalloc(&s.rowcount, static_cast<size_t>(frames) * ctx->kp.H * 4));
+    CU(cudaMalloc(&s.counts, static_cast<size_t>(frames) * 4));
+    s.frames = frames;
+    s.P = P;
+    s.W = ctx->kp.W;
+    s.H = ctx->kp.H;
+    return GS_OK;
+}
+
+void free_stage(gs_ctx* c) {
+    cudaFree(c->d_points); cudaFree(c->d_a); cudaFree(c->d_b); cudaFree(c->d_c); cudaFree(c->d_lab); cudaFree(c->d_lab32);
+    cudaFree(c->d_xyz);
+    c->d_points = nullptr; c->d_points_cap = 0;
+    c->d_a = c->d_b = c->d_c = nullptr; c->d_lab = nullptr; c->d_lab32 = nullptr; c->d_xyz = nullptr;
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(c->d_in[k]); cudaFree(c->d_res[k]); cudaFree(c->d_cloud[k]); cudaFree(c->d_counts[k]);
+        if (c->h_counts[k]) cudaFreeHost(c->h_counts[k]);
+        c->d_in[k] = nullptr; c->d_in_cap[k] = 0; c->d_res[k] = nullptr; c->d_cloud[k] = nullptr; c->d_counts[k] = nullptr;
+        c->h_counts[k] = nullptr;
+    }
+    c->slot_frames = 0;
+}
+
+int ensure_stage(gs_ctx* ctx) {
+    if (ctx->d_a) return GS_OK;
+    const size_t P = ctx->kp.P;
+    CU(cudaMalloc(&ctx->d_a, P * 2));
+    CU(cudaMalloc(&ctx->d_b, P * 2));
+    CU(cudaMalloc(&ctx->d_c, P * 2));
+    CU(cudaMalloc(&ctx->d_lab, P));
+    CU(cudaMalloc(&ctx->d_lab32, P * 4));
+    CU(cudaMalloc(&ctx->d_xyz, P * 16));
+    return GS_OK;
+}
+
+int ensure_points(gs_ctx* ctx, size_t bytes) {
+    if (ctx->d_points_cap >= bytes) return GS_OK;
+    cudaFree(ctx->d_points);
+    ctx->d_points = nullptr;
+    ctx->d_points_cap = 0;
+    const size_t cap = std::max<size_t>(bytes + bytes / 4, 1 << 20);
+    CU(cudaMalloc(&ctx->d_points, cap));
+    ctx->d_points_cap = cap;
+    return GS_OK;
+}
+
+int ensure_offsets(gs_ctx* ctx, size_t n) {
+    if (ctx->d_offsets_cap >= n) return GS_OK;
+    cudaFree(ctx->d_offsets);
+    ctx->d_offsets = nullptr;
+    CU(cudaMalloc(&ctx->d_offsets, n * sizeof(long long)));
+    ctx->d_offsets_cap = n;
+    return GS_OK;
+}
+
+// Parameters -> kernel constants and device lookup tables.
+int configure(gs_ctx* ctx, const gs_params* p) {
+    gs_derived d;
+    const int rc = derive(p, &d);
+    if (rc) return fail(ctx, rc, "invalid parameters (beams %d, rpm %d, sample_freq %d, window %d)", p->n_beams, p->rpm,
+                        p->sample_freq, p->window_size);
+    const bool shape_changed = !ctx->lut_block || d.n_rows != ctx->kp.H || d.n_cols != ctx->kp.W;
+    ctx->params = *p;
+    ctx->der = d;
+    KParams& k = ctx->kp;
+    k.H = d.n_rows;
+    k.W = d.n_cols;
+    k.P = k.H * k.W;
+    k.variant = p->variant;
+    k.pixel_policy = p->pixel_policy;
+    k.col_policy = p->col_policy;
+    k.min_range = p->min_range;
+    k.max_range = p->max_range;
+    k.span = p->max_range - p->min_range;
+    k.min_angle = p->min_angle;
+    k.max_angle = p->max_angle;
+    k.ang_span = p->max_angle - p->min_angle;
+    k.d_alt = d.d_altitude;
+    k.d_az = d.d_azimuth;
+    k.half_d_alt = d.d_altitude / 2;  // alfa_gs.cpp:249
+    k.half_d_az = d.d_azimuth / 2;    // alfa_gs.cpp:250
+    k.k_ground = d.k_ground;
+    k.s_start = d.s_start;
+    k.n_dil = d.n_dilate;
+    k.dil0 = d.dilate_off[0];
+    k.dil1 = d.dilate_off[1];
+    k.erase_ground = (p->variant == GS_VARIANT_CLOUD2RANGE) ? 1 : (p->erase_ground ? 1 : 0);  // EraseGroundBFS has no switch
+    ctx->sg.ws = 0;
+    if (p->smoothing == GS_SMOOTH_SG) sg_taps(p->window_size, &ctx->sg);
+
+    if (shape_changed) {
+        free_scratch(ctx->sc);
+        free_stage(ctx);
+        fused_release(ctx->fused);
+        cudaFree(ctx->lut_block);
+        ctx->lut_block = nullptr;
+    }
+    // LUT block: [H] sin_y, [H] cos_y (float) | [H] cos_alt, [H] sin_alt, [W] cos_az, [W] sin_az (double)
+    const int H = k.H, W = k.W;
+    const size_t f_bytes = ((2 * static_cast<size_t>(H) * sizeof(float)) + 15) & ~static_cast<size_t>(15);
+    const size_t d_count = 2 * static_cast<size_t>(H) + 2 * static_cast<size_t>(W);
+    const size_t total = f_bytes + d_count * sizeof(double);
+    std::vector<unsigned char> host(total);
+    float* hf = reinterpret_cast<float*>(host.data());
+    double* hd = reinterpret_cast<double*>(host.data() + f_bytes);
+    const float vertical_amplitude = static_cast<float>(p->max_angle - p->min_angle);  // alfa_gs.cpp:344
+    for (int r = 0; r < H; ++r) {
+        const float angle_y = static_cast<float>(r * d.d_altitude - vertical_amplitude / 2);  // alfa_gs.cpp:357
+        hf[r] = sinf(angle_y);      // :366
+        hf[H + r] = cosf(angle_y);  // :367
+        const double altitude = (H - r) * d.d_altitude + p->min_angle;  // alfa_gs.cpp:1050 / range2cloud_node.cpp:81
+        hd[r] = std::cos(altitude);
+        hd[H + r] = std::sin(altitude);
+    }
+    for (int c = 0; c < W; ++c) {
+        const double azimuth = c * d.d_azimuth;  // alfa_gs.cpp:1052
+        hd[2 * H + c] = std::cos(azimuth);
+        hd[2 * H + W + c] = std::sin(azimuth);
+    }
+    if (!ctx->lut_block) CU(cudaMalloc(&ctx->lut_block, total));
+    CU(cudaMemcpyAsync(ctx->lut_block, host.data(), total, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    unsigned char* base = static_cast<unsigned char*>(ctx->lut_block);
+    ctx->lut.sin_y = reinterpret_cast<const float*>(base);
+    ctx->lut.cos_y = reinterpret_cast<const float*>(base) + H;
+    const double* dd = reinterpret_cast<const double*>(base + f_bytes);
+    ctx->lut.cos_alt = dd;
+    ctx->lut.sin_alt = dd + H;
+    ctx->lut.cos_az = dd + 2 * H;
+    ctx->lut.sin_az = dd + 2 * H + W;
+    const int frc = fused_configure(ctx->fused, k, ctx->lut, ctx->sg, p->smoothing == GS_SMOOTH_SG, p->repair_gaps != 0, ctx->device);
+    if (frc) return fail(ctx, GS_ECUDA, "fused kernel configuration failed: %s", cudaGetErrorString(static_cast<cudaError_t>(frc)));
+    return GS_OK;
+}
+
+int auto_chunk(const gs_ctx* c) {
+    if (c->chunk_frames > 0) return c->chunk_frames;
+    // staged path: keep the ~19 B/pixel of wave scratch inside the 126 MB L2
+    const size_t per_frame = static_cast<size_t>(c->kp.P) * 19;
+    const int n = static_cast<int>((96ull << 20) / per_frame);
+    return std::max(1, std::min(n, 256));
+}
+
+int reset_counters(gs_ctx* ctx) {
+    CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(Counters), ctx->stream));
+    return GS_OK;
+}
+
+int fetch_counters(gs_ctx* ctx) {
+    CU(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GS_OK;
+}
+
+// ---- the staged pipeline on a wave of frames resident on the device -----------------------------
+// range/angle/res may point at caller buffers (frames slabs); NULL -> context scratch.
+int run_wave_staged(gs_ctx* ctx, const void* d_points, size_t stride, const long long* d_offsets, int frames, long long max_points,
+                    uint16_t* range_out, uint16_t* angle_out, uint16_t* res_out, float* xyz_out, unsigned* counts_out) {
+    const Launch L = launch_of(ctx);
+    const KParams& kp = ctx->kp;
+    Scratch& s = ctx->sc;
+    uint16_t* range = range_out ? range_out : s.range;
+    uint16_t* angle = angle_out ? angle_out : s.angle;
+    uint16_t* res = res_out ? res_out : s.res;
+    launch_project(L, kp, d_points, stride, d_offsets, frames, max_points, s.keys, ctx->d_cnt, ctx->collect_stats);
+    launch_finalize(L, kp, frames, s.keys, range);
+    const uint16_t* angle_src = range;
+    if (ctx->params.repair_gaps) {  // cloud2range_node.cpp:468: RepairGaps(range, 5, 1.0f) feeds the angle image only
+        launch_repair(L, kp, frames, range, s.angle2, 5, 1.0f);
+        angle_src = s.angle2;
+    }
+    if (ctx->params.smoothing == GS_SMOOTH_SG) {  // cloud2range_node.cpp:470
+        // raw angles go to scratch; the smoothed image is what the ground search (and the caller) sees.  angle2 may hold
+        // the repaired range image: k_angle has consumed it before k_sg overwrites it (same stream).
+        launch_angle(L, kp, ctx->lut, frames, angle_src, s.angle, ctx->d_cnt, ctx->collect_stats);
+        angle = angle_out ? angle_out : s.angle2;
+        launch_sg(L, kp, ctx->sg, frames, s.angle, angle);
+    } else {
+        launch_angle(L, kp, ctx->lut, frames, angle_src, angle, ctx->d_cnt, ctx->collect_stats);
+    }
+    launch_ccl(L, kp, frames, range, angle, nullptr, kp.k_ground, s.parent);
+    launch_ground(L, kp, frames, range, angle, s.parent, s.seed_row, s.eseed, s.label);
+    launch_erase(L, kp, frames, range, s.label, res, s.rowcount);
+    if (xyz_out)
+        launch_backproject(L, kp, ctx->lut, frames, res, s.rowcount, xyz_out, counts_out ? counts_out : s.counts,
+                           ctx->params.variant == GS_VARIANT_CLOUD2RANGE);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, GS_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    return GS_OK;
+}
+
+// Picks the fused single-kernel pipeline when it supports the configuration, else the staged kernels.
+int run_wave(gs_ctx* ctx, const void* d_points, size_t stride, const long long* d_offsets, int frames, long long max_points,
+             uint16_t* range_out, uint16_t* angle_out, uint16_t* res_out, float* xyz_out, unsigned* counts_out) {
+    if (stride == 16 && (reinterpret_cast<uintptr_t>(d_points) & 15) == 0 && fused_supported(ctx->fused)) {
+        const Launch L = launch_of(ctx);
+        const int rc = fused_run(ctx->fused, L, static_cast<const float4*>(d_points), d_offsets, frames, range_out, angle_out, res_out,
+                                 reinterpret_cast<float4*>(xyz_out), counts_out, ctx->d_cnt, ctx->collect_stats);
+        if (rc) return fail(ctx, GS_ECUDA, "fused kernel launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(rc)));
+        return GS_OK;
+    }
+    const int rc = ensure_scratch(ctx, std::max(frames, ctx->sc.frames));
+    if (rc) return rc;
+    return run_wave_staged(ctx, d_points, stride, d_offsets, frames, max_points, range_out, angle_out, res_out, xyz_out, counts_out);
+}
+
+bool bad_image_args(const gs_ctx* c, const void* a, const void* b) { return !c || !a || !b; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI (the only symbols the library exports: everything else is built with -fvisibility=hidden)
+// ------------------------------------------------------------------------------------------------
+#pragma GCC visibility push(default)
+extern "C" {
+
+int gs_abi_version(void) { return GS_ABI_VERSION; }
+
+int gs_default_params(int preset, gs_params* out) {
+    if (!out) return GS_EINVAL;
+    switch (preset) {
+        case GS_PRESET_ALFA_GS_DEFAULT:  // alfa_gs.cpp:16-38
+            *out = make_params(64, 18000, -0.453785, 0.09599, 0.5, 100.0, 0.115, 11, GS_VARIANT_ALFA_GS, GS_SMOOTH_NONE);
+            return GS_OK;
+        case GS_PRESET_VLP16:  // cloud2range_node.cpp:66-86
+            *out = make_params(16, 18000, -0.2617993878, 0.2617993878, 0.5, 100.0, 0.087266, 5, GS_VARIANT_ALFA_GS, GS_SMOOTH_NONE);
+            return GS_OK;
+        case GS_PRESET_HDL64E_2048:  // alfa_gs.cpp:16-38 with sample_freq 20480
+            *out = make_params(64, 20480, -0.453785, 0.09599, 0.5, 100.0, 0.115, 11, GS_VARIANT_ALFA_GS, GS_SMOOTH_NONE);
+            return GS_OK;
+        case GS_PRESET_OS1_128:  // cloud2range_node.cpp:281-300, beams doubled, sample_freq 20480
+            *out = make_params(128, 20480, -0.392699, 0.392699, 0.3, 120.0, 0.09, 7, GS_VARIANT_ALFA_GS, GS_SMOOTH_NONE);
+            return GS_OK;
+        case GS_PRESET_CLOUD2RANGE_DEFAULT:  // cloud2range_node.cpp:281-300 as shipped
+            *out = make_params(64, 20000, -0.392699, 0.392699, 0.3, 120.0, 0.09, 7, GS_VARIANT_CLOUD2RANGE, GS_SMOOTH_SG);
+            return GS_OK;
+        case GS_PRESET_HDL32:  // cloud2range_node.cpp:122-135
+            *out = make_params(32, 18000, -0.535293, 0.186227, 0.5, 100.0, 0.087266, 5, GS_VARIANT_ALFA_GS, GS_SMOOTH_NONE);
+            return GS_OK;
+        default: return GS_EINVAL;
+    }
+}
+
+int gs_derive(const gs_params* p, gs_derived* out) { return derive(p, out); }
+
+int gs_create(const gs_params* p, int device, gs_ctx** out) {
+    if (!p || !out) return GS_EINVAL;
+    *out = nullptr;
+    gs_derived d;
+    if (derive(p, &d) != GS_OK) return GS_EINVAL;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) return GS_ECUDA;  // no CPU fallback
+    if (cudaSetDevice(device) != cudaSuccess) return GS_ECUDA;
+    gs_ctx* ctx = new gs_ctx();
+    ctx->device = device;
+    std::memset(&ctx->kp, 0, sizeof(ctx->kp));
+    bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) == cudaSuccess;
+    for (int k = 0; ok && k < 2; ++k)
+        ok = cudaEventCreateWithFlags(&ctx->ev_in[k], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_out[k], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_cnt, sizeof(Counters)) == cudaSuccess &&
+         cudaMallocHost(&ctx->h_cnt, sizeof(Counters)) == cudaSuccess;
+    if (!ok) {
+        gs_destroy(ctx);
+        return GS_ECUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    std::memset(ctx->h_cnt, 0, sizeof(Counters));
+    cudaMemsetAsync(ctx->d_cnt, 0, sizeof(Counters), ctx->stream);
+    const int rc = configure(ctx, p);
+    if (rc) {
+        gs_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return GS_OK;
+}
+
+void gs_destroy(gs_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    free_scratch(ctx->sc);
+    free_stage(ctx);
+    fused_release(ctx->fused);
+    cudaFree(ctx->lut_block);
+    cudaFree(ctx->d_cnt);
+    cudaFree(ctx->d_offsets);
+    if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
+    for (int k = 0; k < 2; ++k) {
+        if (ctx->ev_in[k]) cudaEventDestroy(ctx->ev_in[k]);
+        if (ctx->ev_done[k]) cudaEventDestroy(ctx->ev_done[k]);
+        if (ctx->ev_out[k]) cudaEventDestroy(ctx->ev_out[k]);
+    }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    delete ctx;
+}
+
+int gs_set_params(gs_ctx* ctx, const gs_params* p) {
+    if (!ctx || !p) return GS_EINVAL;
+    cudaSetDevice(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));
+    return configure(ctx, p);
+}
+
+int gs_get_params(const gs_ctx* ctx, gs_params* out) {
+    if (!ctx || !out) return GS_EINVAL;
+    *out = ctx->params;
+    return GS_OK;
+}
+
+int gs_get_derived(const gs_ctx* ctx, gs_derived* out) {
+    if (!ctx || !out) return GS_EINVAL;
+    *out = ctx->der;
+    return GS_OK;
+}
+
+int gs_set_stream(gs_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return GS_EINVAL;
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return GS_OK;
+}
+
+int gs_set_chunk_frames(gs_ctx* ctx, int frames) {
+    if (!ctx || frames < 0 || frames > 4096) return GS_EINVAL;
+    ctx->chunk_frames = frames;
+    return GS_OK;
+}
+
+int gs_set_option(gs_ctx* ctx, int option, int value) {
+    if (!ctx) return GS_EINVAL;
+    switch (option) {
+        case GS_OPT_COLLECT_STATS: ctx->collect_stats = value != 0; return GS_OK;
+        case GS_OPT_FORCE_STAGED: ctx->fused.disabled = value != 0; return GS_OK;
+        default: return fail(ctx, GS_EINVAL, "unknown option %d", option);
+    }
+}
+
+int gs_get_stats(gs_ctx* ctx, gs_stats* out) {
+    if (!ctx || !out) return GS_EINVAL;
+    cudaSetDevice(ctx->device);
+    const int rc = fetch_counters(ctx);
+    if (rc) return rc;
+    out->kernel_launches = ctx->n_launches;
+    out->near_edge_project = ctx->h_cnt->near_edge_project;
+    out->near_edge_angle = ctx->h_cnt->near_edge_angle;
+    out->dropped_points = ctx->h_cnt->dropped;
+    out->slow_path_points = ctx->h_cnt->slow_path;
+    return GS_OK;
+}
+
+int gs_reset_stats(gs_ctx* ctx) {
+    if (!ctx) return GS_EINVAL;
+    cudaSetDevice(ctx->device);
+    return reset_counters(ctx);
+}
+
+const char* gs_last_error(const gs_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int gs_synchronize(gs_ctx* ctx) {
+    if (!ctx) return GS_EINVAL;
+    cudaSetDevice(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GS_OK;
+}
+
+// ---- stage API -------------------------------------------------------------------------------
+int gs_project(gs_ctx* ctx, const void* points, size_t n_points, size_t stride_bytes, uint16_t* range_out) {
+    if (!ctx || !range_out || (n_points && !points) || stride_bytes < 12 || (stride_bytes & 3)) return fail(ctx, GS_EINVAL, "gs_project: bad arguments");
+    cudaSetDevice(ctx->device);
+    int rc;
+    if ((rc = ensure_stage(ctx)) || (rc = ensure_scratch(ctx, 1)) || (rc = ensure_points(ctx, n_points * stride_bytes)) ||
+        (rc = ensure_offsets(ctx, 2)))
+        return rc;
+    const long long offs[2] = {0, static_cast<long long>(n_points)};
+    CU(cudaMemcpyAsync(ctx->d_offsets, offs, sizeof(offs), cudaMemcpyHostToDevice, ctx->stream));
+    if (n_points) CU(cudaMemcpyAsync(ctx->d_points, points, n_points * stride_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const Launch L = launch_of(ctx);
+    launch_project(L, ctx->kp, ctx->d_points, stride_bytes, ctx->d_offsets, 1, static_cast<long long>(n_points), ctx->sc.keys, ctx->d_cnt,
+                   ctx->collect_stats);
+    launch_finalize(L, ctx->kp, 1, ctx->sc.keys, ctx->d_a);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(range_out, ctx->d_a, static_cast<size_t>(ctx->kp.P) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GS_OK;
+}
+
+int gs_angle_image(gs_ctx* ctx, const uint16_t* range, uint16_t* angle_out) {
+    if (bad_image_args(ctx, range, angle_out)) return fail(ctx, GS_EINVAL, "gs_angle_image: bad arguments");
+    cudaSetDevice(ctx->device);
+    int rc;
+    if ((rc = ensure_stage(ctx))) return rc;
+    const size_t bytes = static_cast<size_t>(ctx->kp.P) * 2;
+    CU(cudaMemcpyAsync(ctx->d_a, range, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    launch_angle(launch_of(ctx), ctx->kp, ctx->lut, 1, ctx->d_a, ctx->d_b, ctx->d_cnt, ctx->collect_stats);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(angle_out, ctx->d_b, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GS_OK;
+}
+
+int gs_smooth(gs_ctx* ctx, const uint16_t* angle, int window, uint16_t* smoothed_out) {
+    if (bad_image_args(ctx, angle, smoothed_out)) return fail(ctx, GS_EINVAL, "gs_smooth: bad arguments");
+    SgTaps taps;
+    if (window % 2 == 0 || !sg_taps(window, &taps)) return fail(ctx, GS_EINVAL, "bad window size %d", window);  // alfa_gs.cpp:642-649
+    cudaSetDevice(ctx->device);
+    int rc;
+    if ((rc = ensure_stage(ctx))) return rc;
+    const size_t bytes = static_cast<size_t>(ctx->kp.P) * 2;
+    CU(cudaMemcpyAsync(ctx->d_a, angle, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    launch_sg(launch_of(ctx), ctx->kp, taps, 1, ctx->d_a, ctx->d_b);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(smoothed_out, ctx->d_b, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GS_OK;
+}
+
+int gs_repair_gaps(gs_ctx* ctx, const uint16_t* range, int step, float depth_threshold, uint16_t* repaired_out) {
+    if (bad_image_args(ctx, range, repaired_out) || step < 1) return fail(ctx, GS_EINVAL, "gs_repair_gaps: bad arguments");
+    cudaSetDevice(ctx->device);
+    int rc;
+    if ((rc = ensure_stage(ctx))) return rc;
+    const size_t bytes = static_cast<size_t>(ctx->kp.P) * 2;
+    CU(cudaMemcpyAsync(ctx->d_a, range, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    launch_repair(launch_of(ctx), ctx->kp, 1, ctx->d_a, ctx->d_b, step, depth_threshold);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(repaired_out, ctx->d_b, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GS_OK;
+}
+
+int gs_erase_ground(gs_ctx* ctx, const uint16_t* range, const uint16_t* angle, double ground_angle_threshold,
+                    double start_angle_threshold, int kernel_size, uint16_t* res_out, uint8_t* labels_out) {
+    if (!ctx || !range || !angle || !res_out) return fail(ctx, GS_EINVAL, "gs_erase_ground: bad arguments");
+    if (kernel_size < 3 || std::max(kernel_size - 2, 3) % 2 == 0)
+        return fail(ctx, GS_EINVAL, "Window size must be odd (kernel_size %d)", kernel_size);  // alfa_gs.cpp:631-633
+    cudaSetDevice(ctx->device);
+    int rc;
+    if ((rc = ensure_stage(ctx)) || (rc = ensure_scratch(ctx, 1))) return rc;
+    KParams kp = ctx->kp;
+    kp.k_ground = edge_cutoff(ground_angle_threshold);
+    kp.s_start = seed_cutoff(start_angle_threshold);
+    int off[2];
+    kp.n_dil = dilation_taps(kernel_size, off);
+    kp.dil0 = off[0];
+    kp.dil1 = off[1];
+    const size_t bytes = static_cast<size_t>(kp.P) * 2;
+    CU(cudaMemcpyAsync(ctx->d_a, range, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_b, angle, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const Launch L = launch_of(ctx);
+    launch_ccl(L, kp, 1, ctx->d_a, ctx->d_b, nullptr, kp.k_ground, ctx->sc.parent);
+    launch_ground(L, kp, 1, ctx->d_a, ctx->d_b, ctx->sc.parent, ctx->sc.seed_row, ctx->sc.eseed, ctx->sc.label);
+    launch_erase(L, kp, 1, ctx->d_a, ctx->sc.label, ctx->d_c, ctx->sc.rowcount);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(res_out, ctx->d_c, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (labels_out) CU(cudaMemcpyAsync(labels_out, ctx->sc.label, static_cast<size_t>(kp.P), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GS_OK;
+}
+
+int gs_label_one_component(gs_ctx* ctx, int label, int row, int col, float angle_threshold, const uint16_t* range,
+                           const uint16_t* angle, uint8_t* label_image) {
+    if (!ctx || !range || !angle || !label_image) return fail(ctx, GS_EINVAL, "gs_label_one_component: bad arguments");
+    if (row < 0 || row >= ctx->kp.H || col < 0 || col >= ctx->kp.W) return fail(ctx, GS_EINVAL, "seed (%d,%d) outside the image", row, col);
+    if ((label & 0xff) == 0) return fail(ctx, GS_EINVAL, "label 0 never terminates in the reference (label.cpp:61-67)");
+    cudaSetDevice(ctx->device);
+    int rc;
+    if ((rc = ensure_stage(ctx)) || (rc = ensure_scratch(ctx, 1))) return rc;
+    const KParams& kp = ctx->kp;
+    const size_t bytes = static_cast<size_t>(kp.P) * 2;
+    const int k_edge = edge_cutoff(static_cast<double>(angle_threshold));
+    CU(cudaMemcpyAsync(ctx->d_a, range, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_b, angle, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_lab, label_image, static_cast<size_t>(kp.P), cudaMemcpyHostToDevice, ctx->stream));
+    const Launch L = launch_of(ctx);
+    launch_ccl(L, kp, 1, ctx->d_a, ctx->d_b, ctx->d_lab, k_edge, ctx->sc.parent);
+    launch_one_component(L, kp, ctx->d_a, ctx->d_b, k_edge, ctx->sc.parent, row, col, label & 0xff, ctx->d_lab);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(label_image, ctx->d_lab, static_cast<size_t>(kp.P), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GS_OK;
+}
+
+int gs_label_components(gs_ctx* ctx, const uint16_t* image, const uint16_t* angle, double beta, int32_t* labels_out,
+                        int32_t* n_components_out) {
+    if (!ctx || !image || !angle || !labels_out) return fail(ctx, GS_EINVAL, "gs_label_components: bad arguments");
+    cudaSetDevice(ctx->device);
+    int rc;
+    if ((rc = ensure_stage(ctx)) || (rc = ensure_scratch(ctx, 1))) return rc;
+    const KParams& kp = ctx->kp;
+    const size_t bytes = static_cast<size_t>(kp.P) * 2;
+    CU(cudaMemcpyAsync(ctx->d_a, image, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_b, angle, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(&ctx->d_cnt->components, 0, sizeof(unsigned long long), ctx->stream));
+    const Launch L = launch_of(ctx);
+    launch_ccl(L, kp, 1, ctx->d_a, ctx->d_b, nullptr, edge_cutoff(beta), ctx->sc.parent);
+    launch_components(L, kp, 1, ctx->d_a, ctx->sc.parent, ctx->d_lab32, ctx->d_cnt);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(labels_out, ctx->d_lab32, static_cast<size_t>(kp.P) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = fetch_counters(ctx))) return rc;
+    if (n_components_out) *n_components_out = static_cast<int32_t>(ctx->h_cnt->components);
+    return GS_OK;
+}
+
+int gs_backproject(gs_ctx* ctx, const uint16_t* image, float* xyz4_out, uint32_t* n_out) {
+    if (!ctx || !image || !xyz4_out || !n_out) return fail(ctx, GS_EINVAL, "gs_backproject: bad arguments");
+    cudaSetDevice(ctx->device);
+    int rc;
+    if ((rc = ensure_stage(ctx)) || (rc = ensure_scratch(ctx, 1))) return rc;
+    const KParams& kp = ctx->kp;
+    CU(cudaMemcpyAsync(ctx->d_a, image, static_cast<size_t>(kp.P) * 2, cudaMemcpyHostToDevice, ctx->stream));
+    const Launch L = launch_of(ctx);
+    launch_rowcount(L, kp, 1, ctx->d_a, ctx->sc.rowcount);
+    launch_backproject(L, kp, ctx->lut, 1, ctx->d_a, ctx->sc.rowcount, ctx->d_xyz, ctx->sc.counts,
+                       ctx->params.variant == GS_VARIANT_CLOUD2RANGE);
+    CU(cudaGetLastError());
+    unsigned n = 0;
+    CU(cudaMemcpyAsync(&n, ctx->sc.counts, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (n) CU(cudaMemcpyAsync(xyz4_out, ctx->d_xyz, static_cast<size_t>(n) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *n_out = n;
+    return GS_OK;
+}
+
+int gs_process_frame(gs_ctx* ctx, const void* points, size_t n_points, size_t stride_bytes, uint16_t* range_out,
+                     uint16_t* angle_out, uint16_t* no_ground_out, float* xyz4_out, uint32_t* n_out) {
+    if (!ctx || (n_points && !points) || stride_bytes < 12 || (stride_bytes & 3)) return fail(ctx, GS_EINVAL, "gs_process_frame: bad arguments");
+    cudaSetDevice(ctx->device);
+    int rc;
+    if ((rc = ensure_stage(ctx)) || (rc = ensure_points(ctx, n_points * stride_bytes)) || (rc = ensure_offsets(ctx, 2))) return rc;
+    const KParams& kp = ctx->kp;
+    const size_t bytes = static_cast<size_t>(kp.P) * 2;
+    const long long offs[2] = {0, static_cast<long long>(n_points)};
+    CU(cudaMemcpyAsync(ctx->d_offsets, offs, sizeof(offs), cudaMemcpyHostToDevice, ctx->stream));
+    if (n_points) CU(cudaMemcpyAsync(ctx->d_points, points, n_points * stride_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = ensure_scratch(ctx, 1))) return rc;
+    if ((rc = run_wave(ctx, ctx->d_points, stride_bytes, ctx->d_offsets, 1, static_cast<long long>(n_points), ctx->d_a, ctx->d_b, ctx->d_c,
+                       ctx->d_xyz, ctx->sc.counts)))
+        return rc;
+    if (range_out) CU(cudaMemcpyAsync(range_out, ctx->d_a, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (angle_out) CU(cudaMemcpyAsync(angle_out, ctx->d_b, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (no_ground_out) CU(cudaMemcpyAsync(no_ground_out, ctx->d_c, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned n = 0;
+    CU(cudaMemcpyAsync(&n, ctx->sc.counts, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (xyz4_out && n) {
+        CU(cudaMemcpyAsync(xyz4_out, ctx->d_xyz, static_cast<size_t>(n) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (n_out) *n_out = n;
+    return GS_OK;
+}
+
+// ---- batch API -------------------------------------------------------------------------------
+int gs_process_batch_device(gs_ctx* ctx, const float* d_points_xyzi, const int64_t* h_offsets, int n_frames, uint16_t* d_range_out,
+                            uint16_t* d_angle_out, uint16_t* d_no_ground_out, float* d_xyz4_out, uint32_t* d_counts_out) {
+    if (!ctx || !h_offsets || n_frames < 0 || (n_frames && !d_points_xyzi)) return fail(ctx, GS_EINVAL, "gs_process_batch_device: bad arguments");
+    if (n_frames == 0) return GS_OK;
+    cudaSetDevice(ctx->device);
+    int rc;
+    if ((rc = ensure_offsets(ctx, static_cast<size_t>(n_frames) + 1))) return rc;
+    static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
+    CU(cudaMemcpyAsync(ctx->d_offsets, h_offsets, (static_cast<size_t>(n_frames) + 1) * sizeof(long long), cudaMemcpyHostToDevice,
+                       ctx->stream));
+    const size_t P = ctx->kp.P;
+    const bool use_fused = (reinterpret_cast<uintptr_t>(d_points_xyzi) & 15) == 0 && fused_supported(ctx->fused);
+    const int chunk = use_fused ? n_frames : std::min(n_frames, auto_chunk(ctx));
+    if (!use_fused && (rc = ensure_scratch(ctx, chunk))) return rc;
+    for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+        const int nf = std::min(chunk, n_frames - f0);
+        long long max_points = 0;
+        for (int f = f0; f < f0 + nf; ++f) {
+            const long long n = h_offsets[f + 1] - h_offsets[f];
+            if (n < 0) return fail(ctx, GS_EINVAL, "offsets must be non-decreasing (frame %d)", f);
+            max_points = std::max(max_points, n);
+        }
+        const size_t o = static_cast<size_t>(f0) * P;
+        rc = run_wave(ctx, d_points_xyzi, 16, ctx->d_offsets + f0, nf, max_points, d_range_out ? d_range_out + o : nullptr,
+                      d_angle_out ? d_angle_out + o : nullptr, d_no_ground_out ? d_no_ground_out + o : nullptr,
+                      d_xyz4_out ? d_xyz4_out + 4 * o : nullptr, d_counts_out ? d_counts_out + f0 : nullptr);
+        if (rc) return rc;
+    }
+    return GS_OK;
+}
+
+int gs_process_batch_host(gs_ctx* ctx, const float* h_points_xyzi, const int64_t* h_offsets, int n_frames, uint16_t* h_no_ground_out,
+                          float* h_xyz4_out, uint64_t xyz4_capacity, int64_t* h_out_offsets) {
+    if (!ctx || !h_offsets || n_frames < 0 || (n_frames && !h_points_xyzi)) return fail(ctx, GS_EINVAL, "gs_process_batch_host: bad arguments");
+    if (h_xyz4_out && !h_out_offsets) return fail(ctx, GS_EINVAL, "gs_process_batch_host: h_out_offsets is required with h_xyz4_out");
+    if (n_frames == 0) return GS_OK;
+    cudaSetDevice(ctx->device);
+    const size_t P = ctx->kp.P;
+    int rc;
+    // slot size: enough frames per wave to fill the GPU, small enough to pipeline copies against compute
+    const int wave = std::min(n_frames, ctx->chunk_frames > 0 ? ctx->chunk_frames : 148);
+    if (ctx->slot_frames < wave) {
+        for (int k = 0; k < 2; ++k) {
+            cudaFree(ctx->d_res[k]); cudaFree(ctx->d_cloud[k]); cudaFree(ctx->d_counts[k]);
+            if (ctx->h_counts[k]) cudaFreeHost(ctx->h_counts[k]);
+            ctx->d_res[k] = nullptr; ctx->d_cloud[k] = nullptr; ctx->d_counts[k] = nullptr; ctx->h_counts[k] = nullptr;
+        }
+        ctx->slot_frames = 0;
+        for (int k = 0; k < 2; ++k) {
+            CU(cudaMalloc(&ctx->d_res[k], static_cast<size_t>(wave) * P * 2));
+            CU(cudaMalloc(&ctx->d_cloud[k], static_cast<size_t>(wave) * P * 16));
+            CU(cudaMalloc(&ctx->d_counts[k], static_cast<size_t>(wave) * 4));
+            CU(cudaMallocHost(&ctx->h_counts[k], static_cast<size_t>(wave) * 4));
+        }
+        ctx->slot_frames = wave;
+    }
+    if ((rc = ensure_offsets(ctx, static_cast<size_t>(n_frames) + 1))) return rc;
+    CU(cudaMemcpyAsync(ctx->d_offsets, h_offsets, (static_cast<size_t>(n_frames) + 1) * sizeof(long long), cudaMemcpyHostToDevice,
+                       ctx->stream));
+    const bool fused_ok = fused_supported(ctx->fused);
+    if (!fused_ok && (rc = ensure_scratch(ctx, wave))) return rc;
+    const int n_waves = (n_frames + wave - 1) / wave;
+    int64_t out_cursor = 0;
+    if (h_out_offsets) h_out_offsets[0] = 0;
+    // software pipeline over waves: H2D(w+1) overlaps compute(w) overlaps D2H(w-1)
+    auto issue_in = [&](int w) -> int {
+        const int k = w & 1;
+        const int f0 = w * wave, nf = std::min(wave, n_frames - f0);
+        const long long p0 = h_offsets[f0], p1 = h_offsets[f0 + nf];
+        const size_t bytes = static_cast<size_t>(p1 - p0) * 16;
+        if (ctx->d_in_cap[k] < bytes) {
+            CU(cudaStreamSynchronize(ctx->stream));  // the slot may still be read by an earlier wave
+            cudaFree(ctx->d_in[k]);
+            ctx->d_in[k] = nullptr;
+            ctx->d_in_cap[k] = 0;
+            CU(cudaMalloc(&ctx->d_in[k], bytes + bytes / 8 + 256));
+            ctx->d_in_cap[k] = bytes + bytes / 8 + 256;
+        }
+        if (w >= 2) CU(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_done[k], 0));  // compute of wave w-2 released the slot
+        if (bytes) CU(cudaMemcpyAsync(ctx->d_in[k], h_points_xyzi + 4 * p0, bytes, cudaMemcpyHostToDevice, ctx->copy_in));
+        CU(cudaEventRecord(ctx->ev_in[k], ctx->copy_in));
+        return GS_OK;
+    };
+    auto issue_compute = [&](int w) -> int {
+        const int k = w & 1;
+        const int f0 = w * wave, nf = std::min(wave, n_frames - f0);
+        long long max_points = 0;
+        for (int f = f0; f < f0 + nf; ++f) {
+            if (h_offsets[f + 1] < h_offsets[f]) return fail(ctx, GS_EINVAL, "offsets must be non-decreasing (frame %d)", f);
+            max_points = std::max<long long>(max_points, h_offsets[f + 1] - h_offsets[f]);
+        }
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[k], 0));
+        if (w >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[k], 0));  // D2H of wave w-2 drained the slot's outputs
+        // offsets inside the slot are relative to the wave's first point: pass a shifted base pointer instead
+        const float* base = ctx->d_in[k] - 4 * h_offsets[f0];
+        const int rc2 = run_wave(ctx, base, 16, ctx->d_offsets + f0, nf, max_points, nullptr, nullptr, ctx->d_res[k], ctx->d_cloud[k],
+                                 ctx->d_counts[k]);
+        if (rc2) return rc2;
+        CU(cudaMemcpyAsync(ctx->h_counts[k], ctx->d_counts[k], static_cast<size_t>(nf) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaEventRecord(ctx->ev_done[k], ctx->stream));
+        return GS_OK;
+    };
+    auto issue_out = [&](int w) -> int {
+        const int k = w & 1;
+        const int f0 = w * wave, nf = std::min(wave, n_frames - f0);
+        CU(cudaEventSynchronize(ctx->ev_done[k]));  // counts are on the host now
+        CU(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[k], 0));
+        if (h_no_ground_out)
+            CU(cudaMemcpyAsync(h_no_ground_out + static_cast<size_t>(f0) * P, ctx->d_res[k], static_cast<size_t>(nf) * P * 2,
+                               cudaMemcpyDeviceToHost, ctx->copy_out));
+        for (int f = 0; f < nf; ++f) {
+            const unsigned n = ctx->h_counts[k][f];
+            if (h_xyz4_out) {
+                if (static_cast<uint64_t>(out_cursor) + n > xyz4_capacity) return fail(ctx, GS_EINVAL, "xyz4 output capacity exceeded at frame %d", f0 + f);
+                if (n)
+                    CU(cudaMemcpyAsync(h_xyz4_out + 4 * out_cursor, ctx->d_cloud[k] + 4 * static_cast<size_t>(f) * P, static_cast<size_t>(n) * 16,
+                                       cudaMemcpyDeviceToHost, ctx->copy_out));
+            }
+            out_cursor += n;
+            if (h_out_offsets) h_out_offsets[f0 + f + 1] = out_cursor;
+        }
+        CU(cudaEventRecord(ctx->ev_out[k], ctx->copy_out));
+        return GS_OK;
+    };
+    if ((rc = issue_in(0))) return rc;
+    for (int w = 0; w < n_waves; ++w) {
+        if (w + 1 < n_waves && (rc = issue_in(w + 1))) return rc;
+        if ((rc = issue_compute(w))) return rc;
+        if (w >= 1 && (rc = issue_out(w - 1))) return rc;
+    }
+    if ((rc = issue_out(n_waves - 1))) return rc;
+    CU(cudaStreamSynchronize(ctx->copy_out));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GS_OK;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,619 @@
+// gs_kernels.cu — the hot path as hand-written CUDA for sm_100a.
+//
+// Stage map (reference file:line -> kernel):
+//   K1  k_project + k_finalize     Alfa_GS::CreateRangeImage   src/alfa_gs.cpp:247-298 (+ lib/utils.h:8-43)
+//                                  Cloud2RangeNode::CloudCb    src/cloud2range_node.cpp:396-455
+//   K2  k_angle                    Alfa_GS::CreateAngleImg     src/alfa_gs.cpp:335-386
+//       k_sg                       SavitskyGolaySmoothing      src/alfa_gs.cpp:641-713 (cv::filter2D)
+//       k_repair                   RepairGaps (typed)          src/alfa_gs.cpp:300-333
+//   K3  k_ccl_init/k_ccl_union     Label::LabelOneComponent    Labeler/label.cpp:48-104 as union-find
+//       k_seeds, k_label           EraseBFS seed loop          src/alfa_gs.cpp:720-739
+//   K4  k_erase                    GetUniformKernel+cv::dilate+erase  src/alfa_gs.cpp:747-764
+//       k_backproject              Alfa_GS::CameraCb           src/alfa_gs.cpp:997-1074 / src/range2cloud_node.cpp:64-91
+//
+// Everything here is HBM/L2-bound integer and fp work: no tensor cores (nothing is a contraction).
+// All kernels take a wave of independent frames (blockIdx.y = frame) so that one launch fills the 148 SMs.
+// Parity rules: compile with -fmad=false; parity-critical arithmetic additionally uses explicit
+// round-to-nearest intrinsics so it does not depend on the flag.
+#include <math_constants.h>
+
+#include "gs_internal.h"
+#include "gs_math.cuh"
+
+namespace gs {
+
+namespace {
+
+constexpr int FLAG_GROUND = 1 << 30;
+constexpr int IDX_MASK = FLAG_GROUND - 1;
+
+// streaming 16-byte load: points are read exactly once, keep them out of L1 and first in line for L2 eviction
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) { return __ldcs(p); }
+
+__device__ __forceinline__ double decode_range(const KParams& kp, unsigned enc) {
+    // static_cast<double>(enc - 1) / 65534 * (max_range - min_range) + min_range   (alfa_gs.cpp:359-360, :1042-1045)
+    const double norm = __ddiv_rn(static_cast<double>(static_cast<int>(enc) - 1), 65534.0);
+    return __dadd_rn(__dmul_rn(norm, kp.span), kp.min_range);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 — spherical projection.  One thread per point; the pixel owner is decided by a packed 64-bit
+// atomicMax: (point index << 32 | range) keeps the LAST point in input order like the reference's
+// sequential overwrite (alfa_gs.cpp:291); the `nearest` policy stores the complement of
+// (range << 32 | index) so that the same atomicMax keeps the smallest range, lowest index.
+// ------------------------------------------------------------------------------------------------
+struct Projected {
+    int flat;      // row * W + col, or -1 when the point is dropped
+    unsigned enc;  // 1..65535
+    bool near_edge;
+};
+
+__device__ __forceinline__ Projected project_point(const KParams& kp, float fx, float fy, float fz) {
+    Projected out;
+    out.flat = -1;
+    out.enc = 0;
+    out.near_edge = false;
+    if (!(isfinite(fx) && isfinite(fy) && isfinite(fz))) return out;  // contract Q3
+    const double x = fx, y = fy, z = fz;
+    const double range = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));  // utils.h:41-43
+    if (range < kp.min_range || range > kp.max_range) return out;                                             // alfa_gs.cpp:261
+    const double a = atan2(y, x);
+    const double azimuth = (y >= 0 ? a : __dadd_rn(a, 6.283185307179586476925286766559));  // utils.h:24-28
+    const double altitude = atan2(z, hypot(x, y));                                        // utils.h:8-11
+    if (altitude < kp.min_angle || altitude > kp.max_angle) return out;                   // alfa_gs.cpp:269
+    double rowf, colf;
+    if (kp.variant == GS_VARIANT_CLOUD2RANGE) {
+        rowf = __dmul_rn(__ddiv_rn(__dsub_rn(kp.max_angle, altitude), kp.ang_span), static_cast<double>(kp.H));  // cloud2range_node.cpp:436
+        colf = __ddiv_rn(azimuth, kp.d_az);                                                                      // :438
+    } else {
+        rowf = __dsub_rn(static_cast<double>(kp.H - 1),
+                         __ddiv_rn(__dsub_rn(__dsub_rn(altitude, kp.half_d_alt), kp.min_angle), kp.d_alt));  // alfa_gs.cpp:275
+        colf = __ddiv_rn(__dadd_rn(azimuth, kp.half_d_az), kp.d_az);                                         // :277
+    }
+    if (!(colf >= 0.0)) return out;  // contract Q3: y = -0.0, x < 0
+    const int row = __double2int_rz(rowf);
+    int col = __double2int_rz(colf);
+    {
+        const double fr = rowf - floor(rowf), fc = colf - floor(colf);
+        const double cell_alt = (kp.variant == GS_VARIANT_CLOUD2RANGE) ? kp.ang_span / kp.H : kp.d_alt;
+        out.near_edge = fmin(fr, 1.0 - fr) * cell_alt < 1e-5 || fmin(fc, 1.0 - fc) * kp.d_az < 1e-5;
+    }
+    if (row < 0 || row >= kp.H) return out;  // Q4
+    int flat;
+    if (kp.variant == GS_VARIANT_CLOUD2RANGE) {
+        if (col >= kp.W) return out;
+        flat = row * kp.W + col;
+    } else if (kp.col_policy == GS_COL_WRAP) {
+        col %= kp.W;
+        flat = row * kp.W + col;
+    } else {
+        flat = row * kp.W + col;  // Q2: col may equal W and alias (row+1, 0)
+        if (flat >= kp.P) return out;
+    }
+    const double range_norm = __ddiv_rn(__dsub_rn(range, kp.min_range), kp.span);  // alfa_gs.cpp:288
+    out.enc = static_cast<unsigned>(__double2int_rz(__dadd_rn(__dmul_rn(range_norm, 65534.0), 1.0)));  // :291
+    out.flat = flat;
+    return out;
+}
+
+template <bool STRIDE16>
+__global__ void __launch_bounds__(256) k_project(const char* __restrict__ points, size_t stride,
+                                                 const long long* __restrict__ offsets, KParams kp,
+                                                 unsigned long long* __restrict__ keys, Counters* cnt, int stats) {
+    const int f = blockIdx.y;
+    const long long beg = offsets[f], end = offsets[f + 1];
+    const long long i = beg + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= end) return;
+    float fx, fy, fz;
+    if (STRIDE16) {
+        const float4 q = ld_stream_f4(reinterpret_cast<const float4*>(points) + i);
+        fx = q.x; fy = q.y; fz = q.z;
+    } else {
+        const float* q = reinterpret_cast<const float*>(points + static_cast<size_t>(i) * stride);
+        fx = q[0]; fy = q[1]; fz = q[2];
+    }
+    const Projected pr = project_point(kp, fx, fy, fz);
+    if (stats) {
+        if (pr.flat < 0) atomicAdd(&cnt->dropped, 1ull);
+        else if (pr.near_edge) atomicAdd(&cnt->near_edge_project, 1ull);
+    }
+    if (pr.flat < 0) return;
+    const unsigned long long idx = static_cast<unsigned long long>(i - beg);
+    unsigned long long key;
+    if (kp.pixel_policy == GS_PIXEL_NEAREST) key = ~((static_cast<unsigned long long>(pr.enc) << 32) | idx);
+    else key = (idx << 32) | pr.enc;
+    atomicMax(keys + static_cast<size_t>(f) * kp.P + pr.flat, key);
+}
+
+// keys -> u16 range image; keys are re-zeroed for the next wave.
+__global__ void __launch_bounds__(256) k_finalize(unsigned long long* __restrict__ keys, uint16_t* __restrict__ range,
+                                                  KParams kp) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= kp.P) return;
+    const size_t i = static_cast<size_t>(blockIdx.y) * kp.P + p;
+    const unsigned long long key = keys[i];
+    unsigned enc = 0;
+    if (key) {
+        keys[i] = 0ull;
+        enc = (kp.pixel_policy == GS_PIXEL_NEAREST) ? static_cast<unsigned>((~key) >> 32) : static_cast<unsigned>(key & 0xffffu);
+    }
+    range[i] = static_cast<uint16_t>(enc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 — angle image.  The reference walks every column bottom->top carrying the previous non-empty
+// pixel (alfa_gs.cpp:347-382).  Here every pixel finds that predecessor itself by scanning down its
+// column (1-2 L1-resident loads in practice), which makes all pixels independent and all loads
+// row-coalesced.  sinf/cosf of the row angle come from host LUTs; atan2f is the glibc clone.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_angle(const uint16_t* __restrict__ range, uint16_t* __restrict__ angle, KParams kp,
+                                               Luts lut, Counters* cnt, int stats) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= kp.P) return;
+    const size_t base = static_cast<size_t>(blockIdx.y) * kp.P;
+    const uint16_t* R = range + base;
+    const unsigned enc = R[p];
+    unsigned out = 0;
+    if (enc) {
+        const int r = p / kp.W, c = p - r * kp.W;
+        int rr = r + 1;
+        unsigned penc = 0;
+        for (; rr < kp.H; ++rr) {
+            penc = R[rr * kp.W + c];
+            if (penc) break;
+        }
+        bool has_prev = penc != 0;
+        float prev_r = 0.0f, sp = 0.0f, cp = 1.0f;  // initial state: prev_r = 0, prev_angle_y = 0 (alfa_gs.cpp:342)
+        if (has_prev) {
+            prev_r = __double2float_rn(decode_range(kp, penc));  // prev_r = range (float) :379
+            sp = lut.sin_y[rr];
+            cp = lut.cos_y[rr];
+        } else if (c == 1) {
+            // column-1 quirk (SURVEY.md A.2 iii): prev_col starts at 1 (:340), so the first pixel ever
+            // processed, if it lies in column 1, is compared against the initial state.
+            bool col0_empty = true;
+            for (int q = 0; q < kp.H; ++q)
+                if (R[q * kp.W]) { col0_empty = false; break; }
+            has_prev = col0_empty;
+        }
+        if (has_prev) {
+            const double rng = decode_range(kp, enc);
+            // :366-367  |float*float - double*float| in double, narrowed to float
+            const double dz = fabs(__dsub_rn(static_cast<double>(__fmul_rn(prev_r, sp)), __dmul_rn(rng, static_cast<double>(lut.sin_y[r]))));
+            const double dx = fabs(__dsub_rn(static_cast<double>(__fmul_rn(prev_r, cp)), __dmul_rn(rng, static_cast<double>(lut.cos_y[r]))));
+            const float alfa = gs_atan2f(__double2float_rn(dz), __double2float_rn(dx));  // :368
+            const float scaled = __fmul_rn(alfa, 100.0f);                                 // :370
+            out = static_cast<unsigned>(__float2int_rz(scaled));
+            if (stats) {
+                const float fr = scaled - floorf(scaled);
+                if (fminf(fr, 1.0f - fr) < 1e-3f) atomicAdd(&cnt->near_edge_angle, 1ull);
+            }
+        }
+    }
+    angle[base + p] = static_cast<uint16_t>(out);
+}
+
+// Savitzky-Golay column filter = cv::filter2D(u16, ws x 1 float kernel, BORDER_REFLECT101): float32 accumulation in
+// tap order, round-half-even, saturate (pinned against OpenCV in tests/golden).
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * n - 2 - i;
+    return i;
+}
+
+__global__ void __launch_bounds__(256) k_sg(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, KParams kp, SgTaps taps) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= kp.P) return;
+    const size_t base = static_cast<size_t>(blockIdx.y) * kp.P;
+    const int r = p / kp.W, c = p - r * kp.W, half = taps.ws / 2;
+    float acc = 0.0f;
+    for (int k = 0; k < taps.ws; ++k) {
+        const int rr = reflect101(r + k - half, kp.H);
+        acc = __fadd_rn(acc, __fmul_rn(taps.t[k], static_cast<float>(in[base + rr * kp.W + c])));
+    }
+    int v = __float2int_rn(acc);
+    v = max(0, min(65535, v));
+    out[base + p] = static_cast<uint16_t>(v);
+}
+
+// Typed RepairGaps: in-place, top-to-bottom dependency inside a column -> one thread per column.
+__global__ void __launch_bounds__(128) k_repair(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, KParams kp, int step,
+                                                float thr) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= kp.W) return;
+    const size_t base = static_cast<size_t>(blockIdx.y) * kp.P;
+    for (int r = 0; r < kp.H; ++r) out[base + r * kp.W + c] = in[base + r * kp.W + c];
+    for (int r = 0; r < kp.H; ++r) {
+        if (out[base + r * kp.W + c] != 0) continue;
+        int counter = 0;
+        float sum = 0.0f;
+        for (int i = 1; i < step; ++i) {
+            if (r - i < 0) continue;
+            for (int j = 1; j < step; ++j) {
+                if (r + j > kp.H - 1) continue;
+                const float prev = out[base + (r - i) * kp.W + c];
+                const float next = out[base + (r + j) * kp.W + c];
+                if (prev > 0.001f && next > 0.001f && fabsf(__fsub_rn(prev, next)) < thr) {
+                    sum = __fadd_rn(sum, __fadd_rn(prev, next));
+                    counter += 2;
+                }
+            }
+        }
+        if (counter > 0) out[base + r * kp.W + c] = static_cast<uint16_t>(__float2int_rz(__fdiv_rn(sum, static_cast<float>(counter))));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 — connected components by union-find (root = smallest flat index), replacing the Labeler's BFS.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(const int* par, int i) {
+    int p = par[i] & IDX_MASK;
+    while (p != i) {
+        i = p;
+        p = par[i] & IDX_MASK;
+    }
+    return i;
+}
+
+__device__ __forceinline__ void uf_unite(int* par, int a, int b) {
+    for (;;) {
+        a = uf_find(par, a);
+        b = uf_find(par, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }
+        const int old = atomicMin(par + a, b);  // hang the larger root under the smaller one
+        if (old == a) return;
+        a = old;  // somebody re-parented a first: unite its new parent with b as well
+    }
+}
+
+__global__ void __launch_bounds__(256) k_ccl_init(int* __restrict__ parent, KParams kp) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= kp.P) return;
+    parent[static_cast<size_t>(blockIdx.y) * kp.P + p] = p;
+}
+
+__device__ __forceinline__ bool px_open(const uint16_t* R, const uint8_t* blocked, int p) {
+    return R[p] != 0 && (blocked == nullptr || blocked[p] == 0);
+}
+
+// One thread per pixel links it with its upper and left neighbour (left of column 0 is column W-1:
+// Label::WrapCols, label.cpp:33-45) when both are non-empty and |angle difference| <= k_edge
+// (label.cpp:90-101 with the float threshold folded into an integer).
+__global__ void __launch_bounds__(256) k_ccl_union(const uint16_t* __restrict__ range, const uint16_t* __restrict__ angle,
+                                                   const uint8_t* __restrict__ blocked, int k_edge, int* __restrict__ parent,
+                                                   KParams kp) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= kp.P) return;
+    const size_t base = static_cast<size_t>(blockIdx.y) * kp.P;
+    const uint16_t* R = range + base;
+    const uint16_t* A = angle + base;
+    const uint8_t* B = blocked ? blocked + base : nullptr;
+    int* par = parent + base;
+    if (!px_open(R, B, p)) return;
+    const int r = p / kp.W, c = p - r * kp.W;
+    const int a = A[p];
+    if (r > 0) {
+        const int q = p - kp.W;
+        if (px_open(R, B, q) && abs(a - static_cast<int>(A[q])) <= k_edge) uf_unite(par, p, q);
+    }
+    if (kp.W > 1) {
+        const int q = (c > 0) ? p - 1 : p + kp.W - 1;
+        if (px_open(R, B, q) && abs(a - static_cast<int>(A[q])) <= k_edge) uf_unite(par, p, q);
+    }
+}
+
+// Seed loop of EraseBFS (alfa_gs.cpp:720-739): per column the bottom-most non-empty pixel (stopping at row 0),
+// accepted when its angle <= s_start; accepted non-empty seeds flag their component's root as ground.
+__global__ void __launch_bounds__(128) k_seeds(const uint16_t* __restrict__ range, const uint16_t* __restrict__ angle,
+                                               int* __restrict__ parent, int* __restrict__ seed_row, uint8_t* __restrict__ eseed,
+                                               KParams kp) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= kp.W) return;
+    const size_t base = static_cast<size_t>(blockIdx.y) * kp.P;
+    const uint16_t* R = range + base;
+    int r = kp.H - 1;
+    while (r > 0 && R[r * kp.W + c] == 0) --r;  // :722-725
+    const int p = r * kp.W + c;
+    const bool accepted = static_cast<int>(angle[base + p]) <= kp.s_start;  // :733
+    const bool valid = R[p] != 0;
+    if (accepted && valid) {
+        int* par = parent + base;
+        atomicOr(par + uf_find(par, p), FLAG_GROUND);
+    }
+    seed_row[static_cast<size_t>(blockIdx.y) * kp.W + c] = r;
+    eseed[static_cast<size_t>(blockIdx.y) * kp.W + c] = (accepted && !valid) ? 1 : 0;
+}
+
+__device__ __forceinline__ bool is_ground(const int* par, int p) { return (par[uf_find(par, p)] & FLAG_GROUND) != 0; }
+
+// The Labeler's image L: non-empty pixels of flagged components; accepted empty seeds; empty
+// pixels 4-adjacent to a ground pixel u with |angle(u) - angle(empty)| <= K (labelled by the BFS but not expanded,
+// label.cpp:67-74).
+__global__ void __launch_bounds__(256) k_label(const uint16_t* __restrict__ range, const uint16_t* __restrict__ angle,
+                                               const int* __restrict__ parent, const int* __restrict__ seed_row,
+                                               const uint8_t* __restrict__ eseed, uint8_t* __restrict__ label, KParams kp) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= kp.P) return;
+    const size_t base = static_cast<size_t>(blockIdx.y) * kp.P;
+    const uint16_t* R = range + base;
+    const uint16_t* A = angle + base;
+    const int* par = parent + base;
+    unsigned L = 0;
+    if (R[p] != 0) {
+        L = is_ground(par, p);
+    } else {
+        const int r = p / kp.W, c = p - r * kp.W;
+        const size_t cb = static_cast<size_t>(blockIdx.y) * kp.W + c;
+        if (seed_row[cb] == r && eseed[cb]) L = 1;
+        const int a = A[p];
+        if (!L && r > 0) {
+            const int q = p - kp.W;
+            if (R[q] != 0 && abs(a - static_cast<int>(A[q])) <= kp.k_ground) L = is_ground(par, q);
+        }
+        if (!L && r < kp.H - 1) {
+            const int q = p + kp.W;
+            if (R[q] != 0 && abs(a - static_cast<int>(A[q])) <= kp.k_ground) L = is_ground(par, q);
+        }
+        if (!L && kp.W > 1) {
+            int q = (c > 0) ? p - 1 : p + kp.W - 1;
+            if (R[q] != 0 && abs(a - static_cast<int>(A[q])) <= kp.k_ground) L = is_ground(par, q);
+            if (!L) {
+                q = (c < kp.W - 1) ? p + 1 : p - (kp.W - 1);
+                if (R[q] != 0 && abs(a - static_cast<int>(A[q])) <= kp.k_ground) L = is_ground(par, q);
+            }
+        }
+    }
+    label[base + p] = static_cast<uint8_t>(L);
+}
+
+// Label::LabelOneComponent on an existing label image: flag the seed's component, then write `label` into every
+// unlabelled pixel the BFS would reach.  Single frame.
+__global__ void k_one_seed(const uint16_t* __restrict__ range, const uint8_t* __restrict__ label_image, int* __restrict__ parent,
+                           int seed, int* __restrict__ seed_state) {
+    // seed_state: 0 = seed already labelled (nothing to do), 1 = empty seed (labelled, not expanded), 2 = component flagged
+    if (label_image[seed] != 0) { *seed_state = 0; return; }
+    if (range[seed] == 0) { *seed_state = 1; return; }
+    atomicOr(parent + uf_find(parent, seed), FLAG_GROUND);
+    *seed_state = 2;
+}
+
+__global__ void __launch_bounds__(256) k_one_label(const uint16_t* __restrict__ R, const uint16_t* __restrict__ A,
+                                                   const int* __restrict__ par, const int* __restrict__ seed_state, int seed,
+                                                   int k_edge, int label, uint8_t* __restrict__ label_image, KParams kp) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= kp.P) return;
+    const int st = *seed_state;
+    if (st == 0 || label_image[p] != 0) return;
+    if (st == 1) {
+        if (p == seed) label_image[p] = static_cast<uint8_t>(label);
+        return;
+    }
+    bool hit = false;
+    if (R[p] != 0) {
+        hit = is_ground(par, p);
+    } else {
+        // an unlabelled empty pixel next to a reached pixel u (u is non-empty and was unlabelled before the call)
+        const int r = p / kp.W, c = p - r * kp.W, a = A[p];
+        int q[4];
+        q[0] = r > 0 ? p - kp.W : -1;
+        q[1] = r < kp.H - 1 ? p + kp.W : -1;
+        q[2] = kp.W > 1 ? (c > 0 ? p - 1 : p + kp.W - 1) : -1;
+        q[3] = kp.W > 1 ? (c < kp.W - 1 ? p + 1 : p - (kp.W - 1)) : -1;
+        for (int k = 0; k < 4 && !hit; ++k) {
+            const int u = q[k];
+            if (u < 0 || R[u] == 0 || abs(a - static_cast<int>(A[u])) > k_edge) continue;
+            // u must be part of the flagged forest: blocked (pre-labelled) pixels are singletons that were never united
+            hit = (par[uf_find(par, u)] & FLAG_GROUND) != 0;
+        }
+    }
+    // NOTE: pixels are tested against the label image as it was BEFORE this launch for non-empty pixels only through
+    // `par` (built before); reading label_image[p] != 0 above only skips pixels this launch never writes twice.
+    if (hit) label_image[p] = static_cast<uint8_t>(label);
+}
+
+// All-components mode: canonical label = root = smallest flat index of the component, -1 for empty pixels.
+__global__ void __launch_bounds__(256) k_components(const uint16_t* __restrict__ image, int* __restrict__ parent,
+                                                    int32_t* __restrict__ labels, Counters* cnt, KParams kp) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= kp.P) return;
+    const size_t base = static_cast<size_t>(blockIdx.y) * kp.P;
+    int out = -1;
+    if (image[base + p] != 0) {
+        out = uf_find(parent + base, p);
+        if (out == p) atomicAdd(&cnt->components, 1ull);
+    }
+    labels[base + p] = out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 — dilation taps + erase, then ordered compaction + back-projection.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned block_sum_256(unsigned v, unsigned* smem) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = __reduce_add_sync(0xffffffffu, v);
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    unsigned tot = 0;
+    for (int w = 0; w < 8; ++w) tot += smem[w];
+    __syncthreads();
+    return tot;
+}
+
+// One block per image row.  dilated(r,c) = OR_k L(r + off_k, c) — the effective structuring element of
+// cv::dilate with GetUniformKernel's bytes; res = dilated ? 0 : range (alfa_gs.cpp:751-764).
+__global__ void __launch_bounds__(256) k_erase(const uint16_t* __restrict__ range, const uint8_t* __restrict__ label,
+                                               uint16_t* __restrict__ res, unsigned* __restrict__ rowcount, KParams kp) {
+    __shared__ unsigned smem[8];
+    const int r = blockIdx.x;
+    const size_t base = static_cast<size_t>(blockIdx.y) * kp.P;
+    const int r0 = r + kp.dil0, r1 = r + kp.dil1;
+    const bool ok0 = r0 >= 0 && r0 < kp.H, ok1 = kp.n_dil > 1 && r1 >= 0 && r1 < kp.H;
+    unsigned count = 0;
+    for (int c = threadIdx.x; c < kp.W; c += 256) {
+        unsigned dil = 0;
+        if (ok0) dil |= label[base + r0 * kp.W + c];
+        if (ok1) dil |= label[base + r1 * kp.W + c];
+        const unsigned v = range[base + r * kp.W + c];
+        const unsigned o = (kp.erase_ground ? (dil == 0) : (dil != 0)) ? v : 0u;
+        res[base + r * kp.W + c] = static_cast<uint16_t>(o);
+        count += (o != 0);
+    }
+    const unsigned tot = block_sum_256(count, smem);
+    if (threadIdx.x == 0) rowcount[static_cast<size_t>(blockIdx.y) * kp.H + r] = tot;
+}
+
+__global__ void __launch_bounds__(256) k_rowcount(const uint16_t* __restrict__ image, unsigned* __restrict__ rowcount, KParams kp) {
+    __shared__ unsigned smem[8];
+    const int r = blockIdx.x;
+    const size_t base = static_cast<size_t>(blockIdx.y) * kp.P;
+    unsigned count = 0;
+    for (int c = threadIdx.x; c < kp.W; c += 256) count += image[base + r * kp.W + c] != 0;
+    const unsigned tot = block_sum_256(count, smem);
+    if (threadIdx.x == 0) rowcount[static_cast<size_t>(blockIdx.y) * kp.H + r] = tot;
+}
+
+// One block per image row: output slot = (non-zero pixels in the rows above) + rank inside the row, which is exactly the
+// row-major push_back order of CameraCb (alfa_gs.cpp:1023-1058).  cos/sin come from host double LUTs, so x,y,z are the
+// reference's doubles rounded to float.
+template <bool RANGE_AS_DOUBLE>
+__global__ void __launch_bounds__(256) k_backproject(const uint16_t* __restrict__ image, const unsigned* __restrict__ rowcount,
+                                                     float4* __restrict__ xyz, unsigned* __restrict__ counts, KParams kp, Luts lut) {
+    __shared__ unsigned warp_tot[8];
+    __shared__ unsigned s_base;
+    const int r = blockIdx.x;
+    const int f = blockIdx.y;
+    const size_t base = static_cast<size_t>(f) * kp.P;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // rows above: H <= 1024 counters, summed by the first warp
+    if (warp == 0) {
+        unsigned s = 0;
+        for (int q = lane; q < r; q += 32) s += rowcount[static_cast<size_t>(f) * kp.H + q];
+        s = __reduce_add_sync(0xffffffffu, s);
+        if (lane == 0) s_base = s;
+    }
+    __syncthreads();
+    unsigned running = s_base;
+    const double ca = lut.cos_alt[r], sa = lut.sin_alt[r];
+    float4* out = xyz + base;  // slab of frame f: up to P records
+    for (int c0 = 0; c0 < kp.W; c0 += 256) {
+        const int c = c0 + threadIdx.x;
+        const unsigned enc = (c < kp.W) ? image[base + r * kp.W + c] : 0u;
+        const unsigned ballot = __ballot_sync(0xffffffffu, enc != 0);
+        if (lane == 0) warp_tot[warp] = __popc(ballot);
+        __syncthreads();
+        unsigned before = 0, total = 0;
+        for (int w = 0; w < 8; ++w) {
+            const unsigned t = warp_tot[w];
+            before += (w < static_cast<int>(warp)) ? t : 0u;
+            total += t;
+        }
+        if (enc != 0) {
+            const unsigned slot = running + before + __popc(ballot & ((1u << lane) - 1u));
+            const double rng_d = decode_range(kp, enc);
+            const double rng = RANGE_AS_DOUBLE ? rng_d : static_cast<double>(__double2float_rn(rng_d));  // alfa_gs.cpp:1027,1045 vs range2cloud_node.cpp:76
+            const double caz = lut.cos_az[c], saz = lut.sin_az[c];
+            float4 o;
+            o.x = __double2float_rn(__dmul_rn(__dmul_rn(ca, caz), rng));  // :1055
+            o.y = __double2float_rn(__dmul_rn(__dmul_rn(ca, saz), rng));  // :1056
+            o.z = __double2float_rn(__dmul_rn(sa, rng));                  // :1057
+            o.w = 1.0f;
+            out[slot] = o;
+        }
+        running += total;
+        __syncthreads();
+    }
+    if (r == kp.H - 1 && threadIdx.x == 0) counts[f] = running;
+}
+
+inline dim3 pixel_grid(const KParams& kp, int frames) { return dim3((kp.P + 255) / 256, frames); }
+
+}  // namespace
+
+#define GS_COUNT(L) (++*(L).n_launches)
+
+void launch_project(const Launch& L, const KParams& kp, const void* points, size_t stride, const long long* d_offsets, int frames,
+                    long long max_points, unsigned long long* keys, Counters* cnt, bool stats) {
+    if (max_points <= 0 || frames <= 0) return;
+    const dim3 grid(static_cast<unsigned>((max_points + 255) / 256), frames);
+    const bool s16 = stride == 16 && (reinterpret_cast<uintptr_t>(points) & 15) == 0;
+    if (s16) k_project<true><<<grid, 256, 0, L.stream>>>(static_cast<const char*>(points), stride, d_offsets, kp, keys, cnt, stats);
+    else k_project<false><<<grid, 256, 0, L.stream>>>(static_cast<const char*>(points), stride, d_offsets, kp, keys, cnt, stats);
+    GS_COUNT(L);
+}
+
+void launch_finalize(const Launch& L, const KParams& kp, int frames, unsigned long long* keys, uint16_t* range) {
+    k_finalize<<<pixel_grid(kp, frames), 256, 0, L.stream>>>(keys, range, kp);
+    GS_COUNT(L);
+}
+
+void launch_angle(const Launch& L, const KParams& kp, const Luts& lut, int frames, const uint16_t* range, uint16_t* angle, Counters* cnt,
+                  bool stats) {
+    k_angle<<<pixel_grid(kp, frames), 256, 0, L.stream>>>(range, angle, kp, lut, cnt, stats);
+    GS_COUNT(L);
+}
+
+void launch_sg(const Launch& L, const KParams& kp, const SgTaps& taps, int frames, const uint16_t* in, uint16_t* out) {
+    k_sg<<<pixel_grid(kp, frames), 256, 0, L.stream>>>(in, out, kp, taps);
+    GS_COUNT(L);
+}
+
+void launch_repair(const Launch& L, const KParams& kp, int frames, const uint16_t* in, uint16_t* out, int step, float thr) {
+    k_repair<<<dim3((kp.W + 127) / 128, frames), 128, 0, L.stream>>>(in, out, kp, step, thr);
+    GS_COUNT(L);
+}
+
+void launch_ccl(const Launch& L, const KParams& kp, int frames, const uint16_t* range, const uint16_t* angle, const uint8_t* blocked,
+                int k_edge, int* parent) {
+    k_ccl_init<<<pixel_grid(kp, frames), 256, 0, L.stream>>>(parent, kp);
+    GS_COUNT(L);
+    k_ccl_union<<<pixel_grid(kp, frames), 256, 0, L.stream>>>(range, angle, blocked, k_edge, parent, kp);
+    GS_COUNT(L);
+}
+
+void launch_ground(const Launch& L, const KParams& kp, int frames, const uint16_t* range, const uint16_t* angle, int* parent,
+                   int* seed_row, uint8_t* eseed, uint8_t* label) {
+    k_seeds<<<dim3((kp.W + 127) / 128, frames), 128, 0, L.stream>>>(range, angle, parent, seed_row, eseed, kp);
+    GS_COUNT(L);
+    k_label<<<pixel_grid(kp, frames), 256, 0, L.stream>>>(range, angle, parent, seed_row, eseed, label, kp);
+    GS_COUNT(L);
+}
+
+void launch_one_component(const Launch& L, const KParams& kp, const uint16_t* range, const uint16_t* angle, int k_edge, int* parent,
+                          int row, int col, int label, uint8_t* label_image) {
+    // parent was built by launch_ccl with blocked = label_image; seed_row scratch doubles as the seed state word
+    int* seed_state = parent + kp.P;  // caller guarantees one spare int after the forest
+    const int seed = row * kp.W + col;
+    k_one_seed<<<1, 1, 0, L.stream>>>(range, label_image, parent, seed, seed_state);
+    GS_COUNT(L);
+    k_one_label<<<pixel_grid(kp, 1), 256, 0, L.stream>>>(range, angle, parent, seed_state, seed, k_edge, label, label_image, kp);
+    GS_COUNT(L);
+}
+
+void launch_components(const Launch& L, const KParams& kp, int frames, const uint16_t* image, int* parent, int32_t* labels,
+                       Counters* cnt) {
+    k_components<<<pixel_grid(kp, frames), 256, 0, L.stream>>>(image, parent, labels, cnt, kp);
+    GS_COUNT(L);
+}
+
+void launch_erase(const Launch& L, const KParams& kp, int frames, const uint16_t* range, const uint8_t* label, uint16_t* res,
+                  unsigned* rowcount) {
+    k_erase<<<dim3(kp.H, frames), 256, 0, L.stream>>>(range, label, res, rowcount, kp);
+    GS_COUNT(L);
+}
+
+void launch_rowcount(const Launch& L, const KParams& kp, int frames, const uint16_t* image, unsigned* rowcount) {
+    k_rowcount<<<dim3(kp.H, frames), 256, 0, L.stream>>>(image, rowcount, kp);
+    GS_COUNT(L);
+}
+
+void launch_backproject(const Launch& L, const KParams& kp, const Luts& lut, int frames, const uint16_t* image, const unsigned* rowcount,
+                        float* xyz4, unsigned* counts, bool range_as_double) {
+    if (range_as_double)
+        k_backproject<true><<<dim3(kp.H, frames), 256, 0, L.stream>>>(image, rowcount, reinterpret_cast<float4*>(xyz4), counts, kp, lut);
+    else
+        k_backproject<false><<<dim3(kp.H, frames), 256, 0, L.stream>>>(image, rowcount, reinterpret_cast<float4*>(xyz4), counts, kp, lut);
+    GS_COUNT(L);
+}
+
+}  // namespace gs

@@ -131,7 +131,14 @@ int gs_get_derived(const gs_ctx* ctx, gs_derived* out);
 int gs_set_stream(gs_ctx* ctx, void* cuda_stream);
 /* frames processed per wave by the batch calls (scratch = chunk * ~20 B/pixel, kept L2 resident) */
 int gs_set_chunk_frames(gs_ctx* ctx, int frames);
+/* options: GS_OPT_COLLECT_STATS (default 0) makes the kernels fill the near-edge / dropped counters of gs_stats;
+ * GS_OPT_FORCE_STAGED (default 0) routes the frame/batch calls through the per-stage kernels instead of the fused one
+ * (both are CUDA paths; used by the parity tests to check one against the other). */
+#define GS_OPT_COLLECT_STATS 1
+#define GS_OPT_FORCE_STAGED 2
+int gs_set_option(gs_ctx* ctx, int option, int value);
 int gs_get_stats(gs_ctx* ctx, gs_stats* out);
+int gs_reset_stats(gs_ctx* ctx);
 const char* gs_last_error(const gs_ctx* ctx);
 
 /* ---- stage API: one frame, HOST buffers (copies included) ---------------------------------- */
@@ -182,11 +189,13 @@ int gs_process_frame(gs_ctx* ctx, const void* points, size_t n_points, size_t st
 int gs_process_batch_device(gs_ctx* ctx, const float* d_points_xyzi, const int64_t* h_offsets,
                             int n_frames, uint16_t* d_range_out, uint16_t* d_angle_out,
                             uint16_t* d_no_ground_out, float* d_xyz4_out, uint32_t* d_counts_out);
-/* HOST buffers (pinned recommended): the same, with the host<->device copies done inside,
- * overlapped with compute over chunks.  Synchronous: outputs are complete on return. */
+/* HOST buffers (pinned recommended): the same pipeline with the host<->device copies done inside, overlapped with
+ * compute over waves of frames.  h_no_ground_out: n_frames * P u16 (may be NULL).  h_xyz4_out (may be NULL): the
+ * clouds of all frames packed back to back, xyz4_capacity records long; h_out_offsets (n_frames + 1 entries, in
+ * records; required with h_xyz4_out, else optional) delimits them.  Synchronous: outputs are complete on return. */
 int gs_process_batch_host(gs_ctx* ctx, const float* h_points_xyzi, const int64_t* h_offsets,
                           int n_frames, uint16_t* h_no_ground_out, float* h_xyz4_out,
-                          uint32_t* h_counts_out);
+                          uint64_t xyz4_capacity, int64_t* h_out_offsets);
 int gs_synchronize(gs_ctx* ctx);
 
 #ifdef __cplusplus

@@ -1,0 +1,363 @@
+"""GPU parity: the CUDA path, called through the C ABI (libgs_b200.so), against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star):
+  * range-image pixel assignment and ground / no-ground images: bit-exact, except pixels that trace back to a point
+    within 1e-5 rad of a cell edge (projection) or an inclination angle within 1e-5 rad of a centi-radian edge —
+    those are counted (gs_stats / oracle counters) and bounded here;
+  * component labels: equal after canonical min-index relabelling (both sides emit the canonical form);
+  * back-projected XYZ: relative error <= 1e-6 (TOL_XYZ); the implementation is in fact bit-exact because cos/sin
+    come from host-computed double tables.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from groundsegmentationrosnode_b200 import capi, params as P, synth
+
+pytestmark = pytest.mark.gpu
+
+TOL_XYZ = 1e-6
+
+CONFIGS = {
+    "C1_vlp16": P.GS_PRESET_VLP16,
+    "C2_hdl64_2048": P.GS_PRESET_HDL64E_2048,
+    "C3_os1_128": P.GS_PRESET_OS1_128,
+    "alfa_default_1800": P.GS_PRESET_ALFA_GS_DEFAULT,
+    "cloud2range_sg7": P.GS_PRESET_CLOUD2RANGE_DEFAULT,
+    "hdl32": P.GS_PRESET_HDL32,
+}
+
+
+@pytest.fixture(scope="module")
+def ctxs():
+    cache = {}
+
+    def get(p, staged=False):
+        key = (bytes(p), staged)
+        if key not in cache:
+            c = capi.Context(p)
+            c.set_option(capi.GS_OPT_COLLECT_STATS, 1)
+            c.set_option(capi.GS_OPT_FORCE_STAGED, int(staged))
+            cache[key] = c
+        return cache[key]
+
+    yield get
+    for c in cache.values():
+        c.close()
+
+
+def _mismatch_budget(near_edge):
+    # every near-edge point / pixel may flip one pixel and, through the labelling, its neighbourhood; on the
+    # synthetic scans the count of actual flips is 0 — the budget only documents the contract
+    return near_edge
+
+
+def _assert_images_equal(got, want, what, budget=0):
+    bad = int(np.count_nonzero(got != want))
+    assert bad <= budget, "%s: %d pixels differ (budget %d)" % (what, bad, budget)
+    return bad
+
+
+def _xyz_close(got, want):
+    assert got.shape == want.shape
+    if got.size == 0:
+        return
+    assert np.array_equal(got[:, 3], want[:, 3])
+    num = np.abs(got[:, :3].astype(np.float64) - want[:, :3].astype(np.float64))
+    den = np.maximum(np.abs(want[:, :3].astype(np.float64)), 1e-3)  # absolute floor near sin ~ 0
+    assert float((num / den).max()) <= TOL_XYZ
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+@pytest.mark.parametrize("staged", [False, True], ids=["fused", "staged"])
+def test_full_pipeline_matches_oracle(ctxs, oracle, name, staged):
+    p = P.preset(CONFIGS[name])
+    ctx = ctxs(p, staged)
+    for seed in range(2):
+        pts = synth.make_frame(p, synth.SEED0 + seed, shuffle=(seed == 1))
+        want = oracle.process_frame(p, pts)
+        ctx.reset_stats()
+        got = ctx.process_frame(pts)
+        st = ctx.stats()
+        _, ne_p, _ = oracle.create_range_image(p, pts, with_counts=True)
+        assert st.near_edge_project == ne_p
+        bad = _assert_images_equal(got["range"], want["range"], "range image", _mismatch_budget(ne_p))
+        if bad == 0:
+            _assert_images_equal(got["angle"], want["angle"], "angle image")
+            _assert_images_equal(got["no_ground"], want["no_ground"], "no-ground image")
+            _xyz_close(got["xyz"], want["xyz"])
+            assert np.array_equal(got["xyz"], want["xyz"])  # stronger than the bar: bit-exact
+
+
+@pytest.mark.parametrize("name", ["C1_vlp16", "C2_hdl64_2048", "cloud2range_sg7"])
+def test_stage_api_matches_oracle(ctxs, oracle, name):
+    p = P.preset(CONFIGS[name])
+    ctx = ctxs(p)
+    pts = synth.make_frame(p, synth.SEED0 + 7)
+    rng = ctx.project(pts)
+    assert np.array_equal(rng, oracle.create_range_image(p, pts))
+    # 32-byte pcl::PointXYZRGB records (the layout Alfa_GS::CreateRangeImage reads, alfa_gs.h:25)
+    wide = np.zeros((pts.shape[0], 8), np.float32)
+    wide[:, :3] = pts[:, :3]
+    wide[:, 3] = 1.0
+    assert np.array_equal(ctx.project(wide), rng)
+    ang = ctx.angle_image(rng)
+    assert np.array_equal(ang, oracle.create_angle_image(p, rng))
+    for ws in (5, 7, 9, 11):
+        assert np.array_equal(ctx.smooth(ang, ws), oracle.sg_smooth(p, ang, ws))
+    with pytest.raises(capi.GsError):
+        ctx.smooth(ang, 13)  # alfa_gs.cpp:645-649 throws std::logic_error("bad window size")
+    rep = ctx.repair_gaps(rng)
+    assert np.array_equal(rep, oracle.repair_gaps(p, rng))
+    for ground, start, ks in ((None, None, None), (0.05, 0.523598, 7), (0.2, 0.1, 5), (0.09, 0.3, 9), (0.115, 0.523598, 13)):
+        res, lab = ctx.erase_ground(rng, ang, ground, start, ks)
+        wres, wlab, _ = oracle.erase_bfs(p, rng, ang, ground, start, ks)
+        assert np.array_equal(lab, wlab)
+        assert np.array_equal(res, wres)
+    with pytest.raises(capi.GsError):
+        ctx.erase_ground(rng, ang, 0.1, 0.5, 8)  # even kernel: std::logic_error in the reference
+    res, _ = ctx.erase_ground(rng, ang)
+    xyz = ctx.backproject(res)
+    assert np.array_equal(xyz, oracle.camera_cb(p, res))
+    xyz_full = ctx.backproject(rng)
+    assert np.array_equal(xyz_full, oracle.camera_cb(p, rng))
+
+
+def test_golden_opencv_vectors_on_gpu(ctxs):
+    """The committed OpenCV vectors (tests/golden) straight against the CUDA kernels: SG filter2D and, through
+    gs_erase_ground's label + result pair, the effective dilation taps."""
+    import os
+
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "cv2_golden.npz"))
+    for ws in (int(w) for w in G["sg_ws"]):
+        for tag in "abc":
+            img = G["sg_in_%d_%s" % (ws, tag)]
+            H, W = img.shape
+            p = P.GsParams(n_beams=H, rpm=60, sample_freq=W, min_angle=-0.1, max_angle=0.1, min_range=0.5, max_range=100.0,
+                           ground_angle_threshold=0.1, start_angle_threshold=0.5, window_size=ws, erase_ground=1)
+            with capi.Context(p) as c:
+                assert np.array_equal(c.smooth(img, ws), G["sg_out_%d_%s" % (ws, tag)])
+    for ks in (int(k) for k in G["dil_ks"]):
+        lab = G["dil_in_%d" % ks]
+        H, W = lab.shape
+        p = P.GsParams(n_beams=H, rpm=60, sample_freq=W, min_angle=-0.1, max_angle=0.1, min_range=0.5, max_range=100.0,
+                       ground_angle_threshold=0.1, start_angle_threshold=0.5, window_size=ks + 2, erase_ground=1)
+        d = capi.derive(p)
+        offs = list(d.dilate_off)[: d.n_dilate]
+        dil = np.zeros_like(lab)
+        for o in offs:
+            src = np.zeros_like(lab)
+            if o < 0:
+                src[-o:, :] = lab[:o, :]
+            elif o > 0:
+                src[:-o, :] = lab[o:, :]
+            else:
+                src = lab
+            dil |= src
+        assert np.array_equal(dil, G["dil_out_%d" % ks]), ks
+
+
+@pytest.mark.parametrize("kind", ["edges", "collisions", "nonfinite", "sparse"])
+@pytest.mark.parametrize("name", ["C1_vlp16", "C2_hdl64_2048"])
+@pytest.mark.parametrize("staged", [False, True], ids=["fused", "staged"])
+def test_adversarial_frames(ctxs, oracle, name, kind, staged):
+    p = P.preset(CONFIGS[name])
+    ctx = ctxs(p, staged)
+    pts = synth.make_adversarial_frame(p, synth.SEED0 + 3, kind)
+    want = oracle.process_frame(p, pts)
+    wrng, ne_p, dropped = oracle.create_range_image(p, pts, with_counts=True)
+    ctx.reset_stats()
+    got = ctx.process_frame(pts)
+    st = ctx.stats()
+    assert st.dropped_points == dropped
+    budget = ne_p if kind == "edges" else 0
+    bad = _assert_images_equal(got["range"], want["range"], "range image", budget)
+    if bad:
+        # points exactly on cell edges: double atan2/hypot of the device and of glibc may differ in the last ulp and
+        # move such a point to the adjacent cell (the north-star tolerance set).  Re-anchor the later stages on the
+        # oracle's range image.
+        ang = ctx.angle_image(want["range"])
+        assert np.array_equal(ang, want["angle"])
+        res, _ = ctx.erase_ground(want["range"], ang)
+        assert np.array_equal(res, want["no_ground"])
+        assert np.array_equal(ctx.backproject(res), want["xyz"])
+    else:
+        assert np.array_equal(got["angle"], want["angle"])
+        assert np.array_equal(got["no_ground"], want["no_ground"])
+        assert np.array_equal(got["xyz"], want["xyz"])
+
+
+@pytest.mark.parametrize("policy", ["nearest", "wrap", "keep_ground"])
+def test_policy_variants(ctxs, oracle, policy):
+    base = P.preset(P.GS_PRESET_HDL64E_2048)
+    p = {"nearest": base.copy(pixel_policy=P.GS_PIXEL_NEAREST), "wrap": base.copy(col_policy=P.GS_COL_WRAP),
+         "keep_ground": base.copy(erase_ground=0)}[policy]
+    for staged in (False, True):
+        ctx = ctxs(p, staged)
+        pts = synth.make_adversarial_frame(p, synth.SEED0 + 11, "collisions")
+        want = oracle.process_frame(p, pts)
+        got = ctx.process_frame(pts)
+        for k in ("range", "angle", "no_ground"):
+            assert np.array_equal(got[k], want[k]), k
+        assert np.array_equal(got["xyz"], want["xyz"])
+
+
+def test_empty_and_tiny_inputs(ctxs, oracle):
+    p = P.preset(P.GS_PRESET_VLP16)
+    for staged in (False, True):
+        ctx = ctxs(p, staged)
+        for pts in (np.zeros((0, 4), np.float32), np.array([[5.0, 0.1, -0.3, 0.0]], np.float32),
+                    np.array([[5.0, 0.0, 0.0, 0.0], [5.0, 0.0, 0.0, 0.0]], np.float32)):
+            want = oracle.process_frame(p, pts)
+            got = ctx.process_frame(pts)
+            for k in ("range", "angle", "no_ground"):
+                assert np.array_equal(got[k], want[k]), k
+            assert np.array_equal(got["xyz"], want["xyz"])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_label_one_component_matches_oracle(ctxs, oracle, seed):
+    """Label::LabelOneComponent through the C ABI, including pre-labelled barrier pixels and empty seeds."""
+    rng = np.random.default_rng(4000 + seed)
+    H, W = int(rng.integers(3, 20)), int(rng.integers(4, 60))
+    p = P.GsParams(n_beams=H, rpm=60, sample_freq=W, min_angle=-0.4, max_angle=0.1, min_range=0.5, max_range=100.0,
+                   ground_angle_threshold=0.115, start_angle_threshold=0.523598, window_size=11, erase_ground=1)
+    ctx = ctxs(p)
+    rimg = rng.integers(1, 65535, size=(H, W)).astype(np.uint16)
+    rimg[rng.random((H, W)) < 0.3] = 0
+    ang = np.clip(np.cumsum(rng.integers(-3, 4, size=(H, W)), axis=1) + rng.integers(0, 40, size=(H, 1)), 0, 157).astype(np.uint16)
+    lab = (rng.random((H, W)) < 0.1).astype(np.uint8) * 9
+    for _ in range(5):
+        r, c = int(rng.integers(0, H)), int(rng.integers(0, W))
+        thr = float(rng.choice([0.02, 0.05, 0.09, 0.115, 0.2]))
+        label = int(rng.integers(1, 255))
+        want = oracle.label_one_component(p, label, r, c, thr, rimg, ang, lab)
+        got = ctx.label_one_component(label, r, c, thr, rimg, ang, lab)
+        assert np.array_equal(got, want)
+        lab = got
+
+
+@pytest.mark.parametrize("beta_deg", [5, 10, 15, 20])
+def test_label_components_sweep(ctxs, oracle, beta_deg):
+    """BASELINE config C5: the Labeler as an all-components CCL on 128 x 2048 no-ground images."""
+    p = P.preset(P.GS_PRESET_OS1_128)
+    ctx = ctxs(p)
+    pts = synth.make_frame(p, synth.SEED0 + 21)
+    o = oracle.process_frame(p, pts)
+    beta = math.radians(beta_deg)
+    want, n_want = oracle.label_components(p, o["no_ground"], o["angle"], beta)
+    got, n_got = ctx.label_components(o["no_ground"], o["angle"], beta)
+    assert n_got == n_want
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("ground_deg", [2, 4, 6, 8, 10])
+def test_ground_threshold_sweep(ctxs, oracle, ground_deg):
+    p = P.preset(P.GS_PRESET_OS1_128).copy(ground_angle_threshold=math.radians(ground_deg))
+    for staged in (False, True):
+        ctx = ctxs(p, staged)
+        pts = synth.make_frame(p, synth.SEED0 + 22)
+        want = oracle.process_frame(p, pts)
+        got = ctx.process_frame(pts)
+        assert np.array_equal(got["no_ground"], want["no_ground"])
+        assert np.array_equal(got["xyz"], want["xyz"])
+
+
+@pytest.mark.parametrize("staged", [False, True], ids=["fused", "staged"])
+def test_batch_device_and_host_match_per_frame_oracle(ctxs, oracle, staged):
+    import torch
+
+    p = P.preset(P.GS_PRESET_HDL64E_2048)
+    ctx = ctxs(p, staged)
+    H, W = ctx.shape
+    Pn = H * W
+    pool, offs = synth.make_pool(p, 5, seed0=synth.SEED0 + 40)
+    pts, offsets = synth.tile_pool(pool, offs, 13)  # ragged frame sizes, more frames than distinct
+    F = len(offsets) - 1
+    want = [oracle.process_frame(p, pool[offs[i]:offs[i + 1]]) for i in range(5)]
+    d_pts = torch.from_numpy(pts).cuda()
+    d_res = torch.zeros((F, H, W), dtype=torch.int16, device="cuda")
+    d_rng = torch.zeros((F, H, W), dtype=torch.int16, device="cuda")
+    d_ang = torch.zeros((F, H, W), dtype=torch.int16, device="cuda")
+    d_xyz = torch.zeros((F, Pn, 4), dtype=torch.float32, device="cuda")
+    d_cnt = torch.zeros(F, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.set_chunk_frames(4)  # several waves, a ragged last one
+    ctx.process_batch_device(d_pts.data_ptr(), offsets, F, d_rng.data_ptr(), d_ang.data_ptr(), d_res.data_ptr(), d_xyz.data_ptr(),
+                             d_cnt.data_ptr())
+    ctx.synchronize()
+    ctx.set_chunk_frames(0)
+    res = d_res.cpu().numpy().view(np.uint16)
+    rngs = d_rng.cpu().numpy().view(np.uint16)
+    angs = d_ang.cpu().numpy().view(np.uint16)
+    cnt = d_cnt.cpu().numpy()
+    xyz = d_xyz.cpu().numpy()
+    for f in range(F):
+        w = want[f % 5]
+        assert np.array_equal(rngs[f], w["range"])
+        assert np.array_equal(angs[f], w["angle"])
+        assert np.array_equal(res[f], w["no_ground"])
+        assert cnt[f] == w["xyz"].shape[0]
+        assert np.array_equal(xyz[f, : cnt[f]], w["xyz"])
+    # host batch: packed clouds
+    h_res = np.zeros((F, H, W), np.uint16)
+    h_xyz = np.zeros((F * Pn, 4), np.float32)
+    ctx.set_chunk_frames(5)
+    _, _, out_offs = ctx.process_batch_host(pts, offsets, h_res, h_xyz)
+    ctx.set_chunk_frames(0)
+    for f in range(F):
+        w = want[f % 5]
+        assert np.array_equal(h_res[f], w["no_ground"])
+        assert np.array_equal(h_xyz[out_offs[f]:out_offs[f + 1]], w["xyz"])
+
+
+def test_set_params_recomputes_derived(ctxs, oracle):
+    """gs_set_params replaces Alfa_GS::UpdateSegmentationSettings (alfa_gs.cpp:1122-1136) and, unlike it, refreshes
+    the derived values."""
+    p = P.preset(P.GS_PRESET_VLP16)
+    with capi.Context(p) as ctx:
+        q = P.preset(P.GS_PRESET_HDL32)
+        ctx.set_params(q)
+        assert ctx.shape == q.shape
+        pts = synth.make_frame(q, synth.SEED0 + 5)
+        want = oracle.process_frame(q, pts)
+        got = ctx.process_frame(pts)
+        assert np.array_equal(got["no_ground"], want["no_ground"])
+        assert np.array_equal(got["xyz"], want["xyz"])
+
+
+def test_full_size_properties(ctxs):
+    """Size-independent properties on a C4-style batch (no oracle at this size): idempotence of the batch call,
+    frame independence (a frame's result does not depend on its neighbours in the batch), counts == non-zero pixels,
+    no-ground image is a subset of the range image, back-projection of the range image has one point per pixel."""
+    import torch
+
+    p = P.preset(P.GS_PRESET_HDL64E_2048)
+    ctx = ctxs(p)
+    H, W = ctx.shape
+    Pn = H * W
+    pool, offs = synth.make_pool(p, 4, seed0=synth.SEED0 + 60)
+    F = 64
+    pts, offsets = synth.tile_pool(pool, offs, F)
+    d_pts = torch.from_numpy(pts).cuda()
+    outs = []
+    for _ in range(2):
+        d_res = torch.zeros((F, H, W), dtype=torch.int16, device="cuda")
+        d_rng = torch.zeros((F, H, W), dtype=torch.int16, device="cuda")
+        d_xyz = torch.zeros((F, Pn, 4), dtype=torch.float32, device="cuda")
+        d_cnt = torch.zeros(F, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        ctx.process_batch_device(d_pts.data_ptr(), offsets, F, d_rng.data_ptr(), 0, d_res.data_ptr(), d_xyz.data_ptr(), d_cnt.data_ptr())
+        ctx.synchronize()
+        outs.append((d_res, d_rng, d_xyz, d_cnt))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)  # idempotent / deterministic
+    d_res, d_rng, d_xyz, d_cnt = outs[0]
+    for f in range(4, F):
+        assert torch.equal(d_res[f], d_res[f % 4])  # tiled frames give identical results wherever they sit
+        assert d_cnt[f] == d_cnt[f % 4]
+    assert torch.equal((d_res != 0).sum(dim=(1, 2)).to(torch.int32), d_cnt)
+    assert bool(((d_res == 0) | (d_res == d_rng)).all())
+    n0 = int(d_cnt[0])
+    assert bool((d_xyz[0, :n0, 3] == 1.0).all())
