@@ -1,14 +1,948 @@
-// gs_fused.cu — placeholder: the fused single-kernel pipeline is not built yet; every call routes to the staged kernels.
+// gs_fused.cu — the whole path  cloud -> range image -> angle image -> ground mask -> cloud  as ONE persistent kernel.
+//
+// A thread-block cluster owns one frame at a time; CTA `rank` of the cluster owns the column slab
+// [rank*CW, rank*CW + CW) of the range image and keeps it in shared memory from the projection to the
+// back-projection, so that per frame HBM sees exactly the algorithmic bytes: 16 B per input point, 2 B per pixel of
+// the no-ground image, 16 B per surviving point.  Nothing in between (pixel owners, range image, angle
+// image, label image, dilation, row counts) ever leaves the SMs.
+//
+// Stages inside the kernel (reference file:line):
+//   P  projection            Alfa_GS::CreateRangeImage  src/alfa_gs.cpp:247-298, lib/utils.h:8-43  (variant:
+//                            Cloud2RangeNode::CloudCb src/cloud2range_node.cpp:396-455)
+//   A  angle image           Alfa_GS::CreateAngleImg    src/alfa_gs.cpp:335-386
+//   G  ground labelling      Alfa_GS::EraseBFS seeds :720-739 + Label::LabelOneComponent Labeler/label.cpp:48-104,
+//                            restated as bit-parallel flood fill over per-column row masks
+//   D  dilate + erase        GetUniformKernel + cv::dilate + erase  src/alfa_gs.cpp:747-764
+//   B  back-projection       Alfa_GS::CameraCb  src/alfa_gs.cpp:997-1074 (variant: range2cloud_node.cpp:64-91)
+//
+// Pixel ownership ("the last point in input order wins", alfa_gs.cpp:291) without atomics on the common path: every
+// group of 32 consecutive points carries the order tag g = index/32 + 1; lanes that hit the same pixel inside a warp
+// are resolved with __match_any_sync (highest lane wins); across warps a pixel's 16-bit tag in shared memory is raised
+// by plain stores, verified after a barrier (compare-and-swap only for the rare lost race), and the winner then stores
+// its range.  Blocks of 256 points are dealt to the CTA predicted (from 4 sampled points) to own their columns, so for
+// ordered clouds (sensor firing order or row-major organised) almost every store is CTA-local; the rest go through a
+// small remote list that is applied over distributed shared memory after the local rounds.
+#include <cooperative_groups.h>
+#include <math_constants.h>
+
 #include "gs_internal.h"
+#include "gs_math.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace gs {
-int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const SgTaps& sg, bool smooth, bool repair, int) {
-    fs.kp = kp; fs.lut = lut; fs.sg = sg; fs.smooth = smooth; fs.repair = repair; fs.configured = false;
+
+namespace {
+
+constexpr int NT = 1024;        // threads per CTA
+constexpr int NPT = 2;          // points per thread per round
+constexpr int BLK = 256;        // points per dealt block
+constexpr int MAX_BLOCKS = 4096;  // per frame: up to 1 Mi points
+constexpr int MAX_CL = 8;
+constexpr int MAX_H = 128;
+
+struct FusedArgs {
+    KParams kp;
+    Luts lut;
+    int CL, CW;   // CTAs per frame, columns per CTA (the last CTA may own fewer)
+    int S16;      // row stride of the range / tag slabs, u16 elements
+    int S8;       // row stride of the angle slab, bytes
+    int NG;       // 32-column groups per slab
+    // shared memory offsets (bytes)
+    unsigned off_range, off_tag, off_angle, off_misc;
+    const float4* points;
+    const long long* offsets;
+    int frames;
+    uint16_t* range_out;
+    uint16_t* angle_out;
+    uint16_t* res_out;
+    float4* xyz_out;
+    unsigned* counts_out;
+    Counters* cnt;
+    int stats;
+    uint2* rlist;        // [clusters][CL][rcap] remote records
+    unsigned* rcount;    // [clusters][CL]
+    unsigned rcap;
+};
+
+// ---- small helpers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double decode_range_d(const KParams& kp, unsigned enc) {
+    // static_cast<double>(enc - 1) / 65534 * (max_range - min_range) + min_range   (alfa_gs.cpp:359-360, :1042-1045)
+    const double norm = __ddiv_rn(static_cast<double>(static_cast<int>(enc) - 1), 65534.0);
+    return __dadd_rn(__dmul_rn(norm, kp.span), kp.min_range);
+}
+
+__device__ __forceinline__ void cas_max_u16(uint16_t* p, unsigned v) {
+    // raises the 16-bit word *p to at least v (shared or distributed shared memory)
+    unsigned* w = reinterpret_cast<unsigned*>(reinterpret_cast<uintptr_t>(p) & ~static_cast<uintptr_t>(3));
+    const int sh = (reinterpret_cast<uintptr_t>(p) & 2) ? 16 : 0;
+    unsigned old = *w;
+    for (;;) {
+        const unsigned cur = (old >> sh) & 0xffffu;
+        if (cur >= v) return;
+        const unsigned want = (old & ~(0xffffu << sh)) | (v << sh);
+        const unsigned got = atomicCAS(w, old, want);
+        if (got == old) return;
+        old = got;
+    }
+}
+
+// Row masks: bit r of the 128-bit mask <-> image row r.
+struct M128 {
+    unsigned long long lo, hi;
+};
+template <int NW>
+struct Mask;
+template <>
+struct Mask<1> {
+    unsigned long long w0;
+    __device__ __forceinline__ static Mask zero() { return Mask{0ull}; }
+    __device__ __forceinline__ bool any() const { return w0 != 0; }
+    __device__ __forceinline__ Mask operator|(Mask o) const { return Mask{w0 | o.w0}; }
+    __device__ __forceinline__ Mask operator&(Mask o) const { return Mask{w0 & o.w0}; }
+    __device__ __forceinline__ Mask operator^(Mask o) const { return Mask{w0 ^ o.w0}; }
+    __device__ __forceinline__ Mask operator~() const { return Mask{~w0}; }
+    __device__ __forceinline__ bool operator!=(Mask o) const { return w0 != o.w0; }
+    __device__ __forceinline__ Mask shl(int k) const { return Mask{k >= 64 ? 0ull : w0 << k}; }
+    __device__ __forceinline__ Mask shr(int k) const { return Mask{k >= 64 ? 0ull : w0 >> k}; }
+    __device__ __forceinline__ Mask add(Mask o) const { return Mask{w0 + o.w0}; }
+    __device__ __forceinline__ Mask rev() const { return Mask{__brevll(w0)}; }
+    __device__ __forceinline__ bool bit(int r) const { return (w0 >> r) & 1ull; }
+    __device__ __forceinline__ void set(int r) { w0 |= 1ull << r; }
+    __device__ __forceinline__ int top() const { return w0 ? 63 - __clzll(w0) : -1; }
+    __device__ __forceinline__ unsigned word32(int i) const { return static_cast<unsigned>(w0 >> (32 * i)); }
+    __device__ __forceinline__ static Mask low(int n) { return Mask{n >= 64 ? ~0ull : ((1ull << n) - 1ull)}; }
+};
+template <>
+struct Mask<2> {
+    unsigned long long w0, w1;
+    __device__ __forceinline__ static Mask zero() { return Mask{0ull, 0ull}; }
+    __device__ __forceinline__ bool any() const { return (w0 | w1) != 0; }
+    __device__ __forceinline__ Mask operator|(Mask o) const { return Mask{w0 | o.w0, w1 | o.w1}; }
+    __device__ __forceinline__ Mask operator&(Mask o) const { return Mask{w0 & o.w0, w1 & o.w1}; }
+    __device__ __forceinline__ Mask operator^(Mask o) const { return Mask{w0 ^ o.w0, w1 ^ o.w1}; }
+    __device__ __forceinline__ Mask operator~() const { return Mask{~w0, ~w1}; }
+    __device__ __forceinline__ bool operator!=(Mask o) const { return w0 != o.w0 || w1 != o.w1; }
+    __device__ __forceinline__ Mask shl(int k) const {
+        if (k == 0) return *this;
+        if (k >= 128) return zero();
+        if (k >= 64) return Mask{0ull, w0 << (k - 64)};
+        return Mask{w0 << k, (w1 << k) | (w0 >> (64 - k))};
+    }
+    __device__ __forceinline__ Mask shr(int k) const {
+        if (k == 0) return *this;
+        if (k >= 128) return zero();
+        if (k >= 64) return Mask{w1 >> (k - 64), 0ull};
+        return Mask{(w0 >> k) | (w1 << (64 - k)), w1 >> k};
+    }
+    __device__ __forceinline__ Mask add(Mask o) const {
+        const unsigned long long lo = w0 + o.w0;
+        return Mask{lo, w1 + o.w1 + (lo < w0 ? 1ull : 0ull)};
+    }
+    __device__ __forceinline__ Mask rev() const { return Mask{__brevll(w1), __brevll(w0)}; }
+    __device__ __forceinline__ bool bit(int r) const { return ((r < 64 ? w0 >> r : w1 >> (r - 64)) & 1ull) != 0; }
+    __device__ __forceinline__ void set(int r) {
+        if (r < 64) w0 |= 1ull << r;
+        else w1 |= 1ull << (r - 64);
+    }
+    __device__ __forceinline__ int top() const { return w1 ? 127 - __clzll(w1) : (w0 ? 63 - __clzll(w0) : -1); }
+    __device__ __forceinline__ unsigned word32(int i) const { return static_cast<unsigned>((i < 2 ? w0 : w1) >> (32 * (i & 1))); }
+    __device__ __forceinline__ static Mask low(int n) {
+        if (n >= 128) return Mask{~0ull, ~0ull};
+        if (n >= 64) return Mask{~0ull, n == 64 ? 0ull : ((1ull << (n - 64)) - 1ull)};
+        return Mask{(1ull << n) - 1ull, 0ull};
+    }
+};
+
+// All pixels joined to a seed in g through chains of set link bits: link bit r joins rows r and r+1.  The carry of
+// one addition walks up a whole run of links ((A + c) ^ A), bit reversal gives the downward direction.
+template <int NW>
+__device__ __forceinline__ Mask<NW> fill_up(Mask<NW> g, Mask<NW> linked_to_prev) {
+    const Mask<NW> c = g.shl(1) & linked_to_prev;
+    return g | c | ((linked_to_prev.add(c) ^ linked_to_prev) & linked_to_prev);
+}
+template <int NW>
+__device__ __forceinline__ Mask<NW> vfill(Mask<NW> g, Mask<NW> link, int H) {
+    // upward (towards higher row index): pixel r is linked to its predecessor r-1 by link bit r-1
+    const Mask<NW> up = fill_up<NW>(g, link.shl(1));
+    // downward: reverse the bit order; pixel r's predecessor in reversed order is r+1, joined by link bit r.
+    // rev() maps bit r -> (64*NW - 1 - r).
+    const Mask<NW> dn = fill_up<NW>(g.rev(), link.rev()).rev();
+    return (up | dn) & Mask<NW>::low(H);
+}
+
+// mask storage in shared memory: [kind][word][column], u64 words
+enum { MK_VALID = 0, MK_VA, MK_HA, MK_V, MK_HM, MK_G, MK_KEEP, MK_COUNT };
+
+template <int NW>
+__device__ __forceinline__ Mask<NW> ld_mask(const unsigned long long* base, int kind, int CWp, int c) {
+    Mask<NW> m;
+    m.w0 = base[(kind * NW + 0) * CWp + c];
+    if constexpr (NW == 2) m.w1 = base[(kind * NW + 1) * CWp + c];
+    return m;
+}
+template <int NW>
+__device__ __forceinline__ void st_mask(unsigned long long* base, int kind, int CWp, int c, Mask<NW> m) {
+    base[(kind * NW + 0) * CWp + c] = m.w0;
+    if constexpr (NW == 2) base[(kind * NW + 1) * CWp + c] = m.w1;
+}
+
+// ---- projection of one point (double precision, the reference's operation order) ---------------------------------
+struct Proj {
+    int row, col;   // col may equal W for the alfa_gs variant (flat alias), row/col = -1 when dropped
+    unsigned enc;
+    bool near_edge;
+};
+
+__device__ __forceinline__ Proj project_point_d(const KParams& kp, float fx, float fy, float fz) {
+    Proj out;
+    out.row = -1;
+    out.col = -1;
+    out.enc = 0;
+    out.near_edge = false;
+    if (!(isfinite(fx) && isfinite(fy) && isfinite(fz))) return out;  // contract Q3
+    const double x = fx, y = fy, z = fz;
+    const double range = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));  // utils.h:41-43
+    if (range < kp.min_range || range > kp.max_range) return out;                                             // alfa_gs.cpp:261
+    const double a = atan2(y, x);
+    const double azimuth = (y >= 0 ? a : __dadd_rn(a, 6.283185307179586476925286766559));  // utils.h:24-28
+    const double altitude = atan2(z, hypot(x, y));                                        // utils.h:8-11
+    if (altitude < kp.min_angle || altitude > kp.max_angle) return out;                   // alfa_gs.cpp:269
+    double rowf, colf;
+    if (kp.variant == GS_VARIANT_CLOUD2RANGE) {
+        rowf = __dmul_rn(__ddiv_rn(__dsub_rn(kp.max_angle, altitude), kp.ang_span), static_cast<double>(kp.H));  // cloud2range_node.cpp:436
+        colf = __ddiv_rn(azimuth, kp.d_az);                                                                      // :438
+    } else {
+        rowf = __dsub_rn(static_cast<double>(kp.H - 1),
+                         __ddiv_rn(__dsub_rn(__dsub_rn(altitude, kp.half_d_alt), kp.min_angle), kp.d_alt));  // alfa_gs.cpp:275
+        colf = __ddiv_rn(__dadd_rn(azimuth, kp.half_d_az), kp.d_az);                                         // :277
+    }
+    if (!(colf >= 0.0)) return out;  // contract Q3: y = -0.0, x < 0
+    const int row = __double2int_rz(rowf);
+    int col = __double2int_rz(colf);
+    {
+        const double fr = rowf - floor(rowf), fc = colf - floor(colf);
+        const double cell_alt = (kp.variant == GS_VARIANT_CLOUD2RANGE) ? kp.ang_span / kp.H : kp.d_alt;
+        out.near_edge = fmin(fr, 1.0 - fr) * cell_alt < 1e-5 || fmin(fc, 1.0 - fc) * kp.d_az < 1e-5;
+    }
+    if (row < 0 || row >= kp.H) return out;  // Q4
+    if (kp.variant == GS_VARIANT_CLOUD2RANGE) {
+        if (col >= kp.W) return out;
+    } else if (kp.col_policy == GS_COL_WRAP) {
+        col %= kp.W;
+    } else {
+        if (col > kp.W || (col == kp.W && row == kp.H - 1)) return out;  // Q2: flat index past the end of the image
+    }
+    const double range_norm = __ddiv_rn(__dsub_rn(range, kp.min_range), kp.span);  // alfa_gs.cpp:288
+    out.enc = static_cast<unsigned>(__double2int_rz(__dadd_rn(__dmul_rn(range_norm, 65534.0), 1.0)));  // :291
+    out.row = row;
+    out.col = col;
+    return out;
+}
+
+// cheap column estimate used only to deal point blocks to CTAs (any answer is correct, a good one is fast)
+__device__ __forceinline__ int approx_col(const KParams& kp, float x, float y) {
+    float a = atan2f(y, x);
+    if (a < 0.0f) a += 6.2831853f;
+    const float half = kp.variant == GS_VARIANT_CLOUD2RANGE ? 0.0f : 0.5f;
+    int c = static_cast<int>(a / static_cast<float>(kp.d_az) + half);
+    return min(max(c, 0), kp.W - 1);
+}
+
+struct Smem {
+    uint16_t* range;
+    uint16_t* tag;
+    uint8_t* angle;
+    unsigned long long* masks;  // aliases tag (dead after the projection)
+    unsigned* rowmask;          // [H][NG]   after masks
+    unsigned* grp_prefix;       // [H][NG]
+    unsigned* rowcnt_all;       // [MAX_CL][H]  written by every CTA of the cluster
+    unsigned* rowbase;          // [H]
+    uint8_t* assign;            // aliases angle (dead during the projection)
+    uint16_t* mylist;           // after assign
+    unsigned char* halo;        // fixed area: halo angle column [H]
+    unsigned long long* halo_masks;  // [4][NW]: right neighbour VALID, right neighbour G, left neighbour G, left neighbour HM, left neighbour HA
+    unsigned* flags;            // [MAX_CL] + misc counters
+};
+
+}  // namespace
+
+// ====================================================================================================================
+// the kernel
+// ====================================================================================================================
+template <int NW>
+__global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const KParams& kp = A.kp;
+    const int CL = A.CL, CW = A.CW, H = kp.H, W = kp.W;
+    const int rank = static_cast<int>(cluster.block_rank());
+    const int cluster_id = blockIdx.x / CL;
+    const int n_clusters = gridDim.x / CL;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int col0 = rank * CW;                 // first global column of my slab
+    const int myCW = min(CW, W - col0);         // columns I own (> 0 by construction)
+    const int S16 = A.S16, S8 = A.S8, NG = A.NG;
+    const int CWp = CW;                         // mask arrays are CW wide
+
+    // ---- shared memory carve-up
+    uint16_t* s_range = reinterpret_cast<uint16_t*>(smem_raw + A.off_range);
+    uint16_t* s_tag = reinterpret_cast<uint16_t*>(smem_raw + A.off_tag);
+    uint8_t* s_angle = smem_raw + A.off_angle;
+    unsigned long long* s_masks = reinterpret_cast<unsigned long long*>(smem_raw + A.off_tag);           // [MK_COUNT][NW][CW]
+    unsigned* s_rowmask = reinterpret_cast<unsigned*>(s_masks + static_cast<size_t>(MK_COUNT) * NW * CWp);  // [H][NG]
+    unsigned* s_grp = s_rowmask + H * NG;                                                                  // [H][NG]
+    uint8_t* s_assign = s_angle;                                                                           // [MAX_BLOCKS]
+    uint16_t* s_mylist = reinterpret_cast<uint16_t*>(s_angle + MAX_BLOCKS);                                // [MAX_BLOCKS]
+    unsigned char* misc = smem_raw + A.off_misc;
+    unsigned* s_rowcnt_all = reinterpret_cast<unsigned*>(misc);                         // [MAX_CL][MAX_H]
+    unsigned* s_rowbase = s_rowcnt_all + MAX_CL * MAX_H;                                // [MAX_H]
+    unsigned long long* s_halo_masks = reinterpret_cast<unsigned long long*>(s_rowbase + MAX_H);  // [5][2]
+    uint8_t* s_halo_angle = reinterpret_cast<uint8_t*>(s_halo_masks + 10);              // [MAX_H]
+    unsigned* s_flags = reinterpret_cast<unsigned*>(s_halo_angle + MAX_H);              // [MAX_CL]
+    unsigned* s_misc = s_flags + MAX_CL;                                                // [0] nmine, [1] scratch
+
+    uint2* rlist = A.rlist + (static_cast<size_t>(cluster_id) * CL + rank) * A.rcap;
+    unsigned* rcount = A.rcount + static_cast<size_t>(cluster_id) * CL;
+
+    unsigned long long st_dropped = 0, st_near = 0, st_near_angle = 0, st_remote = 0;
+
+    for (int f = cluster_id; f < A.frames; f += n_clusters) {
+        const long long beg = A.offsets[f], end = A.offsets[f + 1];
+        const int N = static_cast<int>(end - beg);
+        const int nb = (N + BLK - 1) / BLK;
+        const float4* pts = A.points + beg;
+
+        // ================================================================================ P0: clear + deal blocks
+        {
+            uint4* r4 = reinterpret_cast<uint4*>(s_range);
+            const int n16 = (H * S16 * 2 + 15) / 16;
+            for (int i = tid; i < n16; i += NT) r4[i] = make_uint4(0, 0, 0, 0);
+            uint4* t4 = reinterpret_cast<uint4*>(s_tag);
+            for (int i = tid; i < n16; i += NT) t4[i] = make_uint4(0, 0, 0, 0);
+        }
+        for (int b = tid; b < nb; b += NT) {
+            // owner vote over 4 sampled points of the block
+            int votes[MAX_CL];
+#pragma unroll
+            for (int k = 0; k < MAX_CL; ++k) votes[k] = 0;
+            const int base = b * BLK;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = min(base + 32 + 64 * k, N - 1);
+                const float4 q = __ldg(pts + i);
+                const int o = min(approx_col(kp, q.x, q.y) / CW, CL - 1);
+#pragma unroll
+                for (int j = 0; j < MAX_CL; ++j) votes[j] += (j == o);
+            }
+            int best = 0;
+#pragma unroll
+            for (int j = 1; j < MAX_CL; ++j)
+                if (votes[j] > votes[best]) best = j;
+            s_assign[b] = static_cast<uint8_t>(best);
+        }
+        if (tid == 0) rcount[rank] = 0;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned n = 0;
+            for (int b0 = 0; b0 < nb; b0 += 32) {
+                const int b = b0 + lane;
+                const bool mine = b < nb && s_assign[b] == rank;
+                const unsigned m = __ballot_sync(0xffffffffu, mine);
+                if (mine) s_mylist[n + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(b);
+                n += __popc(m);
+            }
+            if (lane == 0) s_misc[0] = n;
+        }
+        __syncthreads();
+        const int nmine = static_cast<int>(s_misc[0]);
+
+        // ================================================================================ P1: local rounds
+        for (int qb = 0; qb < nmine * BLK; qb += NT * NPT) {
+            unsigned key[NPT], val[NPT];  // key: owner << 16 | slab address (0xffffffff = nothing to store); val: g << 16 | enc
+#pragma unroll
+            for (int j = 0; j < NPT; ++j) {
+                key[j] = 0xffffffffu;
+                val[j] = 0;
+                const int q = qb + j * NT + tid;
+                int i = -1;
+                if (q < nmine * BLK) {
+                    i = static_cast<int>(s_mylist[q >> 8]) * BLK + (q & (BLK - 1));
+                    if (i >= N) i = -1;
+                }
+                unsigned k = 0x80000000u | lane;  // unique per lane: never matches
+                if (i >= 0) {
+                    const float4 p4 = __ldcs(pts + i);
+                    const Proj pr = project_point_d(kp, p4.x, p4.y, p4.z);
+                    if (A.stats) {
+                        if (pr.row < 0) ++st_dropped;
+                        else if (pr.near_edge) ++st_near;
+                    }
+                    if (pr.row >= 0) {
+                        int row = pr.row, col = pr.col;
+                        if (col == W) {  // Q2: at<ushort>(row, W) is flat index (row + 1) * W
+                            row += 1;
+                            col = 0;
+                        }
+                        const int owner = min(col / CW, CL - 1);
+                        const int lc = col - owner * CW;
+                        k = (static_cast<unsigned>(owner) << 16) | static_cast<unsigned>(row * S16 + lc);
+                        val[j] = ((static_cast<unsigned>(i >> 5) + 1u) << 16) | pr.enc;
+                    }
+                }
+                // the highest lane among the lanes that hit the same pixel holds the latest point of this group
+                const unsigned peers = __match_any_sync(0xffffffffu, k);
+                const bool winner = !(k & 0x80000000u) && (31 - __clz(peers)) == lane;
+                if (winner) {
+                    const int owner = static_cast<int>(k >> 16);
+                    if (owner == rank) {
+                        key[j] = k & 0xffffu;
+                        const unsigned g = val[j] >> 16;
+                        uint16_t* t = s_tag + key[j];
+                        if (*t < g) *t = static_cast<uint16_t>(g);
+                    }
+                }
+                // remote pixels: queue the record (warp-aggregated slot claim)
+                const bool remote = winner && static_cast<int>(k >> 16) != rank;
+                const unsigned rm = __ballot_sync(0xffffffffu, remote);
+                if (rm) {
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(&rcount[rank], __popc(rm));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (remote) {
+                        const unsigned slot = base + __popc(rm & ((1u << lane) - 1u));
+                        if (slot < A.rcap) rlist[slot] = make_uint2(k, val[j]);
+                        if (A.stats) ++st_remote;
+                    }
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < NPT; ++j)
+                if (key[j] != 0xffffffffu) {
+                    const unsigned g = val[j] >> 16;
+                    uint16_t* t = s_tag + key[j];
+                    if (*t < g) cas_max_u16(t, g);  // lost a same-round race to an earlier point
+                }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < NPT; ++j)
+                if (key[j] != 0xffffffffu && s_tag[key[j]] == (val[j] >> 16)) s_range[key[j]] = static_cast<uint16_t>(val[j] & 0xffffu);
+        }
+        __threadfence();  // remote records and counts visible before the cluster-wide phase
+        cluster.sync();   // #1: all local pixels committed everywhere
+
+        // ================================================================================ P2: remote records
+        {
+            unsigned n_any = 0;
+            for (int k = 0; k < CL; ++k) n_any |= __ldcg(&rcount[k]);
+            if (n_any) {
+                const unsigned n = min(__ldcg(&rcount[rank]), A.rcap);
+                for (unsigned i = tid; i < n; i += NT) {
+                    const uint2 rec = __ldcg(&rlist[i]);
+                    uint16_t* t = cluster.map_shared_rank(s_tag, rec.x >> 16) + (rec.x & 0xffffu);
+                    cas_max_u16(t, rec.y >> 16);
+                }
+                cluster.sync();  // #2
+                for (unsigned i = tid; i < n; i += NT) {
+                    const uint2 rec = __ldcg(&rlist[i]);
+                    const unsigned o = rec.x >> 16, a = rec.x & 0xffffu;
+                    if (cluster.map_shared_rank(s_tag, o)[a] == (rec.y >> 16)) cluster.map_shared_rank(s_range, o)[a] = static_cast<uint16_t>(rec.y & 0xffffu);
+                }
+                cluster.sync();  // #3
+            }
+        }
+
+        // optional output: the range image
+        if (A.range_out) {
+            uint16_t* out = A.range_out + static_cast<size_t>(f) * kp.P;
+            for (int i = tid; i < H * myCW; i += NT) {
+                const int r = i / myCW, c = i - r * myCW;
+                out[r * W + col0 + c] = s_range[r * S16 + c];
+            }
+        }
+
+        // ================================================================================ A: angle image (column walks)
+        // one thread per (column, 32-row segment); bottom -> top like the reference (alfa_gs.cpp:347-382)
+        {
+            const int nword = (H + 31) / 32;
+            const int nseg = myCW * nword;
+            for (int s = tid; s < nseg; s += NT) {
+                const int c = s % myCW, wseg = s / myCW;
+                const int lo = wseg * 32, hi = min(lo + 31, H - 1);
+                // previous non-empty pixel below the segment
+                float p_z = 0.0f, p_x = 0.0f;  // prev_r * sinf(prev_angle_y), prev_r * cosf(prev_angle_y) (float products, :366-367)
+                bool has_prev = false;
+                for (int r = hi + 1; r < H; ++r) {
+                    const unsigned e = s_range[r * S16 + c];
+                    if (e) {
+                        const float pr = __double2float_rn(decode_range_d(kp, e));  // prev_r = range (:379)
+                        p_z = __fmul_rn(pr, A.lut.sin_y[r]);
+                        p_x = __fmul_rn(pr, A.lut.cos_y[r]);
+                        has_prev = true;
+                        break;
+                    }
+                }
+                if (!has_prev && col0 + c == 1) {
+                    // column-1 quirk (SURVEY.md A.2 iii): prev_col starts at 1 (:340) with prev_r = 0, prev_angle_y = 0
+                    bool col0_empty = true;
+                    for (int r = 0; r < H; ++r)
+                        if (s_range[r * S16]) { col0_empty = false; break; }
+                    if (col0_empty) {
+                        has_prev = true;
+                        p_z = __fmul_rn(0.0f, 0.0f);  // 0 * sinf(0)
+                        p_x = __fmul_rn(0.0f, 1.0f);  // 0 * cosf(0)
+                    }
+                }
+                unsigned vbits = 0;
+                for (int r = hi; r >= lo; --r) {
+                    const unsigned e = s_range[r * S16 + c];
+                    unsigned a_out = 0;
+                    if (e) {
+                        vbits |= 1u << (r - lo);
+                        const double rng = decode_range_d(kp, e);
+                        const float sy = A.lut.sin_y[r], cy = A.lut.cos_y[r];
+                        if (has_prev) {
+                            const double dz = fabs(__dsub_rn(static_cast<double>(p_z), __dmul_rn(rng, static_cast<double>(sy))));
+                            const double dx = fabs(__dsub_rn(static_cast<double>(p_x), __dmul_rn(rng, static_cast<double>(cy))));
+                            const float alfa = gs_atan2f(__double2float_rn(dz), __double2float_rn(dx));  // :368
+                            const float scaled = __fmul_rn(alfa, 100.0f);                                 // :370
+                            a_out = static_cast<unsigned>(__float2int_rz(scaled));
+                            if (A.stats) {
+                                const float fr = scaled - floorf(scaled);
+                                if (fminf(fr, 1.0f - fr) < 1e-3f) ++st_near_angle;
+                            }
+                        }
+                        const float rf = __double2float_rn(rng);
+                        p_z = __fmul_rn(rf, sy);
+                        p_x = __fmul_rn(rf, cy);
+                        has_prev = true;
+                    }
+                    s_angle[r * S8 + c] = static_cast<uint8_t>(a_out);
+                }
+                // valid bits of this segment -> the column's VALID mask word (masks alias the tag slab: dead now)
+                reinterpret_cast<unsigned*>(s_masks)[((MK_VALID * NW) * CWp + c) * 2 + 0] = 0;  // placeholder, fixed below
+                (void)vbits;
+                // store as 32-bit halves of the u64 words: word index wseg/2, half wseg&1
+                unsigned* vw = reinterpret_cast<unsigned*>(s_masks + (MK_VALID * NW + (wseg >> 1)) * CWp + c);
+                vw[wseg & 1] = vbits;
+                if ((nword & 1) && wseg == nword - 1) vw[1] = 0;  // H <= 32 or odd word count: clear the unused half
+            }
+        }
+        __syncthreads();
+        if (A.angle_out) {
+            uint16_t* out = A.angle_out + static_cast<size_t>(f) * kp.P;
+            for (int i = tid; i < H * myCW; i += NT) {
+                const int r = i / myCW, c = i - r * myCW;
+                out[r * W + col0 + c] = s_angle[r * S8 + c];
+            }
+        }
+        cluster.sync();  // #4: angle slabs and VALID masks complete in the whole cluster
+
+        // ================================================================================ G: edges, seeds, flood fill
+        const int right_rank = (rank + 1 == CL) ? 0 : rank + 1;
+        const int left_rank = (rank == 0) ? CL - 1 : rank - 1;
+        const int left_last = min(CW, W - left_rank * CW) - 1;  // last local column of the left neighbour
+        // halo: angle column 0 and VALID of the right neighbour (column W-1's right neighbour is column 0: Label::WrapCols)
+        {
+            const uint8_t* r_angle = cluster.map_shared_rank(s_angle, right_rank);
+            for (int r = tid; r < H; r += NT) s_halo_angle[r] = r_angle[r * S8];
+            if (tid < NW) s_halo_masks[0 * 2 + tid] = cluster.map_shared_rank(s_masks, right_rank)[(MK_VALID * NW + tid) * CWp + 0];
+        }
+        __syncthreads();
+        const Mask<NW> Hmask = Mask<NW>::low(H);
+        for (int c = tid; c < myCW; c += NT) {
+            const Mask<NW> valid = ld_mask<NW>(s_masks, MK_VALID, CWp, c);
+            Mask<NW> va = Mask<NW>::zero(), ha = Mask<NW>::zero();
+            const bool last = (c == myCW - 1);
+            int a_here = s_angle[c];
+            for (int r = 0; r < H; ++r) {
+                const int a_down = (r + 1 < H) ? s_angle[(r + 1) * S8 + c] : 0;
+                const int a_right = last ? s_halo_angle[r] : s_angle[r * S8 + c + 1];
+                if (r + 1 < H && abs(a_here - a_down) <= kp.k_ground) va.set(r);   // label.cpp:90-99, threshold folded to an integer
+                if (abs(a_here - a_right) <= kp.k_ground) ha.set(r);
+                a_here = a_down;
+            }
+            Mask<NW> valid_right;
+            if (last) {
+                valid_right.w0 = s_halo_masks[0];
+                if constexpr (NW == 2) valid_right.w1 = s_halo_masks[1];
+            } else {
+                valid_right = ld_mask<NW>(s_masks, MK_VALID, CWp, c + 1);
+            }
+            const bool has_right = W > 1;
+            if (!has_right) ha = Mask<NW>::zero();
+            const Mask<NW> v = va & valid & valid.shr(1);
+            const Mask<NW> hm = ha & valid & valid_right;
+            // seed (alfa_gs.cpp:720-736): bottom-most non-empty pixel, row 0 when the column is empty
+            int sr = valid.top();
+            const bool seed_valid = sr >= 0;
+            if (sr < 0) sr = 0;
+            const bool accepted = static_cast<int>(s_angle[sr * S8 + c]) <= kp.s_start;  // :733
+            Mask<NW> g = Mask<NW>::zero();
+            if (accepted && seed_valid) g.set(sr);
+            Mask<NW> keep = Mask<NW>::zero();  // KEEP temporarily carries the accepted empty seed (labelled, not expanded: label.cpp:67-74)
+            if (accepted && !seed_valid) keep.set(0);
+            st_mask<NW>(s_masks, MK_VA, CWp, c, va);
+            st_mask<NW>(s_masks, MK_HA, CWp, c, ha);
+            st_mask<NW>(s_masks, MK_V, CWp, c, v);
+            st_mask<NW>(s_masks, MK_HM, CWp, c, hm);
+            st_mask<NW>(s_masks, MK_G, CWp, c, vfill<NW>(g, v, H));
+            st_mask<NW>(s_masks, MK_KEEP, CWp, c, keep);
+        }
+        cluster.sync();  // #5: HM / HA / G of every slab readable by the neighbours
+        // static halos from the left neighbour: HM and HA of its last column (the edge between that column and my column 0)
+        if (tid < NW) {
+            const unsigned long long* lm = cluster.map_shared_rank(s_masks, left_rank);
+            s_halo_masks[3 * 2 + tid] = lm[(MK_HM * NW + tid) * CWp + left_last];
+            s_halo_masks[4 * 2 + tid] = lm[(MK_HA * NW + tid) * CWp + left_last];
+        }
+        // flood fill: G[c] <- vfill(G[c] | (G[c-1] & HM[c-1]) | (G[c+1] & HM[c]))  until nothing changes anywhere
+        for (;;) {
+            // import the neighbours' boundary columns of G
+            if (tid < NW) {
+                s_halo_masks[1 * 2 + tid] = cluster.map_shared_rank(s_masks, right_rank)[(MK_G * NW + tid) * CWp + 0];
+                s_halo_masks[2 * 2 + tid] = cluster.map_shared_rank(s_masks, left_rank)[(MK_G * NW + tid) * CWp + left_last];
+            }
+            __syncthreads();
+            bool any_change = false;
+            for (int it = 0;; ++it) {
+                bool changed = false;
+                for (int c = tid; c < myCW; c += NT) {
+                    const Mask<NW> g = ld_mask<NW>(s_masks, MK_G, CWp, c);
+                    Mask<NW> gl, hl, gr;
+                    if (c == 0) {
+                        gl.w0 = s_halo_masks[2 * 2 + 0];
+                        hl.w0 = s_halo_masks[3 * 2 + 0];
+                        if constexpr (NW == 2) { gl.w1 = s_halo_masks[2 * 2 + 1]; hl.w1 = s_halo_masks[3 * 2 + 1]; }
+                    } else {
+                        gl = ld_mask<NW>(s_masks, MK_G, CWp, c - 1);
+                        hl = ld_mask<NW>(s_masks, MK_HM, CWp, c - 1);
+                    }
+                    if (c == myCW - 1) {
+                        gr.w0 = s_halo_masks[1 * 2 + 0];
+                        if constexpr (NW == 2) gr.w1 = s_halo_masks[1 * 2 + 1];
+                    } else {
+                        gr = ld_mask<NW>(s_masks, MK_G, CWp, c + 1);
+                    }
+                    const Mask<NW> hm = ld_mask<NW>(s_masks, MK_HM, CWp, c);
+                    const Mask<NW> in = g | (gl & hl) | (gr & hm);
+                    if (in != g) {
+                        const Mask<NW> v = ld_mask<NW>(s_masks, MK_V, CWp, c);
+                        st_mask<NW>(s_masks, MK_G, CWp, c, vfill<NW>(in, v, H));
+                        changed = true;
+                    }
+                }
+                const int any = __syncthreads_or(changed ? 1 : 0);
+                if (!any) break;
+                any_change = true;
+            }
+            // cluster-wide: did any slab change in this outer round?
+            if (tid < CL) cluster.map_shared_rank(s_flags, tid)[rank] = any_change ? 1u : 0u;
+            cluster.sync();
+            unsigned anyone = 0;
+            for (int k = 0; k < CL; ++k) anyone |= s_flags[k];
+            cluster.sync();  // flags consumed before the next round overwrites them; G stable for the next import
+            if (!anyone) break;
+        }
+
+        // ================================================================================ D: label image, dilation, erase
+        // L = G | accepted empty seeds | empty pixels 4-adjacent to a ground pixel u with |angle(u) - angle(p)| <= K
+        for (int c = tid; c < myCW; c += NT) {
+            const Mask<NW> valid = ld_mask<NW>(s_masks, MK_VALID, CWp, c);
+            const Mask<NW> g = ld_mask<NW>(s_masks, MK_G, CWp, c);
+            const Mask<NW> va = ld_mask<NW>(s_masks, MK_VA, CWp, c);
+            const Mask<NW> ha = ld_mask<NW>(s_masks, MK_HA, CWp, c);
+            Mask<NW> gl, hal, gr;
+            if (c == 0) {
+                gl.w0 = s_halo_masks[2 * 2 + 0];
+                hal.w0 = s_halo_masks[4 * 2 + 0];
+                if constexpr (NW == 2) { gl.w1 = s_halo_masks[2 * 2 + 1]; hal.w1 = s_halo_masks[4 * 2 + 1]; }
+            } else {
+                gl = ld_mask<NW>(s_masks, MK_G, CWp, c - 1);
+                hal = ld_mask<NW>(s_masks, MK_HA, CWp, c - 1);
+            }
+            if (c == myCW - 1) {
+                gr.w0 = s_halo_masks[1 * 2 + 0];
+                if constexpr (NW == 2) gr.w1 = s_halo_masks[1 * 2 + 1];
+            } else {
+                gr = ld_mask<NW>(s_masks, MK_G, CWp, c + 1);
+            }
+            const Mask<NW> eseed = ld_mask<NW>(s_masks, MK_KEEP, CWp, c);
+            const Mask<NW> near = (g.shr(1) & va) | (g & va).shl(1) | (gl & hal) | (gr & ha);
+            const Mask<NW> L = (g | eseed | (~valid & near)) & Hmask;
+            // dilated(r) = OR_k L(r + off_k)   (effective taps of cv::dilate with GetUniformKernel's bytes)
+            Mask<NW> D = (kp.dil0 >= 0) ? L.shr(kp.dil0) : L.shl(-kp.dil0);
+            if (kp.n_dil > 1) D = D | ((kp.dil1 >= 0) ? L.shr(kp.dil1) : L.shl(-kp.dil1));
+            const Mask<NW> keep = valid & (kp.erase_ground ? ~D : D) & Hmask;  // alfa_gs.cpp:751-764
+            __syncwarp();
+            st_mask<NW>(s_masks, MK_KEEP, CWp, c, keep);
+        }
+        __syncthreads();
+        // transpose the KEEP masks to row-major 32-column groups, count rows
+        for (int gidx = warp; gidx < NG; gidx += NT / 32) {
+            const int c = gidx * 32 + lane;
+            Mask<NW> keep = Mask<NW>::zero();
+            if (c < myCW) keep = ld_mask<NW>(s_masks, MK_KEEP, CWp, c);
+            for (int r = 0; r < H; ++r) {
+                const unsigned m = __ballot_sync(0xffffffffu, keep.bit(r));
+                if (lane == 0) s_rowmask[r * NG + gidx] = m;
+            }
+        }
+        __syncthreads();
+        for (int r = tid; r < H; r += NT) {
+            unsigned run = 0;
+            for (int gidx = 0; gidx < NG; ++gidx) {
+                s_grp[r * NG + gidx] = run;
+                run += __popc(s_rowmask[r * NG + gidx]);
+            }
+            for (int k = 0; k < CL; ++k) cluster.map_shared_rank(s_rowcnt_all, k)[rank * MAX_H + r] = run;
+        }
+        cluster.sync();  // #: row counts of every slab everywhere
+        if (warp == 0) {
+            // rowbase[r] = points in rows above (all slabs) + points of row r in the slabs left of mine
+            unsigned carry = 0;
+            for (int r0 = 0; r0 < H; r0 += 32) {
+                const int r = r0 + lane;
+                unsigned tot = 0, left = 0;
+                if (r < H)
+                    for (int k = 0; k < CL; ++k) {
+                        const unsigned v = s_rowcnt_all[k * MAX_H + r];
+                        tot += v;
+                        if (k < rank) left += v;
+                    }
+                unsigned incl = tot;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                if (r < H) s_rowbase[r] = carry + incl - tot + left;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0 && rank == 0 && A.counts_out) A.counts_out[f] = carry;
+        }
+        __syncthreads();
+
+        // ================================================================================ B: no-ground image + cloud
+        {
+            uint16_t* res = A.res_out ? A.res_out + static_cast<size_t>(f) * kp.P : nullptr;
+            float4* cloud = A.xyz_out ? A.xyz_out + static_cast<size_t>(f) * kp.P : nullptr;
+            const bool range_as_double = kp.variant == GS_VARIANT_CLOUD2RANGE;
+            for (int idx = tid; idx < H * NG * 32; idx += NT) {
+                const int r = idx / (NG * 32);
+                const int cc = idx - r * (NG * 32);
+                const int gidx = cc >> 5;
+                if (cc < myCW) {
+                    const unsigned m = s_rowmask[r * NG + gidx];
+                    const bool keep = (m >> lane) & 1u;
+                    const unsigned enc = s_range[r * S16 + cc];
+                    if (res) res[r * W + col0 + cc] = keep ? static_cast<uint16_t>(enc) : static_cast<uint16_t>(0);
+                    if (keep && cloud) {
+                        const unsigned slot = s_rowbase[r] + s_grp[r * NG + gidx] + __popc(m & ((1u << lane) - 1u));
+                        const double rng_d = decode_range_d(kp, enc);
+                        const double rng = range_as_double ? rng_d : static_cast<double>(__double2float_rn(rng_d));  // alfa_gs.cpp:1027,1045 / range2cloud_node.cpp:76
+                        const double ca = A.lut.cos_alt[r], sa = A.lut.sin_alt[r];
+                        const double caz = A.lut.cos_az[col0 + cc], saz = A.lut.sin_az[col0 + cc];
+                        float4 o;
+                        o.x = __double2float_rn(__dmul_rn(__dmul_rn(ca, caz), rng));  // :1055
+                        o.y = __double2float_rn(__dmul_rn(__dmul_rn(ca, saz), rng));  // :1056
+                        o.z = __double2float_rn(__dmul_rn(sa, rng));                  // :1057
+                        o.w = 1.0f;
+                        cloud[slot] = o;
+                    }
+                }
+            }
+        }
+        __syncthreads();  // the slabs are cleared at the top of the next frame
+    }
+
+    if (A.stats) {
+        // block-level reduction is not worth it: stats runs are test runs
+        if (st_dropped) atomicAdd(&A.cnt->dropped, st_dropped);
+        if (st_near) atomicAdd(&A.cnt->near_edge_project, st_near);
+        if (st_near_angle) atomicAdd(&A.cnt->near_edge_angle, st_near_angle);
+        if (st_remote) atomicAdd(&A.cnt->slow_path, st_remote);
+    }
+    cluster.sync();  // no CTA exits while a neighbour may still address its shared memory
+}
+
+// ====================================================================================================================
+// host side
+// ====================================================================================================================
+namespace {
+
+struct Layout {
+    int CL, CW, S16, S8, NG;
+    unsigned off_range, off_tag, off_angle, off_misc;
+    size_t total;
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+bool layout_for(const KParams& kp, int CL, int NW, Layout* L) {
+    const int W = kp.W, H = kp.H;
+    const int CW = (W + CL - 1) / CL;
+    if (CW < 2 && W >= 2) return false;
+    if (W - (CL - 1) * CW <= 0) return false;  // the last CTA must own at least one column
+    L->CL = CL;
+    L->CW = CW;
+    L->S16 = CW + 2 + ((CW & 1) ? 1 : 0);  // odd word stride: a column-major walk over rows hits distinct banks
+    if (((L->S16 / 2) & 1) == 0) L->S16 += 2;
+    L->S8 = static_cast<int>(align_up(CW + 4, 4));
+    if (((L->S8 / 4) & 1) == 0) L->S8 += 4;
+    L->NG = (CW + 31) / 32;
+    if (static_cast<size_t>(H) * L->S16 > 65535) return false;  // slab addresses are 16-bit
+    const size_t range_bytes = align_up(static_cast<size_t>(H) * L->S16 * 2, 16);
+    const size_t masks_bytes = static_cast<size_t>(MK_COUNT) * NW * CW * 8 + static_cast<size_t>(2) * H * L->NG * 4;
+    const size_t tag_bytes = align_up(std::max(range_bytes, masks_bytes), 16);
+    const size_t angle_bytes = align_up(std::max(static_cast<size_t>(H) * L->S8, static_cast<size_t>(MAX_BLOCKS) * 3), 16);
+    const size_t misc_bytes = align_up(static_cast<size_t>(MAX_CL) * MAX_H * 4 + MAX_H * 4 + 10 * 8 + MAX_H + MAX_CL * 4 + 64, 16);
+    L->off_range = 0;
+    L->off_tag = static_cast<unsigned>(range_bytes);
+    L->off_angle = static_cast<unsigned>(range_bytes + tag_bytes);
+    L->off_misc = static_cast<unsigned>(range_bytes + tag_bytes + angle_bytes);
+    L->total = range_bytes + tag_bytes + angle_bytes + misc_bytes;
+    return true;
+}
+
+struct FusedPlan {
+    Layout lay;
+    int NW;
+    int max_clusters;
+};
+
+}  // namespace
+
+int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const SgTaps& sg, bool smooth, bool repair, int device) {
+    fs.kp = kp;
+    fs.lut = lut;
+    fs.sg = sg;
+    fs.smooth = smooth;
+    fs.repair = repair;
+    fs.configured = false;
+    // what the fused kernel covers; everything else runs on the staged kernels
+    if (smooth || repair) return 0;
+    if (kp.pixel_policy != GS_PIXEL_LAST) return 0;
+    if (kp.H > MAX_H || kp.W < 2) return 0;
+    const int NW = kp.H <= 64 ? 1 : 2;
+    int max_smem = 0, n_sms = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    Layout lay;
+    bool found = false;
+    for (int CL = 1; CL <= MAX_CL; CL *= 2) {
+        if (layout_for(kp, CL, NW, &lay) && lay.total <= static_cast<size_t>(max_smem)) {
+            found = true;
+            break;
+        }
+    }
+    if (!found) return 0;
+    auto kern = NW == 1 ? k_frame<1> : k_frame<2>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lay.total));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    // how many clusters can be co-resident
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(n_sms / lay.CL * lay.CL));
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = lay.total;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(lay.CL);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return 0;  // clusters of this size cannot be scheduled here: staged kernels
+    }
+    if (max_clusters < 1) return 0;
+    fs.cluster = lay.CL;
+    fs.cols_per_cta = lay.CW;
+    fs.smem_bytes = lay.total;
+    fs.n_sms = n_sms;
+    fs.max_clusters = max_clusters;
+    fs.configured = true;
     return 0;
 }
+
 bool fused_supported(const FusedState& fs) { return fs.configured && !fs.disabled; }
-int fused_run(FusedState&, const Launch&, const float4*, const long long*, int, uint16_t*, uint16_t*, uint16_t*, float4*, unsigned*, Counters*, bool) {
-    return cudaErrorNotSupported;
+
+void fused_release(FusedState& fs) {
+    cudaFree(fs.d_const);
+    cudaFree(fs.d_rowbase);
+    fs.d_const = nullptr;
+    fs.d_rowbase = nullptr;
+    fs.rowbase_cap = 0;
+    fs.configured = false;
 }
-void fused_release(FusedState& fs) { fs.configured = false; }
+
+int fused_run(FusedState& fs, const Launch& L, const float4* points, const long long* d_offsets, int frames, uint16_t* range_out,
+              uint16_t* angle_out, uint16_t* res_out, float4* xyz_out, unsigned* counts_out, Counters* cnt, bool stats) {
+    if (frames <= 0) return 0;
+    const KParams& kp = fs.kp;
+    const int NW = kp.H <= 64 ? 1 : 2;
+    Layout lay;
+    if (!layout_for(kp, fs.cluster, NW, &lay)) return static_cast<int>(cudaErrorInvalidConfiguration);
+    const int n_clusters = std::min(frames, fs.max_clusters);
+    // remote-record scratch: every point of a frame may be remote in the worst case (shuffled clouds)
+    const unsigned rcap = static_cast<unsigned>(MAX_BLOCKS) * BLK;
+    const size_t need = static_cast<size_t>(fs.max_clusters) * lay.CL * (static_cast<size_t>(rcap) * sizeof(uint2) + sizeof(unsigned));
+    if (fs.rowbase_cap < need) {
+        cudaFree(fs.d_rowbase);
+        fs.d_rowbase = nullptr;
+        fs.rowbase_cap = 0;
+        const cudaError_t e = cudaMalloc(&fs.d_rowbase, need);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        fs.rowbase_cap = need;
+    }
+    FusedArgs a;
+    a.kp = kp;
+    a.lut = fs.lut;
+    a.CL = lay.CL;
+    a.CW = lay.CW;
+    a.S16 = lay.S16;
+    a.S8 = lay.S8;
+    a.NG = lay.NG;
+    a.off_range = lay.off_range;
+    a.off_tag = lay.off_tag;
+    a.off_angle = lay.off_angle;
+    a.off_misc = lay.off_misc;
+    a.points = points;
+    a.offsets = d_offsets;
+    a.frames = frames;
+    a.range_out = range_out;
+    a.angle_out = angle_out;
+    a.res_out = res_out;
+    a.xyz_out = xyz_out;
+    a.counts_out = counts_out;
+    a.cnt = cnt;
+    a.stats = stats ? 1 : 0;
+    a.rcap = rcap;
+    a.rlist = reinterpret_cast<uint2*>(fs.d_rowbase);
+    a.rcount = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(fs.d_rowbase) +
+                                           static_cast<size_t>(fs.max_clusters) * lay.CL * rcap * sizeof(uint2));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(n_clusters * lay.CL));
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = lay.total;
+    cfg.stream = L.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(lay.CL);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = NW == 1 ? cudaLaunchKernelEx(&cfg, k_frame<1>, a) : cudaLaunchKernelEx(&cfg, k_frame<2>, a);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    ++*L.n_launches;
+    return 0;
+}
+
 }  // namespace gs
