@@ -403,9 +403,9 @@ int run_wave_staged(gs_ctx* ctx, const void* d_points, size_t stride, const long
 // Picks the fused single-kernel pipeline when it supports the configuration, else the staged kernels.
 int run_wave(gs_ctx* ctx, const void* d_points, size_t stride, const long long* d_offsets, int frames, long long max_points,
              uint16_t* range_out, uint16_t* angle_out, uint16_t* res_out, float* xyz_out, unsigned* counts_out) {
-    if (stride == 16 && (reinterpret_cast<uintptr_t>(d_points) & 15) == 0 && fused_supported(ctx->fused)) {
+    if (stride == 16 && (reinterpret_cast<uintptr_t>(d_points) & 15) == 0 && fused_supported(ctx->fused) && max_points <= fused_max_points()) {
         const Launch L = launch_of(ctx);
-        const int rc = fused_run(ctx->fused, L, static_cast<const float4*>(d_points), d_offsets, frames, range_out, angle_out, res_out,
+        const int rc = fused_run(ctx->fused, L, static_cast<const float4*>(d_points), d_offsets, frames, max_points, range_out, angle_out, res_out,
                                  reinterpret_cast<float4*>(xyz_out), counts_out, ctx->d_cnt, ctx->collect_stats);
         if (rc) return fail(ctx, GS_ECUDA, "fused kernel launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(rc)));
         return GS_OK;
@@ -780,7 +780,9 @@ int gs_process_batch_device(gs_ctx* ctx, const float* d_points_xyzi, const int64
     CU(cudaMemcpyAsync(ctx->d_offsets, h_offsets, (static_cast<size_t>(n_frames) + 1) * sizeof(long long), cudaMemcpyHostToDevice,
                        ctx->stream));
     const size_t P = ctx->kp.P;
-    const bool use_fused = (reinterpret_cast<uintptr_t>(d_points_xyzi) & 15) == 0 && fused_supported(ctx->fused);
+    long long batch_max = 0;
+    for (int f = 0; f < n_frames; ++f) batch_max = std::max<long long>(batch_max, h_offsets[f + 1] - h_offsets[f]);
+    const bool use_fused = (reinterpret_cast<uintptr_t>(d_points_xyzi) & 15) == 0 && fused_supported(ctx->fused) && batch_max <= fused_max_points();
     const int chunk = use_fused ? n_frames : std::min(n_frames, auto_chunk(ctx));
     if (!use_fused && (rc = ensure_scratch(ctx, chunk))) return rc;
     for (int f0 = 0; f0 < n_frames; f0 += chunk) {
@@ -828,8 +830,7 @@ int gs_process_batch_host(gs_ctx* ctx, const float* h_points_xyzi, const int64_t
     if ((rc = ensure_offsets(ctx, static_cast<size_t>(n_frames) + 1))) return rc;
     CU(cudaMemcpyAsync(ctx->d_offsets, h_offsets, (static_cast<size_t>(n_frames) + 1) * sizeof(long long), cudaMemcpyHostToDevice,
                        ctx->stream));
-    const bool fused_ok = fused_supported(ctx->fused);
-    if (!fused_ok && (rc = ensure_scratch(ctx, wave))) return rc;
+    // run_wave allocates the staged scratch on demand when a wave cannot take the fused kernel
     const int n_waves = (n_frames + wave - 1) / wave;
     int64_t out_cursor = 0;
     if (h_out_offsets) h_out_offsets[0] = 0;

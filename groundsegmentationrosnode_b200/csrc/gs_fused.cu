@@ -23,6 +23,8 @@
 // ordered clouds (sensor firing order or row-major organised) almost every store is CTA-local; the rest go through a
 // small remote list that is applied over distributed shared memory after the local rounds.
 #include <cooperative_groups.h>
+
+#include <algorithm>
 #include <math_constants.h>
 
 #include "gs_internal.h"
@@ -521,9 +523,7 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
                     s_angle[r * S8 + c] = static_cast<uint8_t>(a_out);
                 }
                 // valid bits of this segment -> the column's VALID mask word (masks alias the tag slab: dead now)
-                reinterpret_cast<unsigned*>(s_masks)[((MK_VALID * NW) * CWp + c) * 2 + 0] = 0;  // placeholder, fixed below
-                (void)vbits;
-                // store as 32-bit halves of the u64 words: word index wseg/2, half wseg&1
+                // stored as 32-bit halves of the u64 mask words: word wseg / 2, half wseg & 1
                 unsigned* vw = reinterpret_cast<unsigned*>(s_masks + (MK_VALID * NW + (wseg >> 1)) * CWp + c);
                 vw[wseg & 1] = vbits;
                 if ((nword & 1) && wseg == nword - 1) vw[1] = 0;  // H <= 32 or odd word count: clear the unused half
@@ -675,7 +675,6 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
             Mask<NW> D = (kp.dil0 >= 0) ? L.shr(kp.dil0) : L.shl(-kp.dil0);
             if (kp.n_dil > 1) D = D | ((kp.dil1 >= 0) ? L.shr(kp.dil1) : L.shl(-kp.dil1));
             const Mask<NW> keep = valid & (kp.erase_ground ? ~D : D) & Hmask;  // alfa_gs.cpp:751-764
-            __syncwarp();
             st_mask<NW>(s_masks, MK_KEEP, CWp, c, keep);
         }
         __syncthreads();
@@ -841,7 +840,8 @@ int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const Sg
     }
     if (!found) return 0;
     auto kern = NW == 1 ? k_frame<1> : k_frame<2>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lay.total));
+    // the attribute is per function, not per context: always ask for the device maximum
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e != cudaSuccess) return static_cast<int>(e);
     // how many clusters can be co-resident
     cudaLaunchConfig_t cfg = {};
@@ -882,16 +882,20 @@ void fused_release(FusedState& fs) {
     fs.configured = false;
 }
 
-int fused_run(FusedState& fs, const Launch& L, const float4* points, const long long* d_offsets, int frames, uint16_t* range_out,
-              uint16_t* angle_out, uint16_t* res_out, float4* xyz_out, unsigned* counts_out, Counters* cnt, bool stats) {
+long long fused_max_points() { return static_cast<long long>(MAX_BLOCKS) * BLK; }
+
+int fused_run(FusedState& fs, const Launch& L, const float4* points, const long long* d_offsets, int frames, long long max_points,
+              uint16_t* range_out, uint16_t* angle_out, uint16_t* res_out, float4* xyz_out, unsigned* counts_out, Counters* cnt,
+              bool stats) {
     if (frames <= 0) return 0;
+    if (max_points > fused_max_points()) return static_cast<int>(cudaErrorInvalidValue);
     const KParams& kp = fs.kp;
     const int NW = kp.H <= 64 ? 1 : 2;
     Layout lay;
     if (!layout_for(kp, fs.cluster, NW, &lay)) return static_cast<int>(cudaErrorInvalidConfiguration);
     const int n_clusters = std::min(frames, fs.max_clusters);
     // remote-record scratch: every point of a frame may be remote in the worst case (shuffled clouds)
-    const unsigned rcap = static_cast<unsigned>(MAX_BLOCKS) * BLK;
+    const unsigned rcap = static_cast<unsigned>(std::max<long long>((max_points + 1023) / 1024 * 1024, 1024));
     const size_t need = static_cast<size_t>(fs.max_clusters) * lay.CL * (static_cast<size_t>(rcap) * sizeof(uint2) + sizeof(unsigned));
     if (fs.rowbase_cap < need) {
         cudaFree(fs.d_rowbase);

@@ -106,8 +106,10 @@ struct FusedState {
 // return 0 or a cudaError_t
 int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const SgTaps& sg, bool smooth, bool repair, int device);
 bool fused_supported(const FusedState& fs);
-int fused_run(FusedState& fs, const Launch& L, const float4* points, const long long* d_offsets, int frames, uint16_t* range_out,
-              uint16_t* angle_out, uint16_t* res_out, float4* xyz_out, unsigned* counts_out, Counters* cnt, bool stats);
+long long fused_max_points();  // frames with more points than this run on the staged kernels
+int fused_run(FusedState& fs, const Launch& L, const float4* points, const long long* d_offsets, int frames, long long max_points,
+              uint16_t* range_out, uint16_t* angle_out, uint16_t* res_out, float4* xyz_out, unsigned* counts_out, Counters* cnt,
+              bool stats);
 void fused_release(FusedState& fs);
 
 }  // namespace gs
