@@ -306,10 +306,10 @@ int configure(gs_ctx* ctx, const gs_params* p) {
         cudaFree(ctx->lut_block);
         ctx->lut_block = nullptr;
     }
-    // LUT block: [H] sin_y, [H] cos_y (float) | [H] cos_alt, [H] sin_alt, [W] cos_az, [W] sin_az (double)
+    // LUT block: [H] sin_y, [H] cos_y (float) | [H] cos_alt, [H] sin_alt, [W] cos_az, [W] sin_az, [H] sin_y, [H] cos_y (double)
     const int H = k.H, W = k.W;
     const size_t f_bytes = ((2 * static_cast<size_t>(H) * sizeof(float)) + 15) & ~static_cast<size_t>(15);
-    const size_t d_count = 2 * static_cast<size_t>(H) + 2 * static_cast<size_t>(W);
+    const size_t d_count = 4 * static_cast<size_t>(H) + 2 * static_cast<size_t>(W);
     const size_t total = f_bytes + d_count * sizeof(double);
     std::vector<unsigned char> host(total);
     float* hf = reinterpret_cast<float*>(host.data());
@@ -322,6 +322,8 @@ int configure(gs_ctx* ctx, const gs_params* p) {
         const double altitude = (H - r) * d.d_altitude + p->min_angle;  // alfa_gs.cpp:1050 / range2cloud_node.cpp:81
         hd[r] = std::cos(altitude);
         hd[H + r] = std::sin(altitude);
+        hd[2 * H + 2 * W + r] = static_cast<double>(hf[r]);
+        hd[3 * H + 2 * W + r] = static_cast<double>(hf[H + r]);
     }
     for (int c = 0; c < W; ++c) {
         const double azimuth = c * d.d_azimuth;  // alfa_gs.cpp:1052
@@ -339,6 +341,8 @@ int configure(gs_ctx* ctx, const gs_params* p) {
     ctx->lut.sin_alt = dd + H;
     ctx->lut.cos_az = dd + 2 * H;
     ctx->lut.sin_az = dd + 2 * H + W;
+    ctx->lut.sin_y_d = dd + 2 * H + 2 * W;
+    ctx->lut.cos_y_d = dd + 3 * H + 2 * W;
     const int frc = fused_configure(ctx->fused, k, ctx->lut, ctx->sg, p->smoothing == GS_SMOOTH_SG, p->repair_gaps != 0, ctx->device);
     if (frc) return fail(ctx, GS_ECUDA, "fused kernel configuration failed: %s", cudaGetErrorString(static_cast<cudaError_t>(frc)));
     return GS_OK;
@@ -562,6 +566,8 @@ int gs_get_stats(gs_ctx* ctx, gs_stats* out) {
     out->near_edge_angle = ctx->h_cnt->near_edge_angle;
     out->dropped_points = ctx->h_cnt->dropped;
     out->slow_path_points = ctx->h_cnt->slow_path;
+    out->fast_path_mismatches = ctx->h_cnt->fast_mismatch;
+    out->remote_points = ctx->h_cnt->remote;
     return GS_OK;
 }
 

@@ -25,6 +25,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cmath>
 #include <math_constants.h>
 
 #include "gs_internal.h"
@@ -65,13 +66,51 @@ struct FusedArgs {
     uint2* rlist;        // [clusters][CL][rcap] remote records
     unsigned* rcount;    // [clusters][CL]
     unsigned rcap;
+    // ---- fast (float / fixed-point) projection, certified by margins (see project_fast)
+    double enc_scale;          // 65534 / (max_range - min_range)
+    float alt_to_fix;          // altitude (rad) -> row cells * 2^FB
+    float az_to_fix;           // angle (rad)    -> column cells * 2^FB
+    float alt_lo, alt_hi;      // altitude gates as floats
+    int row0_fix;              // rowfix = row0_fix - altitude_fix
+    int quarter_fix;           // a quarter turn in column cells * 2^FB
+    int col_half_fix;          // + half a cell (alfa_gs variant only)
+    int row_margin, col_margin;  // fixed-point error margins
+    unsigned cw_magic;         // ceil(2^32 / CW): owner = (col * cw_magic) >> 32 for col < 2^16
+    unsigned ng_magic;         // ceil(2^32 / NG)
+    unsigned mycw_shift;       // unused
+    int use_fast;
 };
+
+constexpr int FB = 18;  // fractional bits of the fixed-point cell coordinates
 
 // ---- small helpers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double decode_range_d(const KParams& kp, unsigned enc) {
     // static_cast<double>(enc - 1) / 65534 * (max_range - min_range) + min_range   (alfa_gs.cpp:359-360, :1042-1045)
-    const double norm = __ddiv_rn(static_cast<double>(static_cast<int>(enc) - 1), 65534.0);
+    // The division by the constant 65534 is done as q0 = n * R, r = fma(-q0, 65534, n), q = fma(r, R, q0) with
+    // R = RN(1 / 65534): correctly rounded for every n in [0, 65534] (checked exhaustively against n / 65534.0 by
+    // tests/clone_check.cpp), 3 FP64 instructions instead of the ~25 of a generic double division.
+    const double n = static_cast<double>(static_cast<int>(enc) - 1);
+    const double R = 1.0 / 65534.0;
+    const double q0 = __dmul_rn(n, R);
+    const double r = __fma_rn(-q0, 65534.0, n);
+    const double norm = __fma_rn(r, R, q0);
     return __dadd_rn(__dmul_rn(norm, kp.span), kp.min_range);
+}
+
+// atan(a) for a in [0, 1]: a + a*s*q(s), s = a*a; max error 6.6e-8 rad in binary32 FMA arithmetic (fitted and measured
+// by tools/fit_atan.py).  Used only on the certified fast paths: every result that lands within a margin >= 4x the error
+// budget of a quantisation edge is recomputed with the reference's exact arithmetic.
+__device__ __forceinline__ float atan01(float a) {
+    const float s = __fmul_rn(a, a);
+    float q = 0.0021047850605100393f;
+    q = __fmaf_rn(q, s, -0.012938526459038258f);
+    q = __fmaf_rn(q, s, 0.03731348365545273f);
+    q = __fmaf_rn(q, s, -0.07019482553005219f);
+    q = __fmaf_rn(q, s, 0.1039692610502243f);
+    q = __fmaf_rn(q, s, -0.14136579632759094f);
+    q = __fmaf_rn(q, s, 0.19983631372451782f);
+    q = __fmaf_rn(q, s, -0.3333265483379364f);
+    return __fmaf_rn(__fmul_rn(a, s), q, a);
 }
 
 __device__ __forceinline__ void cas_max_u16(uint16_t* p, unsigned v) {
@@ -242,6 +281,62 @@ __device__ __forceinline__ Proj project_point_d(const KParams& kp, float fx, flo
     return out;
 }
 
+// Fast projection.  The range (hence the gates and the encoded pixel value) is computed with the reference's own double
+// operations, except that the division by (max_range - min_range) becomes a multiplication checked against a 1e-9
+// margin (the two differ by < 1e-10).  Altitude and azimuth come from a float atan (error budget 2e-7 rad) and are
+// turned into fixed-point cell coordinates; when the fractional position lies within the margin (>= 7.5e-7 rad) of a
+// cell edge or an altitude gate, the caller falls back to project_point_d.  returns 0 = pixel found, 1 = dropped,
+// 2 = undecided (fall back).
+__device__ __forceinline__ int project_fast(const FusedArgs& A, float fx, float fy, float fz, int* row_out, int* col_out, unsigned* enc_out) {
+    const KParams& kp = A.kp;
+    const double x = fx, y = fy, z = fz;
+    const double range = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));  // utils.h:41-43
+    if (!(range >= kp.min_range && range <= kp.max_range)) return isfinite(range) ? 1 : 2;  // alfa_gs.cpp:261 (non-finite: exact path decides)
+    const double u = __fma_rn(__dsub_rn(range, kp.min_range), A.enc_scale, 1.0);
+    const int e = __double2int_rz(u);
+    const double uf = u - static_cast<double>(e);
+    if (!(uf > 1e-9 && uf < 1.0 - 1e-9)) return 2;
+    // altitude
+    const float ax = fabsf(fx), ay = fabsf(fy), az = fabsf(fz);
+    if (fy == 0.0f) return 2;  // atan2(-0.0, x < 0) = -pi in the reference (Q3): exact path
+    const float h = sqrtf(__fmaf_rn(fx, fx, __fmul_rn(fy, fy)));
+    const float lo_a = fminf(az, h), hi_a = fmaxf(az, h);
+    float t = atan01(__fdividef(lo_a, hi_a));
+    if (az > h) t = 1.57079632679489662f - t;
+    const float alt = fz < 0.0f ? -t : t;
+    if (!(alt > A.alt_lo + 1e-6f && alt < A.alt_hi - 1e-6f)) {
+        if (alt < A.alt_lo - 1e-6f || alt > A.alt_hi + 1e-6f) return 1;  // alfa_gs.cpp:269, certainly outside
+        return 2;                                                        // within the margin of a gate (or NaN)
+    }
+    const int rowfix = A.row0_fix - __float2int_rn(__fmul_rn(alt, A.alt_to_fix));
+    const int rfrac = rowfix & ((1 << FB) - 1);
+    if (rfrac < A.row_margin || rfrac > (1 << FB) - A.row_margin) return 2;
+    const int row = rowfix >> FB;
+    // azimuth in [0, 2 pi): octant reduction, reflections in exact fixed point
+    const float lo_b = fminf(ax, ay), hi_b = fmaxf(ax, ay);
+    int c = __float2int_rn(__fmul_rn(atan01(__fdividef(lo_b, hi_b)), A.az_to_fix));
+    if (ay > ax) c = A.quarter_fix - c;
+    if (fx < 0.0f) c = 2 * A.quarter_fix - c;
+    if (fy < 0.0f) c = 4 * A.quarter_fix - c;
+    const int colfix = c + A.col_half_fix;
+    const int cfrac = colfix & ((1 << FB) - 1);
+    if (!(cfrac >= A.col_margin && cfrac <= (1 << FB) - A.col_margin)) return 2;
+    int col = colfix >> FB;
+    if (row < 0 || row >= kp.H || col < 0) return 2;  // cannot happen inside the gates; let the exact path decide
+    if (kp.variant == GS_VARIANT_CLOUD2RANGE) {
+        if (col >= kp.W) return 2;
+    } else if (kp.col_policy == GS_COL_WRAP) {
+        if (col >= kp.W) col -= kp.W;
+    } else {
+        if (col > kp.W) return 2;
+        if (col == kp.W && row == kp.H - 1) return 1;  // Q2: flat index past the end of the image
+    }
+    *row_out = row;
+    *col_out = col;
+    *enc_out = static_cast<unsigned>(e);
+    return 0;
+}
+
 // cheap column estimate used only to deal point blocks to CTAs (any answer is correct, a good one is fast)
 __device__ __forceinline__ int approx_col(const KParams& kp, float x, float y) {
     float a = atan2f(y, x);
@@ -307,7 +402,7 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
     uint2* rlist = A.rlist + (static_cast<size_t>(cluster_id) * CL + rank) * A.rcap;
     unsigned* rcount = A.rcount + static_cast<size_t>(cluster_id) * CL;
 
-    unsigned long long st_dropped = 0, st_near = 0, st_near_angle = 0, st_remote = 0;
+    unsigned long long st_dropped = 0, st_near = 0, st_near_angle = 0, st_remote = 0, st_fallback = 0, st_mismatch = 0;
 
     for (int f = cluster_id; f < A.frames; f += n_clusters) {
         const long long beg = A.offsets[f], end = A.offsets[f + 1];
@@ -333,7 +428,7 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
             for (int k = 0; k < 4; ++k) {
                 const int i = min(base + 32 + 64 * k, N - 1);
                 const float4 q = __ldg(pts + i);
-                const int o = min(approx_col(kp, q.x, q.y) / CW, CL - 1);
+                const int o = min(static_cast<int>(__umulhi(static_cast<unsigned>(approx_col(kp, q.x, q.y)), A.cw_magic)), CL - 1);
 #pragma unroll
                 for (int j = 0; j < MAX_CL; ++j) votes[j] += (j == o);
             }
@@ -375,21 +470,34 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
                 unsigned k = 0x80000000u | lane;  // unique per lane: never matches
                 if (i >= 0) {
                     const float4 p4 = __ldcs(pts + i);
-                    const Proj pr = project_point_d(kp, p4.x, p4.y, p4.z);
-                    if (A.stats) {
-                        if (pr.row < 0) ++st_dropped;
-                        else if (pr.near_edge) ++st_near;
+                    int row = -1, col = -1;
+                    unsigned enc = 0;
+                    int st = A.use_fast ? project_fast(A, p4.x, p4.y, p4.z, &row, &col, &enc) : 2;
+                    if (st == 2 || A.stats) {
+                        // exact evaluation: the undecided points, and every point when statistics are collected
+                        const Proj pr = project_point_d(kp, p4.x, p4.y, p4.z);
+                        if (A.stats) {
+                            if (st == 2) ++st_fallback;
+                            else if ((st == 1) != (pr.row < 0) || (st == 0 && (row != pr.row || col != pr.col || enc != pr.enc))) ++st_mismatch;
+                            if (pr.row < 0) ++st_dropped;
+                            else if (pr.near_edge) ++st_near;
+                        }
+                        if (st == 2) {
+                            row = pr.row;
+                            col = pr.col;
+                            enc = pr.enc;
+                            st = pr.row < 0 ? 1 : 0;
+                        }
                     }
-                    if (pr.row >= 0) {
-                        int row = pr.row, col = pr.col;
+                    if (st == 0) {
                         if (col == W) {  // Q2: at<ushort>(row, W) is flat index (row + 1) * W
                             row += 1;
                             col = 0;
                         }
-                        const int owner = min(col / CW, CL - 1);
+                        const int owner = min(static_cast<int>(__umulhi(static_cast<unsigned>(col), A.cw_magic)), CL - 1);
                         const int lc = col - owner * CW;
                         k = (static_cast<unsigned>(owner) << 16) | static_cast<unsigned>(row * S16 + lc);
-                        val[j] = ((static_cast<unsigned>(i >> 5) + 1u) << 16) | pr.enc;
+                        val[j] = ((static_cast<unsigned>(i >> 5) + 1u) << 16) | enc;
                     }
                 }
                 // the highest lane among the lanes that hit the same pixel holds the latest point of this group
@@ -505,14 +613,28 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
                         const double rng = decode_range_d(kp, e);
                         const float sy = A.lut.sin_y[r], cy = A.lut.cos_y[r];
                         if (has_prev) {
-                            const double dz = fabs(__dsub_rn(static_cast<double>(p_z), __dmul_rn(rng, static_cast<double>(sy))));
-                            const double dx = fabs(__dsub_rn(static_cast<double>(p_x), __dmul_rn(rng, static_cast<double>(cy))));
-                            const float alfa = gs_atan2f(__double2float_rn(dz), __double2float_rn(dx));  // :368
-                            const float scaled = __fmul_rn(alfa, 100.0f);                                 // :370
-                            a_out = static_cast<unsigned>(__float2int_rz(scaled));
-                            if (A.stats) {
-                                const float fr = scaled - floorf(scaled);
-                                if (fminf(fr, 1.0f - fr) < 1e-3f) ++st_near_angle;
+                            const float dz = __double2float_rn(fabs(__dsub_rn(static_cast<double>(p_z), __dmul_rn(rng, A.lut.sin_y_d[r]))));  // :366
+                            const float dx = __double2float_rn(fabs(__dsub_rn(static_cast<double>(p_x), __dmul_rn(rng, A.lut.cos_y_d[r]))));  // :367
+                            // fast: float atan with a 2e-7 rad error budget; results within 4e-6 rad of a centi-radian edge
+                            // (and 0/0) are recomputed with the bit-exact clone of the host's atan2f
+                            float t = atan01(__fdividef(fminf(dz, dx), fmaxf(dz, dx)));
+                            if (dz > dx) t = 1.57079632679489662f - t;
+                            const float sc = __fmul_rn(t, 100.0f);
+                            const int kk = __float2int_rd(sc);
+                            const float fr = sc - static_cast<float>(kk);
+                            const bool sure = A.use_fast && fr > 4e-4f && fr < 1.0f - 4e-4f;
+                            a_out = static_cast<unsigned>(kk);
+                            if (!sure || A.stats) {
+                                const float alfa = gs_atan2f(dz, dx);          // :368
+                                const float scaled = __fmul_rn(alfa, 100.0f);  // :370
+                                const unsigned exact = static_cast<unsigned>(__float2int_rz(scaled));
+                                if (A.stats) {
+                                    const float fe = scaled - floorf(scaled);
+                                    if (fminf(fe, 1.0f - fe) < 1e-3f) ++st_near_angle;
+                                    if (!sure) ++st_fallback;
+                                    else if (exact != a_out) ++st_mismatch;
+                                }
+                                if (!sure) a_out = exact;
                             }
                         }
                         const float rf = __double2float_rn(rng);
@@ -597,7 +719,22 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
             s_halo_masks[3 * 2 + tid] = lm[(MK_HM * NW + tid) * CWp + left_last];
             s_halo_masks[4 * 2 + tid] = lm[(MK_HA * NW + tid) * CWp + left_last];
         }
-        // flood fill: G[c] <- vfill(G[c] | (G[c-1] & HM[c-1]) | (G[c+1] & HM[c]))  until nothing changes anywhere
+        // Flood fill of the ground label (the Labeler's BFS, label.cpp:48-104, as reachability): alternate a vertical
+        // closure in the column domain (one row mask per column, links V) with a horizontal closure in the row domain
+        // (one column mask per row, links HMR); each closure runs along whole runs with one carry-propagating addition, so
+        // the number of alternations is the number of turns of the longest path, not its length.  Slab boundaries (and
+        // the column wrap of Label::WrapCols) are crossed once per outer round through the neighbours' boundary columns.
+        unsigned* s_gr = s_rowmask;   // [H][NG] G in the row domain
+        unsigned* s_hmr = s_grp;      // [H][NG] bit l of word g, row r: columns 32g+l and 32g+l+1 of my slab are linked
+        for (int gidx = warp; gidx < NG; gidx += NT / 32) {
+            const int c = gidx * 32 + lane;
+            Mask<NW> hm = Mask<NW>::zero();
+            if (c < myCW - 1) hm = ld_mask<NW>(s_masks, MK_HM, CWp, c);  // the last column's link crosses the slab boundary
+            for (int r = 0; r < H; ++r) {
+                const unsigned m = __ballot_sync(0xffffffffu, hm.bit(r));
+                if (lane == 0) s_hmr[r * NG + gidx] = m;
+            }
+        }
         for (;;) {
             // import the neighbours' boundary columns of G
             if (tid < NW) {
@@ -605,37 +742,91 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
                 s_halo_masks[2 * 2 + tid] = cluster.map_shared_rank(s_masks, left_rank)[(MK_G * NW + tid) * CWp + left_last];
             }
             __syncthreads();
-            bool any_change = false;
+            bool inflow = false;
+            if (tid == 0) {
+                Mask<NW> gl, hl, gr;
+                gl.w0 = s_halo_masks[2 * 2 + 0];
+                hl.w0 = s_halo_masks[3 * 2 + 0];
+                gr.w0 = s_halo_masks[1 * 2 + 0];
+                if constexpr (NW == 2) { gl.w1 = s_halo_masks[2 * 2 + 1]; hl.w1 = s_halo_masks[3 * 2 + 1]; gr.w1 = s_halo_masks[1 * 2 + 1]; }
+                const Mask<NW> g0 = ld_mask<NW>(s_masks, MK_G, CWp, 0);
+                const Mask<NW> n0 = g0 | (gl & hl);
+                if (n0 != g0) { st_mask<NW>(s_masks, MK_G, CWp, 0, n0); inflow = true; }
+                const Mask<NW> g1 = ld_mask<NW>(s_masks, MK_G, CWp, myCW - 1);
+                const Mask<NW> n1 = g1 | (gr & ld_mask<NW>(s_masks, MK_HM, CWp, myCW - 1));
+                if (n1 != g1) { st_mask<NW>(s_masks, MK_G, CWp, myCW - 1, n1); inflow = true; }
+            }
+            bool any_change = __syncthreads_or(inflow ? 1 : 0) != 0;
             for (int it = 0;; ++it) {
-                bool changed = false;
+                // vertical closure, column domain
+                bool ch = false;
                 for (int c = tid; c < myCW; c += NT) {
                     const Mask<NW> g = ld_mask<NW>(s_masks, MK_G, CWp, c);
-                    Mask<NW> gl, hl, gr;
-                    if (c == 0) {
-                        gl.w0 = s_halo_masks[2 * 2 + 0];
-                        hl.w0 = s_halo_masks[3 * 2 + 0];
-                        if constexpr (NW == 2) { gl.w1 = s_halo_masks[2 * 2 + 1]; hl.w1 = s_halo_masks[3 * 2 + 1]; }
-                    } else {
-                        gl = ld_mask<NW>(s_masks, MK_G, CWp, c - 1);
-                        hl = ld_mask<NW>(s_masks, MK_HM, CWp, c - 1);
-                    }
-                    if (c == myCW - 1) {
-                        gr.w0 = s_halo_masks[1 * 2 + 0];
-                        if constexpr (NW == 2) gr.w1 = s_halo_masks[1 * 2 + 1];
-                    } else {
-                        gr = ld_mask<NW>(s_masks, MK_G, CWp, c + 1);
-                    }
-                    const Mask<NW> hm = ld_mask<NW>(s_masks, MK_HM, CWp, c);
-                    const Mask<NW> in = g | (gl & hl) | (gr & hm);
-                    if (in != g) {
-                        const Mask<NW> v = ld_mask<NW>(s_masks, MK_V, CWp, c);
-                        st_mask<NW>(s_masks, MK_G, CWp, c, vfill<NW>(in, v, H));
-                        changed = true;
+                    const Mask<NW> ng = vfill<NW>(g, ld_mask<NW>(s_masks, MK_V, CWp, c), H);
+                    if (ng != g) {
+                        st_mask<NW>(s_masks, MK_G, CWp, c, ng);
+                        ch = true;
                     }
                 }
-                const int any = __syncthreads_or(changed ? 1 : 0);
-                if (!any) break;
+                const int cv = __syncthreads_or(ch ? 1 : 0);
+                if (cv) any_change = true;
+                if (it > 0 && !cv) break;
+                // column domain -> row domain
+                for (int gidx = warp; gidx < NG; gidx += NT / 32) {
+                    const int c = gidx * 32 + lane;
+                    Mask<NW> g = Mask<NW>::zero();
+                    if (c < myCW) g = ld_mask<NW>(s_masks, MK_G, CWp, c);
+                    for (int r = 0; r < H; ++r) {
+                        const unsigned m = __ballot_sync(0xffffffffu, g.bit(r));
+                        if (lane == 0) s_gr[r * NG + gidx] = m;
+                    }
+                }
+                __syncthreads();
+                // horizontal closure, row domain: one thread per row, carries run through the NG words of the row
+                bool chh = false;
+                for (int r = tid; r < H; r += NT) {
+                    unsigned* gr_row = s_gr + r * NG;
+                    const unsigned* l_row = s_hmr + r * NG;
+                    unsigned carry = 0, prev_g = 0, prev_l = 0;
+                    for (int w = 0; w < NG; ++w) {  // towards higher columns: column c is linked to c-1 by link bit c-1
+                        const unsigned g = gr_row[w], l = l_row[w];
+                        const unsigned Aw = (l << 1) | (prev_l >> 31);
+                        const unsigned cb = ((g << 1) | (prev_g >> 31)) & Aw;
+                        const unsigned long long sum = static_cast<unsigned long long>(Aw) + cb + carry;
+                        carry = static_cast<unsigned>(sum >> 32);
+                        const unsigned res = g | cb | ((static_cast<unsigned>(sum) ^ Aw) & Aw);
+                        chh |= res != g;
+                        gr_row[w] = res;
+                        prev_g = res;
+                        prev_l = l;
+                    }
+                    carry = 0;
+                    prev_g = 0;
+                    for (int w = NG - 1; w >= 0; --w) {  // towards lower columns: the same on the bit-reversed row
+                        const unsigned g0 = gr_row[w];
+                        const unsigned g = __brev(g0), Aw = __brev(l_row[w]);
+                        const unsigned cb = ((g << 1) | (prev_g >> 31)) & Aw;
+                        const unsigned long long sum = static_cast<unsigned long long>(Aw) + cb + carry;
+                        carry = static_cast<unsigned>(sum >> 32);
+                        const unsigned res = g | cb | ((static_cast<unsigned>(sum) ^ Aw) & Aw);
+                        chh |= res != g;
+                        gr_row[w] = __brev(res);
+                        prev_g = res;
+                    }
+                }
+                const int chv = __syncthreads_or(chh ? 1 : 0);
+                if (!chv) break;
                 any_change = true;
+                // row domain -> column domain
+                for (int c = tid; c < myCW; c += NT) {
+                    Mask<NW> g = Mask<NW>::zero();
+                    const unsigned* col_word = s_gr + (c >> 5);
+                    const int sh = c & 31;
+                    for (int r = 0; r < H; ++r)
+                        if ((col_word[r * NG] >> sh) & 1u) g.set(r);
+                    st_mask<NW>(s_masks, MK_G, CWp, c, g);  // the row-domain image is a superset of the old column
+                }
+                __syncthreads();
             }
             // cluster-wide: did any slab change in this outer round?
             if (tid < CL) cluster.map_shared_rank(s_flags, tid)[rank] = any_change ? 1u : 0u;
@@ -728,17 +919,17 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
             uint16_t* res = A.res_out ? A.res_out + static_cast<size_t>(f) * kp.P : nullptr;
             float4* cloud = A.xyz_out ? A.xyz_out + static_cast<size_t>(f) * kp.P : nullptr;
             const bool range_as_double = kp.variant == GS_VARIANT_CLOUD2RANGE;
-            for (int idx = tid; idx < H * NG * 32; idx += NT) {
-                const int r = idx / (NG * 32);
-                const int cc = idx - r * (NG * 32);
-                const int gidx = cc >> 5;
+            for (int pair = warp; pair < H * NG; pair += NT / 32) {  // one warp per (row, 32-column group)
+                const int r = static_cast<int>(__umulhi(static_cast<unsigned>(pair), A.ng_magic));
+                const int gidx = pair - r * NG;
+                const int cc = gidx * 32 + lane;
                 if (cc < myCW) {
-                    const unsigned m = s_rowmask[r * NG + gidx];
+                    const unsigned m = s_rowmask[pair];
                     const bool keep = (m >> lane) & 1u;
                     const unsigned enc = s_range[r * S16 + cc];
                     if (res) res[r * W + col0 + cc] = keep ? static_cast<uint16_t>(enc) : static_cast<uint16_t>(0);
                     if (keep && cloud) {
-                        const unsigned slot = s_rowbase[r] + s_grp[r * NG + gidx] + __popc(m & ((1u << lane) - 1u));
+                        const unsigned slot = s_rowbase[r] + s_grp[pair] + __popc(m & ((1u << lane) - 1u));
                         const double rng_d = decode_range_d(kp, enc);
                         const double rng = range_as_double ? rng_d : static_cast<double>(__double2float_rn(rng_d));  // alfa_gs.cpp:1027,1045 / range2cloud_node.cpp:76
                         const double ca = A.lut.cos_alt[r], sa = A.lut.sin_alt[r];
@@ -761,7 +952,9 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
         if (st_dropped) atomicAdd(&A.cnt->dropped, st_dropped);
         if (st_near) atomicAdd(&A.cnt->near_edge_project, st_near);
         if (st_near_angle) atomicAdd(&A.cnt->near_edge_angle, st_near_angle);
-        if (st_remote) atomicAdd(&A.cnt->slow_path, st_remote);
+        if (st_remote) atomicAdd(&A.cnt->remote, st_remote);
+        if (st_fallback) atomicAdd(&A.cnt->slow_path, st_fallback);
+        if (st_mismatch) atomicAdd(&A.cnt->fast_mismatch, st_mismatch);
     }
     cluster.sync();  // no CTA exits while a neighbour may still address its shared memory
 }
@@ -928,6 +1121,30 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
     a.cnt = cnt;
     a.stats = stats ? 1 : 0;
     a.rcap = rcap;
+    // fast-path constants (see project_fast)
+    {
+        const double two_fb = static_cast<double>(1 << FB);
+        const bool c2r = kp.variant == GS_VARIANT_CLOUD2RANGE;
+        const double alt_scale = c2r ? static_cast<double>(kp.H) / kp.ang_span : 1.0 / kp.d_alt;  // cloud2range_node.cpp:436 / alfa_gs.cpp:275
+        const double row0 = c2r ? kp.max_angle * alt_scale : static_cast<double>(kp.H - 1) + (kp.half_d_alt + kp.min_angle) / kp.d_alt;
+        const double az_scale = static_cast<double>(kp.W) / 6.283185307179586476925286766559;   // = 1 / d_azimuth
+        a.enc_scale = 65534.0 / kp.span;
+        a.alt_to_fix = static_cast<float>(alt_scale * two_fb);
+        a.az_to_fix = static_cast<float>(az_scale * two_fb);
+        a.alt_lo = static_cast<float>(kp.min_angle);
+        a.alt_hi = static_cast<float>(kp.max_angle);
+        a.row0_fix = static_cast<int>(llround(row0 * two_fb));
+        a.quarter_fix = kp.W << (FB - 2);
+        a.col_half_fix = c2r ? 0 : (1 << (FB - 1));
+        a.row_margin = static_cast<int>(std::ceil(1.0e-6 * alt_scale * two_fb)) + 8;   // 1e-6 rad >= 4x the altitude error budget
+        a.col_margin = static_cast<int>(std::ceil(7.5e-7 * az_scale * two_fb)) + 8;    // 7.5e-7 rad >= 4x the azimuth error budget
+        a.cw_magic = static_cast<unsigned>((0x100000000ull + lay.CW - 1) / lay.CW);
+        a.ng_magic = static_cast<unsigned>((0x100000000ull + lay.NG - 1) / lay.NG);
+        a.mycw_shift = 0;
+        // the fixed-point coordinates need 4 * quarter_fix < 2^31 and |altitude cells| * 2^FB < 2^31
+        a.use_fast = (kp.W <= 8191 && alt_scale * 1.6 * two_fb < 2.0e9 && std::fabs(row0) * two_fb < 2.0e9 &&
+                      a.row_margin < (1 << (FB - 2)) && a.col_margin < (1 << (FB - 2))) ? 1 : 0;
+    }
     a.rlist = reinterpret_cast<uint2*>(fs.d_rowbase);
     a.rcount = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(fs.d_rowbase) +
                                            static_cast<size_t>(fs.max_clusters) * lay.CL * rcap * sizeof(uint2));

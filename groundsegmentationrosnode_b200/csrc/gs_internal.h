@@ -27,6 +27,8 @@ struct Luts {
     const double* sin_alt;  // [H]
     const double* cos_az;   // [W] cos(c*d_az)                  alfa_gs.cpp:1052
     const double* sin_az;   // [W]
+    const double* sin_y_d;  // [H] (double)sinf(angle_y(row)): the value the reference widens in alfa_gs.cpp:366
+    const double* cos_y_d;  // [H]
 };
 
 struct SgTaps {
@@ -35,7 +37,7 @@ struct SgTaps {
 };
 
 struct Counters {
-    unsigned long long near_edge_project, near_edge_angle, dropped, slow_path, components;
+    unsigned long long near_edge_project, near_edge_angle, dropped, slow_path, components, fast_mismatch, remote;
 };
 
 // Device scratch for one wave ("chunk") of frames; every array holds `frames` slabs.

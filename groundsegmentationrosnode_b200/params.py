@@ -76,6 +76,8 @@ class GsStats(C.Structure):
         ("near_edge_angle", C.c_uint64),
         ("dropped_points", C.c_uint64),
         ("slow_path_points", C.c_uint64),
+        ("fast_path_mismatches", C.c_uint64),
+        ("remote_points", C.c_uint64),
     ]
 
 

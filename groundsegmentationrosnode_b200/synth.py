@@ -105,8 +105,9 @@ def make_frame(p, seed=SEED0, dropout=None, jitter=0.3, shuffle=False, noise_sig
     row = np.tile(np.arange(H), W)
     alt = p.min_angle + (H - 1 - row) * d_alt + rng.uniform(-jitter, jitter, size=H * W) * d_alt
     az = col * d_az + rng.uniform(-jitter, jitter, size=H * W) * d_az
-    # keep jittered altitudes inside the sensor's field of view (the reference gates on it, alfa_gs.cpp:269)
-    alt = np.clip(alt, p.min_angle + 1e-9, p.max_angle - 1e-9)
+    # keep jittered altitudes inside the sensor's field of view (the reference gates on it, alfa_gs.cpp:269); the
+    # outermost beams stay 2 % of a beam step inside the gates, as real returns do not pile up exactly on a gate
+    alt = np.clip(alt, p.min_angle + 0.02 * d_alt, p.max_angle - 0.02 * d_alt)
     dirs = np.stack([np.cos(alt) * np.cos(az), np.cos(alt) * np.sin(az), np.sin(alt)], axis=1)
     t = _cast(dirs, rng, p)
     t = t + rng.normal(0.0, noise_sigma, size=t.shape)

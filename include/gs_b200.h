@@ -110,7 +110,11 @@ typedef struct gs_stats {
     uint64_t near_edge_project; /* points whose altitude/azimuth lies within 1e-5 rad of a cell edge */
     uint64_t near_edge_angle;   /* pixels whose inclination angle lies within 1e-5 rad of a centi-radian edge */
     uint64_t dropped_points;    /* points skipped by range/altitude gates or falling outside the image */
-    uint64_t slow_path_points;  /* points that took the double-precision re-check in the projection */
+    uint64_t slow_path_points;  /* points / pixels whose fast (float) evaluation fell inside its certified error margin of a
+                                   quantisation edge and were re-evaluated with the reference's exact arithmetic */
+    uint64_t fast_path_mismatches; /* with GS_OPT_COLLECT_STATS the fused kernel evaluates BOTH paths for every point and pixel and
+                                      counts accepted fast results that differ from the exact ones: must stay 0 */
+    uint64_t remote_points;     /* points whose pixel lives in another CTA of the frame's cluster (distributed shared memory path) */
 } gs_stats;
 
 /* ---- parameters --------------------------------------------------------------------------- */

@@ -45,6 +45,18 @@ int main(int argc, char** argv) {
         ++n;
         if (gs_f2i(atan2f(sp[i][0], sp[i][1])) != gs_f2i(gs_atan2f(sp[i][0], sp[i][1]))) ++bad;
     }
-    printf("n=%ld bad=%ld\n", n, bad);
-    return bad ? 1 : 0;
+    // decode_range (gs_fused.cu): n / 65534.0 as q0 = n*R, r = fma(-q0, 65534, n), q = fma(r, R, q0) — exhaustive
+    long bad_div = 0;
+    {
+        const double R = 1.0 / 65534.0;
+        for (int k = 0; k <= 65534; ++k) {
+            const double nn = (double)k;
+            const double q0 = nn * R;
+            const double r = fma(-q0, 65534.0, nn);
+            const double q = fma(r, R, q0);
+            if (q != nn / 65534.0) ++bad_div;
+        }
+    }
+    printf("n=%ld bad=%ld bad_div=%ld\n", n, bad, bad_div);
+    return (bad || bad_div) ? 1 : 0;
 }

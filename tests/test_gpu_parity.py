@@ -82,6 +82,10 @@ def test_full_pipeline_matches_oracle(ctxs, oracle, name, staged):
         st = ctx.stats()
         _, ne_p, _ = oracle.create_range_image(p, pts, with_counts=True)
         assert st.near_edge_project == ne_p
+        # with statistics on, the fused kernel evaluates the exact arithmetic beside every fast result it accepts
+        assert st.fast_path_mismatches == 0
+        if not staged:
+            assert st.slow_path_points < 0.02 * (pts.shape[0] + p.n_beams * p.n_cols)
         bad = _assert_images_equal(got["range"], want["range"], "range image", _mismatch_budget(ne_p))
         if bad == 0:
             _assert_images_equal(got["angle"], want["angle"], "angle image")
@@ -171,6 +175,7 @@ def test_adversarial_frames(ctxs, oracle, name, kind, staged):
     got = ctx.process_frame(pts)
     st = ctx.stats()
     assert st.dropped_points == dropped
+    assert st.fast_path_mismatches == 0
     budget = ne_p if kind == "edges" else 0
     bad = _assert_images_equal(got["range"], want["range"], "range image", budget)
     if bad:
