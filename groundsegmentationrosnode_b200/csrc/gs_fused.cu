@@ -52,7 +52,7 @@ struct FusedArgs {
     int S8;       // row stride of the angle slab, bytes
     int NG;       // 32-column groups per slab
     // shared memory offsets (bytes)
-    unsigned off_range, off_tag, off_angle, off_misc;
+    unsigned off_range, off_tag, off_angle, off_masks, off_misc;
     const float4* points;
     const long long* offsets;
     int frames;
@@ -128,6 +128,40 @@ __device__ __forceinline__ void cas_max_u16(uint16_t* p, unsigned v) {
     }
 }
 
+// Union-find over vertical runs, 16-bit parents in shared memory: bits 0..14 = parent index, bit 15 = "ground" flag
+// (meaningful on roots).  Roots hang under the smaller index, so the forest is acyclic without ranks.
+__device__ __forceinline__ int uf16_find(const volatile uint16_t* par, int x) {
+    for (;;) {
+        const int p = par[x] & 0x7fff;
+        if (p == x) return x;
+        x = p;
+    }
+}
+__device__ __forceinline__ void uf16_unite(uint16_t* par, int a, int b) {
+    for (;;) {
+        a = uf16_find(par, a);
+        b = uf16_find(par, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }
+        unsigned* w = reinterpret_cast<unsigned*>(par) + (a >> 1);
+        const int sh = (a & 1) * 16;
+        const unsigned old = *reinterpret_cast<volatile unsigned*>(w);
+        if (static_cast<int>((old >> sh) & 0xffffu) != a) continue;  // a stopped being a root meanwhile
+        const unsigned want = (old & ~(0xffffu << sh)) | (static_cast<unsigned>(b) << sh);
+        if (atomicCAS(w, old, want) == old) return;
+    }
+}
+__device__ __forceinline__ bool uf16_flag_root(uint16_t* par, int x) {  // returns true when the flag was newly set
+    for (;;) {
+        const int root = uf16_find(par, x);
+        unsigned* w = reinterpret_cast<unsigned*>(par) + (root >> 1);
+        const int sh = (root & 1) * 16;
+        const unsigned old = atomicOr(w, 0x8000u << sh);
+        // the flag phase runs after all unions: root is still a root
+        return ((old >> sh) & 0x8000u) == 0;
+    }
+}
+
 // Row masks: bit r of the 128-bit mask <-> image row r.
 struct M128 {
     unsigned long long lo, hi;
@@ -151,6 +185,8 @@ struct Mask<1> {
     __device__ __forceinline__ bool bit(int r) const { return (w0 >> r) & 1ull; }
     __device__ __forceinline__ void set(int r) { w0 |= 1ull << r; }
     __device__ __forceinline__ int top() const { return w0 ? 63 - __clzll(w0) : -1; }
+    __device__ __forceinline__ int lowest() const { return __ffsll(static_cast<long long>(w0)) - 1; }
+    __device__ __forceinline__ void clear_lowest() { w0 &= w0 - 1ull; }
     __device__ __forceinline__ unsigned word32(int i) const { return static_cast<unsigned>(w0 >> (32 * i)); }
     __device__ __forceinline__ static Mask low(int n) { return Mask{n >= 64 ? ~0ull : ((1ull << n) - 1ull)}; }
 };
@@ -187,6 +223,11 @@ struct Mask<2> {
         else w1 |= 1ull << (r - 64);
     }
     __device__ __forceinline__ int top() const { return w1 ? 127 - __clzll(w1) : (w0 ? 63 - __clzll(w0) : -1); }
+    __device__ __forceinline__ int lowest() const { return w0 ? __ffsll(static_cast<long long>(w0)) - 1 : (w1 ? 63 + __ffsll(static_cast<long long>(w1)) : -1); }
+    __device__ __forceinline__ void clear_lowest() {
+        if (w0) w0 &= w0 - 1ull;
+        else w1 &= w1 - 1ull;
+    }
     __device__ __forceinline__ unsigned word32(int i) const { return static_cast<unsigned>((i < 2 ? w0 : w1) >> (32 * (i & 1))); }
     __device__ __forceinline__ static Mask low(int n) {
         if (n >= 128) return Mask{~0ull, ~0ull};
@@ -213,7 +254,7 @@ __device__ __forceinline__ Mask<NW> vfill(Mask<NW> g, Mask<NW> link, int H) {
 }
 
 // mask storage in shared memory: [kind][word][column], u64 words
-enum { MK_VALID = 0, MK_VA, MK_HA, MK_V, MK_HM, MK_G, MK_KEEP, MK_COUNT };
+enum { MK_VALID = 0, MK_VA, MK_HA, MK_V, MK_HM, MK_G, MK_KEEP, MK_S, MK_COUNT };
 
 template <int NW>
 __device__ __forceinline__ Mask<NW> ld_mask(const unsigned long long* base, int kind, int CWp, int c) {
@@ -386,7 +427,8 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
     uint16_t* s_range = reinterpret_cast<uint16_t*>(smem_raw + A.off_range);
     uint16_t* s_tag = reinterpret_cast<uint16_t*>(smem_raw + A.off_tag);
     uint8_t* s_angle = smem_raw + A.off_angle;
-    unsigned long long* s_masks = reinterpret_cast<unsigned long long*>(smem_raw + A.off_tag);           // [MK_COUNT][NW][CW]
+    unsigned long long* s_masks = reinterpret_cast<unsigned long long*>(smem_raw + A.off_masks);         // [MK_COUNT][NW][CW]
+    uint16_t* s_par = s_tag;  // [CW][H] union-find parents of the vertical runs (the tag slab is dead after the projection)
     unsigned* s_rowmask = reinterpret_cast<unsigned*>(s_masks + static_cast<size_t>(MK_COUNT) * NW * CWp);  // [H][NG]
     unsigned* s_grp = s_rowmask + H * NG;                                                                  // [H][NG]
     uint8_t* s_assign = s_angle;                                                                           // [MAX_BLOCKS]
@@ -394,8 +436,8 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
     unsigned char* misc = smem_raw + A.off_misc;
     unsigned* s_rowcnt_all = reinterpret_cast<unsigned*>(misc);                         // [MAX_CL][MAX_H]
     unsigned* s_rowbase = s_rowcnt_all + MAX_CL * MAX_H;                                // [MAX_H]
-    unsigned long long* s_halo_masks = reinterpret_cast<unsigned long long*>(s_rowbase + MAX_H);  // [5][2]
-    uint8_t* s_halo_angle = reinterpret_cast<uint8_t*>(s_halo_masks + 10);              // [MAX_H]
+    unsigned long long* s_halo_masks = reinterpret_cast<unsigned long long*>(s_rowbase + MAX_H);  // [7][2]
+    uint8_t* s_halo_angle = reinterpret_cast<uint8_t*>(s_halo_masks + 14);              // [MAX_H]
     unsigned* s_flags = reinterpret_cast<unsigned*>(s_halo_angle + MAX_H);              // [MAX_CL]
     unsigned* s_misc = s_flags + MAX_CL;                                                // [0] nmine, [1] scratch
 
@@ -709,7 +751,13 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
             st_mask<NW>(s_masks, MK_HA, CWp, c, ha);
             st_mask<NW>(s_masks, MK_V, CWp, c, v);
             st_mask<NW>(s_masks, MK_HM, CWp, c, hm);
-            st_mask<NW>(s_masks, MK_G, CWp, c, vfill<NW>(g, v, H));
+            st_mask<NW>(s_masks, MK_G, CWp, c, g);  // the accepted non-empty seed pixel, if any
+            const Mask<NW> runs = valid & ~v.shl(1);  // first (lowest-index) pixel of every vertical run
+            st_mask<NW>(s_masks, MK_S, CWp, c, runs);
+            for (Mask<NW> it = runs; it.any(); it.clear_lowest()) {
+                const int node = c * H + it.lowest();
+                s_par[node] = static_cast<uint16_t>(node);
+            }
             st_mask<NW>(s_masks, MK_KEEP, CWp, c, keep);
         }
         cluster.sync();  // #5: HM / HA / G of every slab readable by the neighbours
@@ -719,123 +767,121 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
             s_halo_masks[3 * 2 + tid] = lm[(MK_HM * NW + tid) * CWp + left_last];
             s_halo_masks[4 * 2 + tid] = lm[(MK_HA * NW + tid) * CWp + left_last];
         }
-        // Flood fill of the ground label (the Labeler's BFS, label.cpp:48-104, as reachability): alternate a vertical
-        // closure in the column domain (one row mask per column, links V) with a horizontal closure in the row domain
-        // (one column mask per row, links HMR); each closure runs along whole runs with one carry-propagating addition, so
-        // the number of alternations is the number of turns of the longest path, not its length.  Slab boundaries (and
-        // the column wrap of Label::WrapCols) are crossed once per outer round through the neighbours' boundary columns.
-        unsigned* s_gr = s_rowmask;   // [H][NG] G in the row domain
-        unsigned* s_hmr = s_grp;      // [H][NG] bit l of word g, row r: columns 32g+l and 32g+l+1 of my slab are linked
-        for (int gidx = warp; gidx < NG; gidx += NT / 32) {
-            const int c = gidx * 32 + lane;
-            Mask<NW> hm = Mask<NW>::zero();
-            if (c < myCW - 1) hm = ld_mask<NW>(s_masks, MK_HM, CWp, c);  // the last column's link crosses the slab boundary
-            for (int r = 0; r < H; ++r) {
-                const unsigned m = __ballot_sync(0xffffffffu, hm.bit(r));
-                if (lane == 0) s_hmr[r * NG + gidx] = m;
+        // Ground label = reachability from the accepted seeds (the Labeler's BFS, label.cpp:48-104).  Nodes are the
+        // vertical runs of every column (maximal chains of V links); horizontal links unite runs of adjacent columns in
+        // a 16-bit union-find forest; seeds flag their root; slab boundaries (and the column wrap of Label::WrapCols)
+        // are crossed by exchanging the ground masks of the boundary columns until no flag changes in the cluster.
+        __syncthreads();
+        for (int c = tid; c < myCW - 1; c += NT) {
+            const Mask<NW> hm = ld_mask<NW>(s_masks, MK_HM, CWp, c);
+            if (!hm.any()) continue;
+            const Mask<NW> vboth = ld_mask<NW>(s_masks, MK_V, CWp, c) & ld_mask<NW>(s_masks, MK_V, CWp, c + 1);
+            // one union per pair of runs: skip link r when link r-1 joins the same two runs
+            Mask<NW> todo = hm & ~(hm & vboth).shl(1);
+            const Mask<NW> sa = ld_mask<NW>(s_masks, MK_S, CWp, c), sb = ld_mask<NW>(s_masks, MK_S, CWp, c + 1);
+            for (; todo.any(); todo.clear_lowest()) {
+                const int r = todo.lowest();
+                const Mask<NW> upto = Mask<NW>::low(r + 1);
+                uf16_unite(s_par, c * H + (sa & upto).top(), (c + 1) * H + (sb & upto).top());
             }
         }
+        __syncthreads();
+        for (int c = tid; c < myCW; c += NT) {
+            const Mask<NW> seed = ld_mask<NW>(s_masks, MK_G, CWp, c);
+            if (seed.any()) uf16_flag_root(s_par, c * H + (ld_mask<NW>(s_masks, MK_S, CWp, c) & Mask<NW>::low(seed.top() + 1)).top());
+        }
+        __syncthreads();
         for (;;) {
-            // import the neighbours' boundary columns of G
-            if (tid < NW) {
-                s_halo_masks[1 * 2 + tid] = cluster.map_shared_rank(s_masks, right_rank)[(MK_G * NW + tid) * CWp + 0];
-                s_halo_masks[2 * 2 + tid] = cluster.map_shared_rank(s_masks, left_rank)[(MK_G * NW + tid) * CWp + left_last];
+            // ground masks of my two boundary columns -> s_halo_masks[5], [6] (read by the neighbours)
+            if (warp < 2) {
+                const int c = warp == 0 ? 0 : myCW - 1;
+                const Mask<NW> valid = ld_mask<NW>(s_masks, MK_VALID, CWp, c);
+                Mask<NW> runs = ld_mask<NW>(s_masks, MK_S, CWp, c);
+                Mask<NW> g = Mask<NW>::zero();
+                // lane l takes runs l, l + 32, ...
+                for (int k = 0; runs.any(); ++k) {
+                    const int rs = runs.lowest();
+                    runs.clear_lowest();
+                    if ((k & 31) == lane) {
+                        const int root = uf16_find(s_par, c * H + rs);
+                        if (s_par[root] & 0x8000u) {
+                            const int next = runs.any() ? runs.lowest() : H;
+                            g = g | (valid & Mask<NW>::low(next) & ~Mask<NW>::low(rs));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    g.w0 |= __shfl_xor_sync(0xffffffffu, g.w0, d);
+                    if constexpr (NW == 2) g.w1 |= __shfl_xor_sync(0xffffffffu, g.w1, d);
+                }
+                if (lane == 0) {
+                    s_halo_masks[(5 + warp) * 2 + 0] = g.w0;
+                    if constexpr (NW == 2) s_halo_masks[(5 + warp) * 2 + 1] = g.w1;
+                }
             }
-            __syncthreads();
-            bool inflow = false;
-            if (tid == 0) {
-                Mask<NW> gl, hl, gr;
-                gl.w0 = s_halo_masks[2 * 2 + 0];
-                hl.w0 = s_halo_masks[3 * 2 + 0];
-                gr.w0 = s_halo_masks[1 * 2 + 0];
-                if constexpr (NW == 2) { gl.w1 = s_halo_masks[2 * 2 + 1]; hl.w1 = s_halo_masks[3 * 2 + 1]; gr.w1 = s_halo_masks[1 * 2 + 1]; }
-                const Mask<NW> g0 = ld_mask<NW>(s_masks, MK_G, CWp, 0);
-                const Mask<NW> n0 = g0 | (gl & hl);
-                if (n0 != g0) { st_mask<NW>(s_masks, MK_G, CWp, 0, n0); inflow = true; }
-                const Mask<NW> g1 = ld_mask<NW>(s_masks, MK_G, CWp, myCW - 1);
-                const Mask<NW> n1 = g1 | (gr & ld_mask<NW>(s_masks, MK_HM, CWp, myCW - 1));
-                if (n1 != g1) { st_mask<NW>(s_masks, MK_G, CWp, myCW - 1, n1); inflow = true; }
+            cluster.sync();
+            // import: right neighbour's column 0 and left neighbour's last column
+            bool changed = false;
+            if (warp < 2) {
+                Mask<NW> mine, theirs, link;
+                int c;
+                if (warp == 0) {  // my column 0 against the left neighbour's last column (link = its HM)
+                    c = 0;
+                    const unsigned long long* rm = cluster.map_shared_rank(s_halo_masks, left_rank);
+                    theirs.w0 = rm[6 * 2 + 0];
+                    link.w0 = s_halo_masks[3 * 2 + 0];
+                    mine.w0 = s_halo_masks[5 * 2 + 0];
+                    if constexpr (NW == 2) { theirs.w1 = rm[6 * 2 + 1]; link.w1 = s_halo_masks[3 * 2 + 1]; mine.w1 = s_halo_masks[5 * 2 + 1]; }
+                    if (lane == 0) {
+                        s_halo_masks[2 * 2 + 0] = theirs.w0;
+                        if constexpr (NW == 2) s_halo_masks[2 * 2 + 1] = theirs.w1;
+                    }
+                } else {  // my last column against the right neighbour's column 0 (link = my HM)
+                    c = myCW - 1;
+                    const unsigned long long* rm = cluster.map_shared_rank(s_halo_masks, right_rank);
+                    theirs.w0 = rm[5 * 2 + 0];
+                    mine.w0 = s_halo_masks[6 * 2 + 0];
+                    if constexpr (NW == 2) { theirs.w1 = rm[5 * 2 + 1]; mine.w1 = s_halo_masks[6 * 2 + 1]; }
+                    link = ld_mask<NW>(s_masks, MK_HM, CWp, c);
+                    if (lane == 0) {
+                        s_halo_masks[1 * 2 + 0] = theirs.w0;
+                        if constexpr (NW == 2) s_halo_masks[1 * 2 + 1] = theirs.w1;
+                    }
+                }
+                Mask<NW> in = theirs & link & ~mine;  // ground reaches these pixels of mine across the boundary
+                const Mask<NW> runs = ld_mask<NW>(s_masks, MK_S, CWp, c);
+                for (int k = 0; in.any(); ++k) {
+                    const int r = in.lowest();
+                    in.clear_lowest();
+                    if ((k & 31) == lane) changed |= uf16_flag_root(s_par, c * H + (runs & Mask<NW>::low(r + 1)).top());
+                }
             }
-            bool any_change = __syncthreads_or(inflow ? 1 : 0) != 0;
-            for (int it = 0;; ++it) {
-                // vertical closure, column domain
-                bool ch = false;
-                for (int c = tid; c < myCW; c += NT) {
-                    const Mask<NW> g = ld_mask<NW>(s_masks, MK_G, CWp, c);
-                    const Mask<NW> ng = vfill<NW>(g, ld_mask<NW>(s_masks, MK_V, CWp, c), H);
-                    if (ng != g) {
-                        st_mask<NW>(s_masks, MK_G, CWp, c, ng);
-                        ch = true;
-                    }
-                }
-                const int cv = __syncthreads_or(ch ? 1 : 0);
-                if (cv) any_change = true;
-                if (it > 0 && !cv) break;
-                // column domain -> row domain
-                for (int gidx = warp; gidx < NG; gidx += NT / 32) {
-                    const int c = gidx * 32 + lane;
-                    Mask<NW> g = Mask<NW>::zero();
-                    if (c < myCW) g = ld_mask<NW>(s_masks, MK_G, CWp, c);
-                    for (int r = 0; r < H; ++r) {
-                        const unsigned m = __ballot_sync(0xffffffffu, g.bit(r));
-                        if (lane == 0) s_gr[r * NG + gidx] = m;
-                    }
-                }
-                __syncthreads();
-                // horizontal closure, row domain: one thread per row, carries run through the NG words of the row
-                bool chh = false;
-                for (int r = tid; r < H; r += NT) {
-                    unsigned* gr_row = s_gr + r * NG;
-                    const unsigned* l_row = s_hmr + r * NG;
-                    unsigned carry = 0, prev_g = 0, prev_l = 0;
-                    for (int w = 0; w < NG; ++w) {  // towards higher columns: column c is linked to c-1 by link bit c-1
-                        const unsigned g = gr_row[w], l = l_row[w];
-                        const unsigned Aw = (l << 1) | (prev_l >> 31);
-                        const unsigned cb = ((g << 1) | (prev_g >> 31)) & Aw;
-                        const unsigned long long sum = static_cast<unsigned long long>(Aw) + cb + carry;
-                        carry = static_cast<unsigned>(sum >> 32);
-                        const unsigned res = g | cb | ((static_cast<unsigned>(sum) ^ Aw) & Aw);
-                        chh |= res != g;
-                        gr_row[w] = res;
-                        prev_g = res;
-                        prev_l = l;
-                    }
-                    carry = 0;
-                    prev_g = 0;
-                    for (int w = NG - 1; w >= 0; --w) {  // towards lower columns: the same on the bit-reversed row
-                        const unsigned g0 = gr_row[w];
-                        const unsigned g = __brev(g0), Aw = __brev(l_row[w]);
-                        const unsigned cb = ((g << 1) | (prev_g >> 31)) & Aw;
-                        const unsigned long long sum = static_cast<unsigned long long>(Aw) + cb + carry;
-                        carry = static_cast<unsigned>(sum >> 32);
-                        const unsigned res = g | cb | ((static_cast<unsigned>(sum) ^ Aw) & Aw);
-                        chh |= res != g;
-                        gr_row[w] = __brev(res);
-                        prev_g = res;
-                    }
-                }
-                const int chv = __syncthreads_or(chh ? 1 : 0);
-                if (!chv) break;
-                any_change = true;
-                // row domain -> column domain
-                for (int c = tid; c < myCW; c += NT) {
-                    Mask<NW> g = Mask<NW>::zero();
-                    const unsigned* col_word = s_gr + (c >> 5);
-                    const int sh = c & 31;
-                    for (int r = 0; r < H; ++r)
-                        if ((col_word[r * NG] >> sh) & 1u) g.set(r);
-                    st_mask<NW>(s_masks, MK_G, CWp, c, g);  // the row-domain image is a superset of the old column
-                }
-                __syncthreads();
-            }
-            // cluster-wide: did any slab change in this outer round?
+            const int any_change = __syncthreads_or(changed ? 1 : 0);
             if (tid < CL) cluster.map_shared_rank(s_flags, tid)[rank] = any_change ? 1u : 0u;
             cluster.sync();
             unsigned anyone = 0;
             for (int k = 0; k < CL; ++k) anyone |= s_flags[k];
-            cluster.sync();  // flags consumed before the next round overwrites them; G stable for the next import
             if (!anyone) break;
+            // (the next round's first cluster.sync orders these flag reads before the flags are rewritten)
         }
+        // read the ground mask of every column out of the forest
+        for (int c = tid; c < myCW; c += NT) {
+            const Mask<NW> valid = ld_mask<NW>(s_masks, MK_VALID, CWp, c);
+            Mask<NW> runs = ld_mask<NW>(s_masks, MK_S, CWp, c);
+            Mask<NW> g = Mask<NW>::zero();
+            while (runs.any()) {
+                const int rs = runs.lowest();
+                runs.clear_lowest();
+                const int root = uf16_find(s_par, c * H + rs);
+                if (s_par[root] & 0x8000u) {
+                    const int next = runs.any() ? runs.lowest() : H;
+                    g = g | (valid & Mask<NW>::low(next) & ~Mask<NW>::low(rs));
+                }
+            }
+            st_mask<NW>(s_masks, MK_G, CWp, c, g);
+        }
+        __syncthreads();
 
         // ================================================================================ D: label image, dilation, erase
         // L = G | accepted empty seeds | empty pixels 4-adjacent to a ground pixel u with |angle(u) - angle(p)| <= K
@@ -966,7 +1012,7 @@ namespace {
 
 struct Layout {
     int CL, CW, S16, S8, NG;
-    unsigned off_range, off_tag, off_angle, off_misc;
+    unsigned off_range, off_tag, off_angle, off_masks, off_misc;
     size_t total;
 };
 
@@ -985,16 +1031,18 @@ bool layout_for(const KParams& kp, int CL, int NW, Layout* L) {
     if (((L->S8 / 4) & 1) == 0) L->S8 += 4;
     L->NG = (CW + 31) / 32;
     if (static_cast<size_t>(H) * L->S16 > 65535) return false;  // slab addresses are 16-bit
+    if (static_cast<size_t>(H) * CW > 32768) return false;      // run indices are 15-bit
     const size_t range_bytes = align_up(static_cast<size_t>(H) * L->S16 * 2, 16);
-    const size_t masks_bytes = static_cast<size_t>(MK_COUNT) * NW * CW * 8 + static_cast<size_t>(2) * H * L->NG * 4;
-    const size_t tag_bytes = align_up(std::max(range_bytes, masks_bytes), 16);
+    const size_t masks_bytes = align_up(static_cast<size_t>(MK_COUNT) * NW * CW * 8 + static_cast<size_t>(2) * H * L->NG * 4, 16);
+    const size_t tag_bytes = align_up(std::max(range_bytes, static_cast<size_t>(H) * CW * 2), 16);
     const size_t angle_bytes = align_up(std::max(static_cast<size_t>(H) * L->S8, static_cast<size_t>(MAX_BLOCKS) * 3), 16);
-    const size_t misc_bytes = align_up(static_cast<size_t>(MAX_CL) * MAX_H * 4 + MAX_H * 4 + 10 * 8 + MAX_H + MAX_CL * 4 + 64, 16);
+    const size_t misc_bytes = align_up(static_cast<size_t>(MAX_CL) * MAX_H * 4 + MAX_H * 4 + 14 * 8 + MAX_H + MAX_CL * 4 + 64, 16);
     L->off_range = 0;
     L->off_tag = static_cast<unsigned>(range_bytes);
     L->off_angle = static_cast<unsigned>(range_bytes + tag_bytes);
-    L->off_misc = static_cast<unsigned>(range_bytes + tag_bytes + angle_bytes);
-    L->total = range_bytes + tag_bytes + angle_bytes + misc_bytes;
+    L->off_masks = static_cast<unsigned>(range_bytes + tag_bytes + angle_bytes);
+    L->off_misc = static_cast<unsigned>(range_bytes + tag_bytes + angle_bytes + masks_bytes);
+    L->total = range_bytes + tag_bytes + angle_bytes + masks_bytes + misc_bytes;
     return true;
 }
 
@@ -1109,6 +1157,7 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
     a.off_range = lay.off_range;
     a.off_tag = lay.off_tag;
     a.off_angle = lay.off_angle;
+    a.off_masks = lay.off_masks;
     a.off_misc = lay.off_misc;
     a.points = points;
     a.offsets = d_offsets;
