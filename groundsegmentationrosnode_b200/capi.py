@@ -16,11 +16,12 @@ LIB_PATH = os.path.join(HERE, "libgs_b200.so")
 
 GS_OPT_COLLECT_STATS = 1
 GS_OPT_FORCE_STAGED = 2
+GS_OPT_PHASE_TIMING = 3
 
 # every symbol include/gs_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "gs_abi_version", "gs_default_params", "gs_derive", "gs_create", "gs_destroy", "gs_set_params", "gs_get_params",
-    "gs_get_derived", "gs_set_stream", "gs_set_chunk_frames", "gs_set_option", "gs_get_stats", "gs_reset_stats",
+    "gs_get_derived", "gs_set_stream", "gs_set_chunk_frames", "gs_set_option", "gs_get_stats", "gs_reset_stats", "gs_get_phase_cycles",
     "gs_last_error", "gs_project", "gs_angle_image", "gs_smooth", "gs_repair_gaps", "gs_erase_ground",
     "gs_label_one_component", "gs_label_components", "gs_backproject", "gs_process_frame", "gs_process_batch_device",
     "gs_process_batch_host", "gs_synchronize",
@@ -65,6 +66,7 @@ def load(build_if_missing=False):
     L.gs_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.gs_get_stats.argtypes = [C.c_void_p, C.POINTER(GsStats)]
     L.gs_reset_stats.argtypes = [C.c_void_p]
+    L.gs_get_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.gs_last_error.argtypes = [C.c_void_p]
     L.gs_last_error.restype = C.c_char_p
     L.gs_project.argtypes = [C.c_void_p, vp, C.c_size_t, C.c_size_t, u16p]
@@ -175,6 +177,15 @@ class Context:
         s = GsStats()
         self._ck(self._L.gs_get_stats(self._h, C.byref(s)))
         return s
+
+    PHASES = ["clear+deal", "project rounds", "wait: rounds done", "remote records", "angle walk", "wait: angles done",
+              "edges+seeds", "wait: edges done", "unions", "boundary rounds", "forest readout",
+              "label+dilate+transpose", "wait: row counts", "images+cloud out", "flatten forest", "seed flags"]
+
+    def phase_cycles(self):
+        out = (C.c_uint64 * 16)()
+        self._ck(self._L.gs_get_phase_cycles(self._h, out))
+        return dict(zip(self.PHASES, [int(v) for v in out]))
 
     def reset_stats(self):
         self._ck(self._L.gs_reset_stats(self._h))

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -143,6 +144,7 @@ struct gs_ctx {
     Counters* h_cnt = nullptr;  // pinned
     unsigned long long n_launches = 0;
     bool collect_stats = false;
+    bool phase_timing = false;
     // single-frame staging (stage API)
     void* d_points = nullptr;
     size_t d_points_cap = 0;
@@ -410,7 +412,7 @@ int run_wave(gs_ctx* ctx, const void* d_points, size_t stride, const long long* 
     if (stride == 16 && (reinterpret_cast<uintptr_t>(d_points) & 15) == 0 && fused_supported(ctx->fused) && max_points <= fused_max_points()) {
         const Launch L = launch_of(ctx);
         const int rc = fused_run(ctx->fused, L, static_cast<const float4*>(d_points), d_offsets, frames, max_points, range_out, angle_out, res_out,
-                                 reinterpret_cast<float4*>(xyz_out), counts_out, ctx->d_cnt, ctx->collect_stats);
+                                 reinterpret_cast<float4*>(xyz_out), counts_out, ctx->d_cnt, (ctx->collect_stats ? 1 : 0) | (ctx->phase_timing ? 2 : 0));
         if (rc) return fail(ctx, GS_ECUDA, "fused kernel launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(rc)));
         return GS_OK;
     }
@@ -552,6 +554,7 @@ int gs_set_option(gs_ctx* ctx, int option, int value) {
     switch (option) {
         case GS_OPT_COLLECT_STATS: ctx->collect_stats = value != 0; return GS_OK;
         case GS_OPT_FORCE_STAGED: ctx->fused.disabled = value != 0; return GS_OK;
+        case GS_OPT_PHASE_TIMING: ctx->phase_timing = value != 0; return GS_OK;
         default: return fail(ctx, GS_EINVAL, "unknown option %d", option);
     }
 }
@@ -568,6 +571,16 @@ int gs_get_stats(gs_ctx* ctx, gs_stats* out) {
     out->slow_path_points = ctx->h_cnt->slow_path;
     out->fast_path_mismatches = ctx->h_cnt->fast_mismatch;
     out->remote_points = ctx->h_cnt->remote;
+    return GS_OK;
+}
+
+int gs_get_phase_cycles(gs_ctx* ctx, uint64_t* out16) {
+    if (!ctx || !out16) return GS_EINVAL;
+    cudaSetDevice(ctx->device);
+    const int rc = fetch_counters(ctx);
+    if (rc) return rc;
+    for (int k = 0; k < 16; ++k) out16[k] = ctx->h_cnt->phase[k];
+    if (getenv("GS_DEBUG_UF")) fprintf(stderr, "uf: unions %llu, unite iterations %llu, find hops %llu\n", ctx->h_cnt->phase[16], ctx->h_cnt->phase[17], ctx->h_cnt->phase[18]);
     return GS_OK;
 }
 

@@ -52,7 +52,7 @@ struct FusedArgs {
     int S8;       // row stride of the angle slab, bytes
     int NG;       // 32-column groups per slab
     // shared memory offsets (bytes)
-    unsigned off_range, off_tag, off_angle, off_masks, off_misc;
+    unsigned off_range, off_tag, off_angle, off_masks, off_misc, off_lut;
     const float4* points;
     const long long* offsets;
     int frames;
@@ -77,7 +77,7 @@ struct FusedArgs {
     int row_margin, col_margin;  // fixed-point error margins
     unsigned cw_magic;         // ceil(2^32 / CW): owner = (col * cw_magic) >> 32 for col < 2^16
     unsigned ng_magic;         // ceil(2^32 / NG)
-    unsigned mycw_shift;       // unused
+    const KParams* kp_dev;     // device-memory copy of kp for the out-of-line exact path
     int use_fast;
 };
 
@@ -96,6 +96,9 @@ __device__ __forceinline__ double decode_range_d(const KParams& kp, unsigned enc
     const double norm = __fma_rn(r, R, q0);
     return __dadd_rn(__dmul_rn(norm, kp.span), kp.min_range);
 }
+
+// the bit-exact atan2f clone, out of line: it runs for ~1e-3 of the pixels
+__device__ __noinline__ float atan2f_exact(float y, float x) { return gs_atan2f(y, x); }
 
 // atan(a) for a in [0, 1]: a + a*s*q(s), s = a*a; max error 6.6e-8 rad in binary32 FMA arithmetic (fitted and measured
 // by tools/fit_atan.py).  Used only on the certified fast paths: every result that lands within a margin >= 4x the error
@@ -130,17 +133,23 @@ __device__ __forceinline__ void cas_max_u16(uint16_t* p, unsigned v) {
 
 // Union-find over vertical runs, 16-bit parents in shared memory: bits 0..14 = parent index, bit 15 = "ground" flag
 // (meaningful on roots).  Roots hang under the smaller index, so the forest is acyclic without ranks.
-__device__ __forceinline__ int uf16_find(const volatile uint16_t* par, int x) {
+__device__ __forceinline__ int uf16_find(volatile uint16_t* par, int x, unsigned* hops = nullptr) {
+    // path halving: only non-root entries are rewritten (plain 16-bit stores), roots change through atomicCAS / atomicOr only
     for (;;) {
+        if (hops) ++*hops;
         const int p = par[x] & 0x7fff;
         if (p == x) return x;
-        x = p;
+        const int gp = par[p] & 0x7fff;
+        if (gp == p) return p;
+        par[x] = static_cast<uint16_t>(gp);
+        x = gp;
     }
 }
-__device__ __forceinline__ void uf16_unite(uint16_t* par, int a, int b) {
+__device__ __forceinline__ void uf16_unite(uint16_t* par, int a, int b, unsigned* dbg = nullptr) {
     for (;;) {
-        a = uf16_find(par, a);
-        b = uf16_find(par, b);
+        if (dbg) ++dbg[1];
+        a = uf16_find(par, a, dbg ? dbg + 2 : nullptr);
+        b = uf16_find(par, b, dbg ? dbg + 2 : nullptr);
         if (a == b) return;
         if (a < b) { const int t = a; a = b; b = t; }
         unsigned* w = reinterpret_cast<unsigned*>(par) + (a >> 1);
@@ -256,17 +265,28 @@ __device__ __forceinline__ Mask<NW> vfill(Mask<NW> g, Mask<NW> link, int H) {
 // mask storage in shared memory: [kind][word][column], u64 words
 enum { MK_VALID = 0, MK_VA, MK_HA, MK_V, MK_HM, MK_G, MK_KEEP, MK_S, MK_COUNT };
 
+// Row masks live in shared memory as 32-bit words: m32[(kind * NWD + w) * CW + c] holds rows 32w .. 32w+31 of column c.
 template <int NW>
-__device__ __forceinline__ Mask<NW> ld_mask(const unsigned long long* base, int kind, int CWp, int c) {
+__device__ __forceinline__ Mask<NW> ld_mask32(const unsigned* m32, int kind, int NWD, int CW, int c) {
+    const unsigned* p = m32 + static_cast<size_t>(kind) * NWD * CW + c;
     Mask<NW> m;
-    m.w0 = base[(kind * NW + 0) * CWp + c];
-    if constexpr (NW == 2) m.w1 = base[(kind * NW + 1) * CWp + c];
+    m.w0 = p[0];
+    if (NWD > 1) m.w0 |= static_cast<unsigned long long>(p[CW]) << 32;
+    if constexpr (NW == 2) {
+        m.w1 = NWD > 2 ? p[2 * CW] : 0u;
+        if (NWD > 3) m.w1 |= static_cast<unsigned long long>(p[3 * CW]) << 32;
+    }
     return m;
 }
 template <int NW>
-__device__ __forceinline__ void st_mask(unsigned long long* base, int kind, int CWp, int c, Mask<NW> m) {
-    base[(kind * NW + 0) * CWp + c] = m.w0;
-    if constexpr (NW == 2) base[(kind * NW + 1) * CWp + c] = m.w1;
+__device__ __forceinline__ void st_mask32(unsigned* m32, int kind, int NWD, int CW, int c, Mask<NW> m) {
+    unsigned* p = m32 + static_cast<size_t>(kind) * NWD * CW + c;
+    p[0] = static_cast<unsigned>(m.w0);
+    if (NWD > 1) p[CW] = static_cast<unsigned>(m.w0 >> 32);
+    if constexpr (NW == 2) {
+        if (NWD > 2) p[2 * CW] = static_cast<unsigned>(m.w1);
+        if (NWD > 3) p[3 * CW] = static_cast<unsigned>(m.w1 >> 32);
+    }
 }
 
 // ---- projection of one point (double precision, the reference's operation order) ---------------------------------
@@ -276,7 +296,10 @@ struct Proj {
     bool near_edge;
 };
 
-__device__ __forceinline__ Proj project_point_d(const KParams& kp, float fx, float fy, float fz) {
+// Rare path, kept out of line.  It reads the parameters from their device-memory copy: taking the address of the
+// kernel's by-value argument would force a stack copy of the whole struct.
+__device__ __noinline__ Proj project_point_d(const KParams* __restrict__ kpp, float fx, float fy, float fz) {
+    const KParams& kp = *kpp;
     Proj out;
     out.row = -1;
     out.col = -1;
@@ -422,14 +445,25 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
     const int myCW = min(CW, W - col0);         // columns I own (> 0 by construction)
     const int S16 = A.S16, S8 = A.S8, NG = A.NG;
     const int CWp = CW;                         // mask arrays are CW wide
+    // forest index of the run that starts at row rs of local column c.  The row is rotated by 2c inside the column so that
+    // runs starting at the same row in neighbouring columns (the ground does) fall into different shared-memory banks.
+    const bool h_pow2 = (H & (H - 1)) == 0;
+    auto run_node = [=](int c, int rs) -> int {
+        const int rot = rs + 2 * c;
+        return c * H + (h_pow2 ? (rot & (H - 1)) : (rot % H));
+    };
 
     // ---- shared memory carve-up
     uint16_t* s_range = reinterpret_cast<uint16_t*>(smem_raw + A.off_range);
     uint16_t* s_tag = reinterpret_cast<uint16_t*>(smem_raw + A.off_tag);
     uint8_t* s_angle = smem_raw + A.off_angle;
-    unsigned long long* s_masks = reinterpret_cast<unsigned long long*>(smem_raw + A.off_masks);         // [MK_COUNT][NW][CW]
+    const int NWD = (H + 31) >> 5;  // 32-row words per column
+    unsigned* s_m32 = reinterpret_cast<unsigned*>(smem_raw + A.off_masks);  // [MK_COUNT][NWD][CW]
     uint16_t* s_par = s_tag;  // [CW][H] union-find parents of the vertical runs (the tag slab is dead after the projection)
-    unsigned* s_rowmask = reinterpret_cast<unsigned*>(s_masks + static_cast<size_t>(MK_COUNT) * NW * CWp);  // [H][NG]
+    unsigned* s_rowmask = s_m32 + static_cast<size_t>(MK_COUNT) * NWD * CW;  // [H][NG]
+    // scratch of the labelling stage in the angle slab (dead once the links are computed): link words to unite and their scan
+    unsigned* s_todo = reinterpret_cast<unsigned*>(s_angle);                 // [(CW - 1) * NWD]
+    uint16_t* s_excl = reinterpret_cast<uint16_t*>(s_todo + static_cast<size_t>(CW) * NWD);  // [(CW - 1) * NWD + 1]
     unsigned* s_grp = s_rowmask + H * NG;                                                                  // [H][NG]
     uint8_t* s_assign = s_angle;                                                                           // [MAX_BLOCKS]
     uint16_t* s_mylist = reinterpret_cast<uint16_t*>(s_angle + MAX_BLOCKS);                                // [MAX_BLOCKS]
@@ -440,11 +474,50 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
     uint8_t* s_halo_angle = reinterpret_cast<uint8_t*>(s_halo_masks + 14);              // [MAX_H]
     unsigned* s_flags = reinterpret_cast<unsigned*>(s_halo_angle + MAX_H);              // [MAX_CL]
     unsigned* s_misc = s_flags + MAX_CL;                                                // [0] nmine, [1] scratch
+    unsigned* s_halo32 = s_misc + 8;                                                    // [5][4] halo mask words
+    unsigned* s_scan = s_halo32 + 20;                                                   // [64] block scan scratch
+
+    // lookup tables: shared-memory copies made once per CTA (the persistent kernel reuses them for every frame)
+    double* s_cos_az = reinterpret_cast<double*>(smem_raw + A.off_lut);  // [CW]
+    double* s_sin_az = s_cos_az + CW;                                    // [CW]
+    double* s_cos_alt = s_sin_az + CW;                                   // [H]
+    double* s_sin_alt = s_cos_alt + H;
+    double* s_sin_y_d = s_sin_alt + H;
+    double* s_cos_y_d = s_sin_y_d + H;
+    float* s_sin_y = reinterpret_cast<float*>(s_cos_y_d + H);
+    float* s_cos_y = s_sin_y + H;
+    for (int c = tid; c < myCW; c += NT) {
+        s_cos_az[c] = A.lut.cos_az[col0 + c];
+        s_sin_az[c] = A.lut.sin_az[col0 + c];
+    }
+    for (int r = tid; r < H; r += NT) {
+        s_cos_alt[r] = A.lut.cos_alt[r];
+        s_sin_alt[r] = A.lut.sin_alt[r];
+        s_sin_y_d[r] = A.lut.sin_y_d[r];
+        s_cos_y_d[r] = A.lut.cos_y_d[r];
+        s_sin_y[r] = A.lut.sin_y[r];
+        s_cos_y[r] = A.lut.cos_y[r];
+    }
+    __syncthreads();
 
     uint2* rlist = A.rlist + (static_cast<size_t>(cluster_id) * CL + rank) * A.rcap;
     unsigned* rcount = A.rcount + static_cast<size_t>(cluster_id) * CL;
 
     unsigned long long st_dropped = 0, st_near = 0, st_near_angle = 0, st_remote = 0, st_fallback = 0, st_mismatch = 0;
+    // phase timing (GS_OPT_COLLECT_STATS): thread 0 of every CTA accumulates clock64() deltas per phase
+    long long t_mark = 0;
+    int t_phase = 0;
+    unsigned dbg_cnt[3] = {0, 0, 0};  // unions requested, unite loop iterations, find hops
+#define GS_PHASE(next)                                                        \
+    do {                                                                      \
+        if ((A.stats & 2) && tid == 0) {                                      \
+            const long long now_ = clock64();                                 \
+            atomicAdd(&A.cnt->phase[t_phase], static_cast<unsigned long long>(now_ - t_mark)); \
+            t_mark = now_;                                                    \
+            t_phase = (next);                                                 \
+        }                                                                     \
+    } while (0)
+    if ((A.stats & 2) && tid == 0) t_mark = clock64();
 
     for (int f = cluster_id; f < A.frames; f += n_clusters) {
         const long long beg = A.offsets[f], end = A.offsets[f + 1];
@@ -496,29 +569,52 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
         __syncthreads();
         const int nmine = static_cast<int>(s_misc[0]);
 
+        GS_PHASE(1);
         // ================================================================================ P1: local rounds
+        // the points of the next round are loaded while the current round is processed
+        float4 cur_p[NPT];
+        int cur_i[NPT];
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) {
+            const int q = j * NT + tid;
+            int i = -1;
+            if (q < nmine * BLK) {
+                i = static_cast<int>(s_mylist[q >> 8]) * BLK + (q & (BLK - 1));
+                if (i >= N) i = -1;
+            }
+            cur_i[j] = i;
+            cur_p[j] = i >= 0 ? __ldcs(pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         for (int qb = 0; qb < nmine * BLK; qb += NT * NPT) {
             unsigned key[NPT], val[NPT];  // key: owner << 16 | slab address (0xffffffff = nothing to store); val: g << 16 | enc
+            float4 nxt_p[NPT];
+            int nxt_i[NPT];
 #pragma unroll
             for (int j = 0; j < NPT; ++j) {
-                key[j] = 0xffffffffu;
-                val[j] = 0;
-                const int q = qb + j * NT + tid;
+                const int q = qb + NT * NPT + j * NT + tid;
                 int i = -1;
                 if (q < nmine * BLK) {
                     i = static_cast<int>(s_mylist[q >> 8]) * BLK + (q & (BLK - 1));
                     if (i >= N) i = -1;
                 }
+                nxt_i[j] = i;
+                nxt_p[j] = i >= 0 ? __ldcs(pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < NPT; ++j) {
+                key[j] = 0xffffffffu;
+                val[j] = 0;
+                const int i = cur_i[j];
                 unsigned k = 0x80000000u | lane;  // unique per lane: never matches
                 if (i >= 0) {
-                    const float4 p4 = __ldcs(pts + i);
+                    const float4 p4 = cur_p[j];
                     int row = -1, col = -1;
                     unsigned enc = 0;
                     int st = A.use_fast ? project_fast(A, p4.x, p4.y, p4.z, &row, &col, &enc) : 2;
-                    if (st == 2 || A.stats) {
+                    if (st == 2 || (A.stats & 1)) {
                         // exact evaluation: the undecided points, and every point when statistics are collected
-                        const Proj pr = project_point_d(kp, p4.x, p4.y, p4.z);
-                        if (A.stats) {
+                        const Proj pr = project_point_d(A.kp_dev, p4.x, p4.y, p4.z);
+                        if ((A.stats & 1)) {
                             if (st == 2) ++st_fallback;
                             else if ((st == 1) != (pr.row < 0) || (st == 0 && (row != pr.row || col != pr.col || enc != pr.enc))) ++st_mismatch;
                             if (pr.row < 0) ++st_dropped;
@@ -564,7 +660,7 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
                     if (remote) {
                         const unsigned slot = base + __popc(rm & ((1u << lane) - 1u));
                         if (slot < A.rcap) rlist[slot] = make_uint2(k, val[j]);
-                        if (A.stats) ++st_remote;
+                        if ((A.stats & 1)) ++st_remote;
                     }
                 }
             }
@@ -580,10 +676,17 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
 #pragma unroll
             for (int j = 0; j < NPT; ++j)
                 if (key[j] != 0xffffffffu && s_tag[key[j]] == (val[j] >> 16)) s_range[key[j]] = static_cast<uint16_t>(val[j] & 0xffffu);
+#pragma unroll
+            for (int j = 0; j < NPT; ++j) {
+                cur_p[j] = nxt_p[j];
+                cur_i[j] = nxt_i[j];
+            }
         }
+        GS_PHASE(2);
         __threadfence();  // remote records and counts visible before the cluster-wide phase
         cluster.sync();   // #1: all local pixels committed everywhere
 
+        GS_PHASE(3);
         // ================================================================================ P2: remote records
         {
             unsigned n_any = 0;
@@ -614,6 +717,7 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
             }
         }
 
+        GS_PHASE(4);
         // ================================================================================ A: angle image (column walks)
         // one thread per (column, 32-row segment); bottom -> top like the reference (alfa_gs.cpp:347-382)
         {
@@ -629,8 +733,8 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
                     const unsigned e = s_range[r * S16 + c];
                     if (e) {
                         const float pr = __double2float_rn(decode_range_d(kp, e));  // prev_r = range (:379)
-                        p_z = __fmul_rn(pr, A.lut.sin_y[r]);
-                        p_x = __fmul_rn(pr, A.lut.cos_y[r]);
+                        p_z = __fmul_rn(pr, s_sin_y[r]);
+                        p_x = __fmul_rn(pr, s_cos_y[r]);
                         has_prev = true;
                         break;
                     }
@@ -653,10 +757,10 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
                     if (e) {
                         vbits |= 1u << (r - lo);
                         const double rng = decode_range_d(kp, e);
-                        const float sy = A.lut.sin_y[r], cy = A.lut.cos_y[r];
+                        const float sy = s_sin_y[r], cy = s_cos_y[r];
                         if (has_prev) {
-                            const float dz = __double2float_rn(fabs(__dsub_rn(static_cast<double>(p_z), __dmul_rn(rng, A.lut.sin_y_d[r]))));  // :366
-                            const float dx = __double2float_rn(fabs(__dsub_rn(static_cast<double>(p_x), __dmul_rn(rng, A.lut.cos_y_d[r]))));  // :367
+                            const float dz = __double2float_rn(fabs(__dsub_rn(static_cast<double>(p_z), __dmul_rn(rng, s_sin_y_d[r]))));  // :366
+                            const float dx = __double2float_rn(fabs(__dsub_rn(static_cast<double>(p_x), __dmul_rn(rng, s_cos_y_d[r]))));  // :367
                             // fast: float atan with a 2e-7 rad error budget; results within 4e-6 rad of a centi-radian edge
                             // (and 0/0) are recomputed with the bit-exact clone of the host's atan2f
                             float t = atan01(__fdividef(fminf(dz, dx), fmaxf(dz, dx)));
@@ -666,11 +770,11 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
                             const float fr = sc - static_cast<float>(kk);
                             const bool sure = A.use_fast && fr > 4e-4f && fr < 1.0f - 4e-4f;
                             a_out = static_cast<unsigned>(kk);
-                            if (!sure || A.stats) {
-                                const float alfa = gs_atan2f(dz, dx);          // :368
+                            if (!sure || (A.stats & 1)) {
+                                const float alfa = atan2f_exact(dz, dx);       // :368
                                 const float scaled = __fmul_rn(alfa, 100.0f);  // :370
                                 const unsigned exact = static_cast<unsigned>(__float2int_rz(scaled));
-                                if (A.stats) {
+                                if ((A.stats & 1)) {
                                     const float fe = scaled - floorf(scaled);
                                     if (fminf(fe, 1.0f - fe) < 1e-3f) ++st_near_angle;
                                     if (!sure) ++st_fallback;
@@ -686,11 +790,8 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
                     }
                     s_angle[r * S8 + c] = static_cast<uint8_t>(a_out);
                 }
-                // valid bits of this segment -> the column's VALID mask word (masks alias the tag slab: dead now)
-                // stored as 32-bit halves of the u64 mask words: word wseg / 2, half wseg & 1
-                unsigned* vw = reinterpret_cast<unsigned*>(s_masks + (MK_VALID * NW + (wseg >> 1)) * CWp + c);
-                vw[wseg & 1] = vbits;
-                if ((nword & 1) && wseg == nword - 1) vw[1] = 0;  // H <= 32 or odd word count: clear the unused half
+                // valid bits of this segment -> the column's VALID mask word
+                s_m32[(MK_VALID * NWD + wseg) * CW + c] = vbits;
             }
         }
         __syncthreads();
@@ -701,113 +802,220 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
                 out[r * W + col0 + c] = s_angle[r * S8 + c];
             }
         }
+        GS_PHASE(5);
         cluster.sync();  // #4: angle slabs and VALID masks complete in the whole cluster
 
-        // ================================================================================ G: edges, seeds, flood fill
+        GS_PHASE(6);
+        // ================================================================================ G: links, runs, seeds, ground label
         const int right_rank = (rank + 1 == CL) ? 0 : rank + 1;
         const int left_rank = (rank == 0) ? CL - 1 : rank - 1;
         const int left_last = min(CW, W - left_rank * CW) - 1;  // last local column of the left neighbour
+#define MW(kind, w, c) s_m32[((kind) * NWD + (w)) * CW + (c)]
         // halo: angle column 0 and VALID of the right neighbour (column W-1's right neighbour is column 0: Label::WrapCols)
         {
             const uint8_t* r_angle = cluster.map_shared_rank(s_angle, right_rank);
             for (int r = tid; r < H; r += NT) s_halo_angle[r] = r_angle[r * S8];
-            if (tid < NW) s_halo_masks[0 * 2 + tid] = cluster.map_shared_rank(s_masks, right_rank)[(MK_VALID * NW + tid) * CWp + 0];
+            if (tid < NWD) s_halo32[0 * 4 + tid] = cluster.map_shared_rank(s_m32, right_rank)[(MK_VALID * NWD + tid) * CW + 0];
         }
         __syncthreads();
-        const Mask<NW> Hmask = Mask<NW>::low(H);
-        for (int c = tid; c < myCW; c += NT) {
-            const Mask<NW> valid = ld_mask<NW>(s_masks, MK_VALID, CWp, c);
-            Mask<NW> va = Mask<NW>::zero(), ha = Mask<NW>::zero();
+        const int n_units = myCW * NWD;  // one unit = 32 rows of one column
+        for (int u = tid; u < n_units; u += NT) {
+            const int w = u / myCW, c = u - w * myCW;
+            const int lo = w * 32, nrow = min(32, H - lo);
+            const unsigned valid = MW(MK_VALID, w, c);
             const bool last = (c == myCW - 1);
-            int a_here = s_angle[c];
-            for (int r = 0; r < H; ++r) {
+            // angle-difference links (label.cpp:90-99 with the float threshold folded to an integer)
+            unsigned va = 0, ha = 0;  // bit i: |a(r) - a(r+1)| <= K  /  |a(r, c) - a(r, c+1)| <= K,  r = lo + i
+            int a_here = s_angle[lo * S8 + c];
+            const int a_first = a_here;
+            for (int i = 0; i < nrow; ++i) {
+                const int r = lo + i;
                 const int a_down = (r + 1 < H) ? s_angle[(r + 1) * S8 + c] : 0;
                 const int a_right = last ? s_halo_angle[r] : s_angle[r * S8 + c + 1];
-                if (r + 1 < H && abs(a_here - a_down) <= kp.k_ground) va.set(r);   // label.cpp:90-99, threshold folded to an integer
-                if (abs(a_here - a_right) <= kp.k_ground) ha.set(r);
+                if (r + 1 < H && abs(a_here - a_down) <= kp.k_ground) va |= 1u << i;
+                if (abs(a_here - a_right) <= kp.k_ground) ha |= 1u << i;
                 a_here = a_down;
             }
-            Mask<NW> valid_right;
-            if (last) {
-                valid_right.w0 = s_halo_masks[0];
-                if constexpr (NW == 2) valid_right.w1 = s_halo_masks[1];
-            } else {
-                valid_right = ld_mask<NW>(s_masks, MK_VALID, CWp, c + 1);
-            }
-            const bool has_right = W > 1;
-            if (!has_right) ha = Mask<NW>::zero();
-            const Mask<NW> v = va & valid & valid.shr(1);
-            const Mask<NW> hm = ha & valid & valid_right;
-            // seed (alfa_gs.cpp:720-736): bottom-most non-empty pixel, row 0 when the column is empty
-            int sr = valid.top();
-            const bool seed_valid = sr >= 0;
-            if (sr < 0) sr = 0;
-            const bool accepted = static_cast<int>(s_angle[sr * S8 + c]) <= kp.s_start;  // :733
-            Mask<NW> g = Mask<NW>::zero();
-            if (accepted && seed_valid) g.set(sr);
-            Mask<NW> keep = Mask<NW>::zero();  // KEEP temporarily carries the accepted empty seed (labelled, not expanded: label.cpp:67-74)
-            if (accepted && !seed_valid) keep.set(0);
-            st_mask<NW>(s_masks, MK_VA, CWp, c, va);
-            st_mask<NW>(s_masks, MK_HA, CWp, c, ha);
-            st_mask<NW>(s_masks, MK_V, CWp, c, v);
-            st_mask<NW>(s_masks, MK_HM, CWp, c, hm);
-            st_mask<NW>(s_masks, MK_G, CWp, c, g);  // the accepted non-empty seed pixel, if any
-            const Mask<NW> runs = valid & ~v.shl(1);  // first (lowest-index) pixel of every vertical run
-            st_mask<NW>(s_masks, MK_S, CWp, c, runs);
-            for (Mask<NW> it = runs; it.any(); it.clear_lowest()) {
-                const int node = c * H + it.lowest();
+            const unsigned valid_up = (w + 1 < NWD) ? MW(MK_VALID, w + 1, c) : 0u;
+            const unsigned v = va & valid & ((valid >> 1) | (valid_up << 31));  // bit i: rows r and r+1 linked (both non-empty)
+            const unsigned valid_right = last ? s_halo32[0 * 4 + w] : MW(MK_VALID, w, c + 1);
+            const unsigned hm = ha & valid & valid_right;                       // bit i: (r, c) and (r, c+1) linked
+            unsigned linked_prev = v << 1;  // bit i: row r linked to row r-1; bit 0 looks into the word below
+            if (w > 0 && (valid & 1u) && (MW(MK_VALID, w - 1, c) >> 31) && abs(a_first - static_cast<int>(s_angle[(lo - 1) * S8 + c])) <= kp.k_ground) linked_prev |= 1u;
+            const unsigned runs = valid & ~linked_prev;  // first (lowest-index) pixel of every vertical run
+            MW(MK_VA, w, c) = va;
+            MW(MK_HA, w, c) = ha;
+            MW(MK_V, w, c) = v;
+            MW(MK_HM, w, c) = hm;
+            MW(MK_S, w, c) = runs;
+            for (unsigned m = runs; m; m &= m - 1) {
+                const int node = run_node(c, lo + __ffs(m) - 1);
                 s_par[node] = static_cast<uint16_t>(node);
             }
-            st_mask<NW>(s_masks, MK_KEEP, CWp, c, keep);
+            // seed (alfa_gs.cpp:720-736): the bottom-most non-empty pixel of the column, row 0 when the column is empty
+            bool higher = false;
+            for (int w2 = w + 1; w2 < NWD; ++w2) higher |= MW(MK_VALID, w2, c) != 0u;
+            unsigned gseed = 0, eseed = 0;
+            if (!higher) {
+                if (valid) {
+                    const int i = 31 - __clz(valid);
+                    if (static_cast<int>(s_angle[(lo + i) * S8 + c]) <= kp.s_start) gseed = 1u << i;  // :733
+                } else if (w == 0) {
+                    if (static_cast<int>(s_angle[c]) <= kp.s_start) eseed = 1u;  // accepted empty seed: labelled, not expanded (label.cpp:67-74)
+                }
+            }
+            MW(MK_G, w, c) = gseed;
+            MW(MK_KEEP, w, c) = eseed;
         }
-        cluster.sync();  // #5: HM / HA / G of every slab readable by the neighbours
+        GS_PHASE(7);
+        cluster.sync();  // #5: link words of every slab readable by the neighbours; the angle slab is free from here on
         // static halos from the left neighbour: HM and HA of its last column (the edge between that column and my column 0)
-        if (tid < NW) {
-            const unsigned long long* lm = cluster.map_shared_rank(s_masks, left_rank);
-            s_halo_masks[3 * 2 + tid] = lm[(MK_HM * NW + tid) * CWp + left_last];
-            s_halo_masks[4 * 2 + tid] = lm[(MK_HA * NW + tid) * CWp + left_last];
+        if (tid < NWD) {
+            const unsigned* lm = cluster.map_shared_rank(s_m32, left_rank);
+            s_halo32[3 * 4 + tid] = lm[(MK_HM * NWD + tid) * CW + left_last];
+            s_halo32[4 * 4 + tid] = lm[(MK_HA * NWD + tid) * CW + left_last];
         }
+        GS_PHASE(8);
         // Ground label = reachability from the accepted seeds (the Labeler's BFS, label.cpp:48-104).  Nodes are the
-        // vertical runs of every column (maximal chains of V links); horizontal links unite runs of adjacent columns in
-        // a 16-bit union-find forest; seeds flag their root; slab boundaries (and the column wrap of Label::WrapCols)
-        // are crossed by exchanging the ground masks of the boundary columns until no flag changes in the cluster.
-        __syncthreads();
-        for (int c = tid; c < myCW - 1; c += NT) {
-            const Mask<NW> hm = ld_mask<NW>(s_masks, MK_HM, CWp, c);
-            if (!hm.any()) continue;
-            const Mask<NW> vboth = ld_mask<NW>(s_masks, MK_V, CWp, c) & ld_mask<NW>(s_masks, MK_V, CWp, c + 1);
-            // one union per pair of runs: skip link r when link r-1 joins the same two runs
-            Mask<NW> todo = hm & ~(hm & vboth).shl(1);
-            const Mask<NW> sa = ld_mask<NW>(s_masks, MK_S, CWp, c), sb = ld_mask<NW>(s_masks, MK_S, CWp, c + 1);
-            for (; todo.any(); todo.clear_lowest()) {
-                const int r = todo.lowest();
-                const Mask<NW> upto = Mask<NW>::low(r + 1);
-                uf16_unite(s_par, c * H + (sa & upto).top(), (c + 1) * H + (sb & upto).top());
+        // vertical runs of every column; horizontal links unite runs of adjacent columns in a 16-bit union-find forest.
+        // Unions go level by level (level k joins column groups of width 2^k across the boundaries b = 2^k - 1 mod 2^(k+1)),
+        // which keeps the trees shallow; inside a level the links are dealt evenly to all threads through a prefix sum, so
+        // every lane of a warp performs a union in every iteration.
+        int n_levels = 0;
+        while ((1 << n_levels) < myCW) ++n_levels;
+        const int n_q = (myCW - 1) * NWD;  // (boundary in level order, word)
+        auto level_count = [=](int k) -> int {
+            const int first = (1 << k) - 1;
+            return (myCW - 2 >= first) ? (myCW - 2 - first) / (2 << k) + 1 : 0;
+        };
+        auto boundary_of = [=](int p) -> int {  // p-th boundary in level order -> left column of the boundary
+            for (int k = 0;; ++k) {
+                const int nk = level_count(k);
+                if (p < nk) return ((1 << k) - 1) + p * (2 << k);
+                p -= nk;
+            }
+        };
+        {
+            unsigned carry = 0;
+            for (int q0 = 0; q0 < n_q; q0 += NT) {
+                const int q = q0 + tid;
+                unsigned todo = 0;
+                if (q < n_q) {
+                    const int pb = q / NWD, w = q - pb * NWD;
+                    const int c = boundary_of(pb);
+                    const unsigned hm = MW(MK_HM, w, c);
+                    if (hm) {
+                        // one union per pair of runs: skip link r when link r-1 joins the same two runs
+                        const unsigned x = hm & MW(MK_V, w, c) & MW(MK_V, w, c + 1);
+                        unsigned xprev = 0;
+                        if (w > 0) xprev = (MW(MK_HM, w - 1, c) & MW(MK_V, w - 1, c) & MW(MK_V, w - 1, c + 1)) >> 31;
+                        todo = hm & ~((x << 1) | xprev);
+                    }
+                    s_todo[q] = todo;
+                }
+                // block-wide exclusive prefix sum of the link counts
+                const unsigned cnt = __popc(todo);
+                unsigned incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                if (lane == 31) s_scan[warp] = incl;
+                __syncthreads();
+                if (warp == 0) {
+                    unsigned ws = s_scan[lane];
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const unsigned t = __shfl_up_sync(0xffffffffu, ws, d);
+                        if (lane >= d) ws += t;
+                    }
+                    s_scan[32 + lane] = ws;  // inclusive over warps
+                }
+                __syncthreads();
+                const unsigned before = carry + (warp ? s_scan[32 + warp - 1] : 0u) + incl - cnt;
+                if (q < n_q) s_excl[q] = static_cast<uint16_t>(before);
+                carry += s_scan[32 + 31];
+                __syncthreads();
+            }
+            if (tid == 0) s_excl[n_q] = static_cast<uint16_t>(carry);
+            __syncthreads();
+        }
+        {
+            int q_lo = 0;
+            for (int lev = 0; lev < n_levels; ++lev) {
+                const int q_hi = q_lo + level_count(lev) * NWD;
+                const int t0 = s_excl[q_lo], t1 = s_excl[q_hi];
+                if (t1 > t0) {
+                    const int per = (t1 - t0 + NT - 1) / NT;
+                    int task = t0 + tid * per;
+                    const int task_end = min(task + per, t1);
+                    if (task < task_end) {
+                        int ql = q_lo, qh = q_hi - 1;  // largest q in the level with s_excl[q] <= task
+                        while (ql < qh) {
+                            const int mid = (ql + qh + 1) >> 1;
+                            if (static_cast<int>(s_excl[mid]) <= task) ql = mid;
+                            else qh = mid - 1;
+                        }
+                        int q = ql;
+                        unsigned word = s_todo[q];
+                        for (int k = task - static_cast<int>(s_excl[q]); k > 0; --k) word &= word - 1;
+                        int pb = q / NWD, w = q - pb * NWD, c = boundary_of(pb);
+                        for (; task < task_end; ++task) {
+                            while (word == 0u) {
+                                ++q;
+                                word = s_todo[q];
+                                pb = q / NWD;
+                                w = q - pb * NWD;
+                                c = boundary_of(pb);
+                            }
+                            const int i = __ffs(word) - 1;
+                            word &= word - 1;
+                            const unsigned below = 0xffffffffu >> (31 - i);
+                            // run starts of (32w + i, c) and (32w + i, c + 1): highest run-start bit at or below the row
+                            int wa = w, wb = w;
+                            unsigned ma = MW(MK_S, w, c) & below, mb = MW(MK_S, w, c + 1) & below;
+                            while (ma == 0u) ma = MW(MK_S, --wa, c);
+                            while (mb == 0u) mb = MW(MK_S, --wb, c + 1);
+                            uf16_unite(s_par, run_node(c, 32 * wa + 31 - __clz(ma)), run_node(c + 1, 32 * wb + 31 - __clz(mb)));
+                        }
+                    }
+                }
+                q_lo = q_hi;
+                __syncthreads();
+            }
+        }
+        GS_PHASE(15);
+        for (int u = tid; u < n_units; u += NT) {
+            const int w = u / myCW, c = u - w * myCW;
+            const unsigned seed = MW(MK_G, w, c);
+            if (seed) {
+                const int i = 31 - __clz(seed);
+                int wa = w;
+                unsigned ma = MW(MK_S, w, c) & (0xffffffffu >> (31 - i));
+                while (ma == 0u) ma = MW(MK_S, --wa, c);
+                uf16_flag_root(s_par, run_node(c, 32 * wa + 31 - __clz(ma)));
             }
         }
         __syncthreads();
-        for (int c = tid; c < myCW; c += NT) {
-            const Mask<NW> seed = ld_mask<NW>(s_masks, MK_G, CWp, c);
-            if (seed.any()) uf16_flag_root(s_par, c * H + (ld_mask<NW>(s_masks, MK_S, CWp, c) & Mask<NW>::low(seed.top() + 1)).top());
-        }
-        __syncthreads();
+        GS_PHASE(9);
+        // Slab boundaries (and the column wrap of Label::WrapCols): exchange the ground masks of the boundary columns
+        // until no flag changes anywhere in the cluster.  Warp 0 owns my column 0, warp 1 my last column; lane l owns
+        // the rows [l*H/32, (l+1)*H/32).
         for (;;) {
-            // ground masks of my two boundary columns -> s_halo_masks[5], [6] (read by the neighbours)
             if (warp < 2) {
                 const int c = warp == 0 ? 0 : myCW - 1;
-                const Mask<NW> valid = ld_mask<NW>(s_masks, MK_VALID, CWp, c);
-                Mask<NW> runs = ld_mask<NW>(s_masks, MK_S, CWp, c);
+                const Mask<NW> valid = ld_mask32<NW>(s_m32, MK_VALID, NWD, CW, c);
+                const Mask<NW> runs = ld_mask32<NW>(s_m32, MK_S, NWD, CW, c);
+                const int rlo = (lane * H) >> 5, rhi = ((lane + 1) * H) >> 5;
                 Mask<NW> g = Mask<NW>::zero();
-                // lane l takes runs l, l + 32, ...
-                for (int k = 0; runs.any(); ++k) {
-                    const int rs = runs.lowest();
-                    runs.clear_lowest();
-                    if ((k & 31) == lane) {
-                        const int root = uf16_find(s_par, c * H + rs);
-                        if (s_par[root] & 0x8000u) {
-                            const int next = runs.any() ? runs.lowest() : H;
-                            g = g | (valid & Mask<NW>::low(next) & ~Mask<NW>::low(rs));
-                        }
+                for (Mask<NW> it = runs & Mask<NW>::low(rhi) & ~Mask<NW>::low(rlo); it.any(); it.clear_lowest()) {
+                    const int rs = it.lowest();
+                    const int root = uf16_find(s_par, run_node(c, rs));
+                    if (s_par[root] & 0x8000u) {
+                        const Mask<NW> later = runs & ~Mask<NW>::low(rs + 1);
+                        const int next = later.any() ? later.lowest() : H;
+                        g = g | (valid & Mask<NW>::low(next) & ~Mask<NW>::low(rs));
                     }
                 }
 #pragma unroll
@@ -821,7 +1029,6 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
                 }
             }
             cluster.sync();
-            // import: right neighbour's column 0 and left neighbour's last column
             bool changed = false;
             if (warp < 2) {
                 Mask<NW> mine, theirs, link;
@@ -830,9 +1037,13 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
                     c = 0;
                     const unsigned long long* rm = cluster.map_shared_rank(s_halo_masks, left_rank);
                     theirs.w0 = rm[6 * 2 + 0];
-                    link.w0 = s_halo_masks[3 * 2 + 0];
                     mine.w0 = s_halo_masks[5 * 2 + 0];
-                    if constexpr (NW == 2) { theirs.w1 = rm[6 * 2 + 1]; link.w1 = s_halo_masks[3 * 2 + 1]; mine.w1 = s_halo_masks[5 * 2 + 1]; }
+                    link.w0 = s_halo32[3 * 4 + 0] | (NWD > 1 ? static_cast<unsigned long long>(s_halo32[3 * 4 + 1]) << 32 : 0ull);
+                    if constexpr (NW == 2) {
+                        theirs.w1 = rm[6 * 2 + 1];
+                        mine.w1 = s_halo_masks[5 * 2 + 1];
+                        link.w1 = (NWD > 2 ? s_halo32[3 * 4 + 2] : 0u) | (NWD > 3 ? static_cast<unsigned long long>(s_halo32[3 * 4 + 3]) << 32 : 0ull);
+                    }
                     if (lane == 0) {
                         s_halo_masks[2 * 2 + 0] = theirs.w0;
                         if constexpr (NW == 2) s_halo_masks[2 * 2 + 1] = theirs.w1;
@@ -843,19 +1054,17 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
                     theirs.w0 = rm[5 * 2 + 0];
                     mine.w0 = s_halo_masks[6 * 2 + 0];
                     if constexpr (NW == 2) { theirs.w1 = rm[5 * 2 + 1]; mine.w1 = s_halo_masks[6 * 2 + 1]; }
-                    link = ld_mask<NW>(s_masks, MK_HM, CWp, c);
+                    link = ld_mask32<NW>(s_m32, MK_HM, NWD, CW, c);
                     if (lane == 0) {
                         s_halo_masks[1 * 2 + 0] = theirs.w0;
                         if constexpr (NW == 2) s_halo_masks[1 * 2 + 1] = theirs.w1;
                     }
                 }
-                Mask<NW> in = theirs & link & ~mine;  // ground reaches these pixels of mine across the boundary
-                const Mask<NW> runs = ld_mask<NW>(s_masks, MK_S, CWp, c);
-                for (int k = 0; in.any(); ++k) {
-                    const int r = in.lowest();
-                    in.clear_lowest();
-                    if ((k & 31) == lane) changed |= uf16_flag_root(s_par, c * H + (runs & Mask<NW>::low(r + 1)).top());
-                }
+                const int rlo = (lane * H) >> 5, rhi = ((lane + 1) * H) >> 5;
+                const Mask<NW> runs = ld_mask32<NW>(s_m32, MK_S, NWD, CW, c);
+                // ground reaches these pixels of mine across the boundary
+                for (Mask<NW> in = theirs & link & ~mine & Mask<NW>::low(rhi) & ~Mask<NW>::low(rlo); in.any(); in.clear_lowest())
+                    changed |= uf16_flag_root(s_par, run_node(c, (runs & Mask<NW>::low(in.lowest() + 1)).top()));
             }
             const int any_change = __syncthreads_or(changed ? 1 : 0);
             if (tid < CL) cluster.map_shared_rank(s_flags, tid)[rank] = any_change ? 1u : 0u;
@@ -865,64 +1074,79 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
             if (!anyone) break;
             // (the next round's first cluster.sync orders these flag reads before the flags are rewritten)
         }
-        // read the ground mask of every column out of the forest
-        for (int c = tid; c < myCW; c += NT) {
-            const Mask<NW> valid = ld_mask<NW>(s_masks, MK_VALID, CWp, c);
-            Mask<NW> runs = ld_mask<NW>(s_masks, MK_S, CWp, c);
-            Mask<NW> g = Mask<NW>::zero();
-            while (runs.any()) {
-                const int rs = runs.lowest();
-                runs.clear_lowest();
-                const int root = uf16_find(s_par, c * H + rs);
-                if (s_par[root] & 0x8000u) {
-                    const int next = runs.any() ? runs.lowest() : H;
-                    g = g | (valid & Mask<NW>::low(next) & ~Mask<NW>::low(rs));
-                }
+        GS_PHASE(10);
+        // read the ground mask of every unit out of the forest
+        for (int u = tid; u < n_units; u += NT) {
+            const int w = u / myCW, c = u - w * myCW;
+            const unsigned valid = MW(MK_VALID, w, c);
+            unsigned runs = MW(MK_S, w, c);
+            unsigned g = 0;
+            // pixels of a run that started in a lower word: the non-empty pixels below the first run start of this word
+            const unsigned head = valid & (runs ? ((runs & (0u - runs)) - 1u) : 0xffffffffu);
+            if (head) {
+                int wa = w;
+                unsigned ma = 0;
+                while (ma == 0u) ma = MW(MK_S, --wa, c);
+                const int root = uf16_find(s_par, run_node(c, 32 * wa + 31 - __clz(ma)));
+                if (s_par[root] & 0x8000u) g = head;
             }
-            st_mask<NW>(s_masks, MK_G, CWp, c, g);
+            while (runs) {
+                const unsigned bit = runs & (0u - runs);
+                runs ^= bit;
+                const unsigned upto_next = runs ? ((runs & (0u - runs)) - 1u) : 0xffffffffu;
+                const int root = uf16_find(s_par, run_node(c, 32 * w + __ffs(bit) - 1));
+                if (s_par[root] & 0x8000u) g |= valid & upto_next & ~(bit - 1u);
+            }
+            MW(MK_G, w, c) = g;
         }
         __syncthreads();
 
+        GS_PHASE(11);
         // ================================================================================ D: label image, dilation, erase
         // L = G | accepted empty seeds | empty pixels 4-adjacent to a ground pixel u with |angle(u) - angle(p)| <= K
+        const Mask<NW> Hmask = Mask<NW>::low(H);
         for (int c = tid; c < myCW; c += NT) {
-            const Mask<NW> valid = ld_mask<NW>(s_masks, MK_VALID, CWp, c);
-            const Mask<NW> g = ld_mask<NW>(s_masks, MK_G, CWp, c);
-            const Mask<NW> va = ld_mask<NW>(s_masks, MK_VA, CWp, c);
-            const Mask<NW> ha = ld_mask<NW>(s_masks, MK_HA, CWp, c);
+            const Mask<NW> valid = ld_mask32<NW>(s_m32, MK_VALID, NWD, CW, c);
+            const Mask<NW> g = ld_mask32<NW>(s_m32, MK_G, NWD, CW, c);
+            const Mask<NW> va = ld_mask32<NW>(s_m32, MK_VA, NWD, CW, c);
+            const Mask<NW> ha = ld_mask32<NW>(s_m32, MK_HA, NWD, CW, c);
             Mask<NW> gl, hal, gr;
             if (c == 0) {
                 gl.w0 = s_halo_masks[2 * 2 + 0];
-                hal.w0 = s_halo_masks[4 * 2 + 0];
-                if constexpr (NW == 2) { gl.w1 = s_halo_masks[2 * 2 + 1]; hal.w1 = s_halo_masks[4 * 2 + 1]; }
+                hal.w0 = s_halo32[4 * 4 + 0] | (NWD > 1 ? static_cast<unsigned long long>(s_halo32[4 * 4 + 1]) << 32 : 0ull);
+                if constexpr (NW == 2) {
+                    gl.w1 = s_halo_masks[2 * 2 + 1];
+                    hal.w1 = (NWD > 2 ? s_halo32[4 * 4 + 2] : 0u) | (NWD > 3 ? static_cast<unsigned long long>(s_halo32[4 * 4 + 3]) << 32 : 0ull);
+                }
             } else {
-                gl = ld_mask<NW>(s_masks, MK_G, CWp, c - 1);
-                hal = ld_mask<NW>(s_masks, MK_HA, CWp, c - 1);
+                gl = ld_mask32<NW>(s_m32, MK_G, NWD, CW, c - 1);
+                hal = ld_mask32<NW>(s_m32, MK_HA, NWD, CW, c - 1);
             }
             if (c == myCW - 1) {
                 gr.w0 = s_halo_masks[1 * 2 + 0];
                 if constexpr (NW == 2) gr.w1 = s_halo_masks[1 * 2 + 1];
             } else {
-                gr = ld_mask<NW>(s_masks, MK_G, CWp, c + 1);
+                gr = ld_mask32<NW>(s_m32, MK_G, NWD, CW, c + 1);
             }
-            const Mask<NW> eseed = ld_mask<NW>(s_masks, MK_KEEP, CWp, c);
+            const Mask<NW> eseed = ld_mask32<NW>(s_m32, MK_KEEP, NWD, CW, c);
             const Mask<NW> near = (g.shr(1) & va) | (g & va).shl(1) | (gl & hal) | (gr & ha);
             const Mask<NW> L = (g | eseed | (~valid & near)) & Hmask;
             // dilated(r) = OR_k L(r + off_k)   (effective taps of cv::dilate with GetUniformKernel's bytes)
             Mask<NW> D = (kp.dil0 >= 0) ? L.shr(kp.dil0) : L.shl(-kp.dil0);
             if (kp.n_dil > 1) D = D | ((kp.dil1 >= 0) ? L.shr(kp.dil1) : L.shl(-kp.dil1));
             const Mask<NW> keep = valid & (kp.erase_ground ? ~D : D) & Hmask;  // alfa_gs.cpp:751-764
-            st_mask<NW>(s_masks, MK_KEEP, CWp, c, keep);
+            st_mask32<NW>(s_m32, MK_KEEP, NWD, CW, c, keep);
         }
         __syncthreads();
-        // transpose the KEEP masks to row-major 32-column groups, count rows
-        for (int gidx = warp; gidx < NG; gidx += NT / 32) {
+        // transpose the KEEP words to row-major 32-column groups, count rows
+        for (int job = warp; job < NG * NWD; job += NT / 32) {
+            const int gidx = job / NWD, w = job - gidx * NWD;
             const int c = gidx * 32 + lane;
-            Mask<NW> keep = Mask<NW>::zero();
-            if (c < myCW) keep = ld_mask<NW>(s_masks, MK_KEEP, CWp, c);
-            for (int r = 0; r < H; ++r) {
-                const unsigned m = __ballot_sync(0xffffffffu, keep.bit(r));
-                if (lane == 0) s_rowmask[r * NG + gidx] = m;
+            const unsigned kw = c < myCW ? MW(MK_KEEP, w, c) : 0u;
+            const int nrow = min(32, H - 32 * w);
+            for (int i = 0; i < nrow; ++i) {
+                const unsigned m = __ballot_sync(0xffffffffu, (kw >> i) & 1u);
+                if (lane == 0) s_rowmask[(32 * w + i) * NG + gidx] = m;
             }
         }
         __syncthreads();
@@ -934,6 +1158,8 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
             }
             for (int k = 0; k < CL; ++k) cluster.map_shared_rank(s_rowcnt_all, k)[rank * MAX_H + r] = run;
         }
+#undef MW
+        GS_PHASE(12);
         cluster.sync();  // #: row counts of every slab everywhere
         if (warp == 0) {
             // rowbase[r] = points in rows above (all slabs) + points of row r in the slabs left of mine
@@ -960,6 +1186,7 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
         }
         __syncthreads();
 
+        GS_PHASE(13);
         // ================================================================================ B: no-ground image + cloud
         {
             uint16_t* res = A.res_out ? A.res_out + static_cast<size_t>(f) * kp.P : nullptr;
@@ -978,8 +1205,8 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
                         const unsigned slot = s_rowbase[r] + s_grp[pair] + __popc(m & ((1u << lane) - 1u));
                         const double rng_d = decode_range_d(kp, enc);
                         const double rng = range_as_double ? rng_d : static_cast<double>(__double2float_rn(rng_d));  // alfa_gs.cpp:1027,1045 / range2cloud_node.cpp:76
-                        const double ca = A.lut.cos_alt[r], sa = A.lut.sin_alt[r];
-                        const double caz = A.lut.cos_az[col0 + cc], saz = A.lut.sin_az[col0 + cc];
+                        const double ca = s_cos_alt[r], sa = s_sin_alt[r];
+                        const double caz = s_cos_az[cc], saz = s_sin_az[cc];
                         float4 o;
                         o.x = __double2float_rn(__dmul_rn(__dmul_rn(ca, caz), rng));  // :1055
                         o.y = __double2float_rn(__dmul_rn(__dmul_rn(ca, saz), rng));  // :1056
@@ -990,10 +1217,11 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
                 }
             }
         }
+        GS_PHASE(0);
         __syncthreads();  // the slabs are cleared at the top of the next frame
     }
 
-    if (A.stats) {
+    if ((A.stats & 1)) {
         // block-level reduction is not worth it: stats runs are test runs
         if (st_dropped) atomicAdd(&A.cnt->dropped, st_dropped);
         if (st_near) atomicAdd(&A.cnt->near_edge_project, st_near);
@@ -1001,6 +1229,11 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
         if (st_remote) atomicAdd(&A.cnt->remote, st_remote);
         if (st_fallback) atomicAdd(&A.cnt->slow_path, st_fallback);
         if (st_mismatch) atomicAdd(&A.cnt->fast_mismatch, st_mismatch);
+    }
+    if (A.stats & 2) {
+        if (dbg_cnt[0]) atomicAdd(&A.cnt->phase[16], static_cast<unsigned long long>(dbg_cnt[0]));
+        if (dbg_cnt[1]) atomicAdd(&A.cnt->phase[17], static_cast<unsigned long long>(dbg_cnt[1]));
+        if (dbg_cnt[2]) atomicAdd(&A.cnt->phase[18], static_cast<unsigned long long>(dbg_cnt[2]));
     }
     cluster.sync();  // no CTA exits while a neighbour may still address its shared memory
 }
@@ -1012,7 +1245,7 @@ namespace {
 
 struct Layout {
     int CL, CW, S16, S8, NG;
-    unsigned off_range, off_tag, off_angle, off_masks, off_misc;
+    unsigned off_range, off_tag, off_angle, off_masks, off_misc, off_lut;
     size_t total;
 };
 
@@ -1036,13 +1269,16 @@ bool layout_for(const KParams& kp, int CL, int NW, Layout* L) {
     const size_t masks_bytes = align_up(static_cast<size_t>(MK_COUNT) * NW * CW * 8 + static_cast<size_t>(2) * H * L->NG * 4, 16);
     const size_t tag_bytes = align_up(std::max(range_bytes, static_cast<size_t>(H) * CW * 2), 16);
     const size_t angle_bytes = align_up(std::max(static_cast<size_t>(H) * L->S8, static_cast<size_t>(MAX_BLOCKS) * 3), 16);
-    const size_t misc_bytes = align_up(static_cast<size_t>(MAX_CL) * MAX_H * 4 + MAX_H * 4 + 14 * 8 + MAX_H + MAX_CL * 4 + 64, 16);
+    const size_t misc_bytes = align_up(static_cast<size_t>(MAX_CL) * MAX_H * 4 + MAX_H * 4 + 14 * 8 + MAX_H + MAX_CL * 4 + (8 + 20 + 64) * 4 + 64, 16);
     L->off_range = 0;
     L->off_tag = static_cast<unsigned>(range_bytes);
     L->off_angle = static_cast<unsigned>(range_bytes + tag_bytes);
     L->off_masks = static_cast<unsigned>(range_bytes + tag_bytes + angle_bytes);
     L->off_misc = static_cast<unsigned>(range_bytes + tag_bytes + angle_bytes + masks_bytes);
-    L->total = range_bytes + tag_bytes + angle_bytes + masks_bytes + misc_bytes;
+    // per-CTA copies of the lookup tables: cos/sin(azimuth) of my columns, cos/sin(altitude), sin/cos(angle_y) as double and float
+    const size_t lut_bytes = align_up(static_cast<size_t>(2) * CW * 8 + static_cast<size_t>(4) * H * 8 + static_cast<size_t>(2) * H * 4, 16);
+    L->off_lut = static_cast<unsigned>(range_bytes + tag_bytes + angle_bytes + masks_bytes + misc_bytes);
+    L->total = range_bytes + tag_bytes + angle_bytes + masks_bytes + misc_bytes + lut_bytes;
     return true;
 }
 
@@ -1108,6 +1344,12 @@ int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const Sg
     fs.smem_bytes = lay.total;
     fs.n_sms = n_sms;
     fs.max_clusters = max_clusters;
+    if (!fs.d_const) {
+        e = cudaMalloc(&fs.d_const, sizeof(KParams));
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    e = cudaMemcpy(fs.d_const, &kp, sizeof(KParams), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return static_cast<int>(e);
     fs.configured = true;
     return 0;
 }
@@ -1127,7 +1369,7 @@ long long fused_max_points() { return static_cast<long long>(MAX_BLOCKS) * BLK; 
 
 int fused_run(FusedState& fs, const Launch& L, const float4* points, const long long* d_offsets, int frames, long long max_points,
               uint16_t* range_out, uint16_t* angle_out, uint16_t* res_out, float4* xyz_out, unsigned* counts_out, Counters* cnt,
-              bool stats) {
+              int stats) {
     if (frames <= 0) return 0;
     if (max_points > fused_max_points()) return static_cast<int>(cudaErrorInvalidValue);
     const KParams& kp = fs.kp;
@@ -1158,6 +1400,7 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
     a.off_tag = lay.off_tag;
     a.off_angle = lay.off_angle;
     a.off_masks = lay.off_masks;
+    a.off_lut = lay.off_lut;
     a.off_misc = lay.off_misc;
     a.points = points;
     a.offsets = d_offsets;
@@ -1168,7 +1411,7 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
     a.xyz_out = xyz_out;
     a.counts_out = counts_out;
     a.cnt = cnt;
-    a.stats = stats ? 1 : 0;
+    a.stats = stats;  // bit 0: verification + counters, bit 1: phase timing
     a.rcap = rcap;
     // fast-path constants (see project_fast)
     {
@@ -1189,7 +1432,7 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
         a.col_margin = static_cast<int>(std::ceil(7.5e-7 * az_scale * two_fb)) + 8;    // 7.5e-7 rad >= 4x the azimuth error budget
         a.cw_magic = static_cast<unsigned>((0x100000000ull + lay.CW - 1) / lay.CW);
         a.ng_magic = static_cast<unsigned>((0x100000000ull + lay.NG - 1) / lay.NG);
-        a.mycw_shift = 0;
+        a.kp_dev = static_cast<const KParams*>(fs.d_const);
         // the fixed-point coordinates need 4 * quarter_fix < 2^31 and |altitude cells| * 2^FB < 2^31
         a.use_fast = (kp.W <= 8191 && alt_scale * 1.6 * two_fb < 2.0e9 && std::fabs(row0) * two_fb < 2.0e9 &&
                       a.row_margin < (1 << (FB - 2)) && a.col_margin < (1 << (FB - 2))) ? 1 : 0;

@@ -38,6 +38,7 @@ struct SgTaps {
 
 struct Counters {
     unsigned long long near_edge_project, near_edge_angle, dropped, slow_path, components, fast_mismatch, remote;
+    unsigned long long phase[20];  // fused kernel: clock64() cycles per phase, summed over CTAs (statistics runs only)
 };
 
 // Device scratch for one wave ("chunk") of frames; every array holds `frames` slabs.
@@ -111,7 +112,7 @@ bool fused_supported(const FusedState& fs);
 long long fused_max_points();  // frames with more points than this run on the staged kernels
 int fused_run(FusedState& fs, const Launch& L, const float4* points, const long long* d_offsets, int frames, long long max_points,
               uint16_t* range_out, uint16_t* angle_out, uint16_t* res_out, float4* xyz_out, unsigned* counts_out, Counters* cnt,
-              bool stats);
+              int stats);
 void fused_release(FusedState& fs);
 
 }  // namespace gs

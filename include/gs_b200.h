@@ -140,9 +140,13 @@ int gs_set_chunk_frames(gs_ctx* ctx, int frames);
  * (both are CUDA paths; used by the parity tests to check one against the other). */
 #define GS_OPT_COLLECT_STATS 1
 #define GS_OPT_FORCE_STAGED 2
+#define GS_OPT_PHASE_TIMING 3 /* fused kernel accumulates clock64() cycles per internal phase (gs_get_phase_cycles) */
 int gs_set_option(gs_ctx* ctx, int option, int value);
 int gs_get_stats(gs_ctx* ctx, gs_stats* out);
 int gs_reset_stats(gs_ctx* ctx);
+/* fused kernel, with GS_OPT_PHASE_TIMING: SM clock cycles per internal phase summed over all CTAs since the last reset
+ * (16 entries; the phase names are in DESIGN.md).  A profiling aid, not part of the reference's surface. */
+int gs_get_phase_cycles(gs_ctx* ctx, uint64_t* out16);
 const char* gs_last_error(const gs_ctx* ctx);
 
 /* ---- stage API: one frame, HOST buffers (copies included) ---------------------------------- */
