@@ -179,8 +179,8 @@ class Context:
         return s
 
     PHASES = ["clear+deal", "project rounds", "wait: rounds done", "remote records", "angle walk", "wait: angles done",
-              "edges+seeds", "wait: edges done", "unions", "boundary rounds", "forest readout",
-              "label+dilate+transpose", "wait: row counts", "images+cloud out", "flatten forest", "seed flags"]
+              "edges+seeds", "wait: edges done", "link scan", "boundary rounds", "forest readout",
+              "label+dilate+transpose", "wait: row counts", "images+cloud out", "union pass", "seed flags"]
 
     def phase_cycles(self):
         out = (C.c_uint64 * 16)()

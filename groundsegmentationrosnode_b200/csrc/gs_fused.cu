@@ -26,6 +26,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <math_constants.h>
 
 #include "gs_internal.h"
@@ -37,8 +38,7 @@ namespace gs {
 
 namespace {
 
-constexpr int NT = 1024;        // threads per CTA
-constexpr int NPT = 2;          // points per thread per round
+constexpr int NPT = 4;          // points per thread per round
 constexpr int BLK = 256;        // points per dealt block
 constexpr int MAX_BLOCKS = 4096;  // per frame: up to 1 Mi points
 constexpr int MAX_CL = 8;
@@ -78,6 +78,7 @@ struct FusedArgs {
     unsigned cw_magic;         // ceil(2^32 / CW): owner = (col * cw_magic) >> 32 for col < 2^16
     unsigned ng_magic;         // ceil(2^32 / NG)
     const KParams* kp_dev;     // device-memory copy of kp for the out-of-line exact path
+    int col_limit, col_wrap;   // largest column the fast path may return; GS_COL_WRAP
     int use_fast;
 };
 
@@ -363,7 +364,8 @@ __device__ __forceinline__ int project_fast(const FusedArgs& A, float fx, float 
     // altitude
     const float ax = fabsf(fx), ay = fabsf(fy), az = fabsf(fz);
     if (fy == 0.0f) return 2;  // atan2(-0.0, x < 0) = -pi in the reference (Q3): exact path
-    const float h = sqrtf(__fmaf_rn(fx, fx, __fmul_rn(fy, fy)));
+    const float h2 = __fmaf_rn(fx, fx, __fmul_rn(fy, fy));
+    const float h = __fmul_rn(h2, rsqrtf(h2));  // 2-3 ulp: 1e-7 rad of altitude at most
     const float lo_a = fminf(az, h), hi_a = fmaxf(az, h);
     float t = atan01(__fdividef(lo_a, hi_a));
     if (az > h) t = 1.57079632679489662f - t;
@@ -386,14 +388,11 @@ __device__ __forceinline__ int project_fast(const FusedArgs& A, float fx, float 
     const int cfrac = colfix & ((1 << FB) - 1);
     if (!(cfrac >= A.col_margin && cfrac <= (1 << FB) - A.col_margin)) return 2;
     int col = colfix >> FB;
-    if (row < 0 || row >= kp.H || col < 0) return 2;  // cannot happen inside the gates; let the exact path decide
-    if (kp.variant == GS_VARIANT_CLOUD2RANGE) {
-        if (col >= kp.W) return 2;
-    } else if (kp.col_policy == GS_COL_WRAP) {
-        if (col >= kp.W) col -= kp.W;
-    } else {
-        if (col > kp.W) return 2;
-        if (col == kp.W && row == kp.H - 1) return 1;  // Q2: flat index past the end of the image
+    // inside the gates 0 <= row < H and 0 <= col <= W hold; anything else goes to the exact path
+    if (static_cast<unsigned>(row) >= static_cast<unsigned>(kp.H) || static_cast<unsigned>(col) > static_cast<unsigned>(A.col_limit)) return 2;
+    if (col == kp.W) {  // only the alfa_gs variant gets here (col_limit = W)
+        if (A.col_wrap) col = 0;                  // GS_COL_WRAP
+        else if (row == kp.H - 1) return 1;       // Q2: flat index past the end of the image
     }
     *row_out = row;
     *col_out = col;
@@ -431,8 +430,8 @@ struct Smem {
 // ====================================================================================================================
 // the kernel
 // ====================================================================================================================
-template <int NW>
-__global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
+template <int NW, int NT>  // NW: 64-bit words per column mask (H <= 64 * NW); NT: threads per CTA (1024 x 1 CTA/SM or 512 x 2 CTAs/SM)
+__global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
     const KParams& kp = A.kp;
@@ -464,15 +463,17 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
     // scratch of the labelling stage in the angle slab (dead once the links are computed): link words to unite and their scan
     unsigned* s_todo = reinterpret_cast<unsigned*>(s_angle);                 // [(CW - 1) * NWD]
     uint16_t* s_excl = reinterpret_cast<uint16_t*>(s_todo + static_cast<size_t>(CW) * NWD);  // [(CW - 1) * NWD + 1]
+    uint16_t* s_qcw = s_excl + static_cast<size_t>(CW) * NWD + 2;                            // [(CW - 1) * NWD] column << 2 | word
     unsigned* s_grp = s_rowmask + H * NG;                                                                  // [H][NG]
     uint8_t* s_assign = s_angle;                                                                           // [MAX_BLOCKS]
     uint16_t* s_mylist = reinterpret_cast<uint16_t*>(s_angle + MAX_BLOCKS);                                // [MAX_BLOCKS]
     unsigned char* misc = smem_raw + A.off_misc;
-    unsigned* s_rowcnt_all = reinterpret_cast<unsigned*>(misc);                         // [MAX_CL][MAX_H]
-    unsigned* s_rowbase = s_rowcnt_all + MAX_CL * MAX_H;                                // [MAX_H]
-    unsigned long long* s_halo_masks = reinterpret_cast<unsigned long long*>(s_rowbase + MAX_H);  // [7][2]
-    uint8_t* s_halo_angle = reinterpret_cast<uint8_t*>(s_halo_masks + 14);              // [MAX_H]
-    unsigned* s_flags = reinterpret_cast<unsigned*>(s_halo_angle + MAX_H);              // [MAX_CL]
+    const int Hp = (H + 7) & ~7;
+    unsigned long long* s_halo_masks = reinterpret_cast<unsigned long long*>(misc);     // [7][2]
+    unsigned* s_rowcnt_all = reinterpret_cast<unsigned*>(s_halo_masks + 14);            // [MAX_CL][Hp]
+    unsigned* s_rowbase = s_rowcnt_all + MAX_CL * Hp;                                   // [Hp]
+    uint8_t* s_halo_angle = reinterpret_cast<uint8_t*>(s_rowbase + Hp);                 // [Hp]
+    unsigned* s_flags = reinterpret_cast<unsigned*>(s_halo_angle + Hp);                 // [MAX_CL]
     unsigned* s_misc = s_flags + MAX_CL;                                                // [0] nmine, [1] scratch
     unsigned* s_halo32 = s_misc + 8;                                                    // [5][4] halo mask words
     unsigned* s_scan = s_halo32 + 20;                                                   // [64] block scan scratch
@@ -571,34 +572,20 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
 
         GS_PHASE(1);
         // ================================================================================ P1: local rounds
-        // the points of the next round are loaded while the current round is processed
-        float4 cur_p[NPT];
-        int cur_i[NPT];
-#pragma unroll
-        for (int j = 0; j < NPT; ++j) {
-            const int q = j * NT + tid;
-            int i = -1;
-            if (q < nmine * BLK) {
-                i = static_cast<int>(s_mylist[q >> 8]) * BLK + (q & (BLK - 1));
-                if (i >= N) i = -1;
-            }
-            cur_i[j] = i;
-            cur_p[j] = i >= 0 ? __ldcs(pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
         for (int qb = 0; qb < nmine * BLK; qb += NT * NPT) {
             unsigned key[NPT], val[NPT];  // key: owner << 16 | slab address (0xffffffff = nothing to store); val: g << 16 | enc
-            float4 nxt_p[NPT];
-            int nxt_i[NPT];
+            float4 cur_p[NPT];
+            int cur_i[NPT];
 #pragma unroll
-            for (int j = 0; j < NPT; ++j) {
-                const int q = qb + NT * NPT + j * NT + tid;
+            for (int j = 0; j < NPT; ++j) {  // all loads of the round are in flight before the first one is used
+                const int q = qb + j * NT + tid;
                 int i = -1;
                 if (q < nmine * BLK) {
                     i = static_cast<int>(s_mylist[q >> 8]) * BLK + (q & (BLK - 1));
                     if (i >= N) i = -1;
                 }
-                nxt_i[j] = i;
-                nxt_p[j] = i >= 0 ? __ldcs(pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                cur_i[j] = i;
+                cur_p[j] = i >= 0 ? __ldcs(pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int j = 0; j < NPT; ++j) {
@@ -676,11 +663,6 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
 #pragma unroll
             for (int j = 0; j < NPT; ++j)
                 if (key[j] != 0xffffffffu && s_tag[key[j]] == (val[j] >> 16)) s_range[key[j]] = static_cast<uint16_t>(val[j] & 0xffffu);
-#pragma unroll
-            for (int j = 0; j < NPT; ++j) {
-                cur_p[j] = nxt_p[j];
-                cur_i[j] = nxt_i[j];
-            }
         }
         GS_PHASE(2);
         __threadfence();  // remote records and counts visible before the cluster-wide phase
@@ -886,7 +868,7 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
         const int n_q = (myCW - 1) * NWD;  // (boundary in level order, word)
         auto level_count = [=](int k) -> int {
             const int first = (1 << k) - 1;
-            return (myCW - 2 >= first) ? (myCW - 2 - first) / (2 << k) + 1 : 0;
+            return (myCW - 2 >= first) ? ((myCW - 2 - first) >> (k + 1)) + 1 : 0;
         };
         auto boundary_of = [=](int p) -> int {  // p-th boundary in level order -> left column of the boundary
             for (int k = 0;; ++k) {
@@ -903,6 +885,7 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
                 if (q < n_q) {
                     const int pb = q / NWD, w = q - pb * NWD;
                     const int c = boundary_of(pb);
+                    s_qcw[q] = static_cast<uint16_t>((c << 2) | w);
                     const unsigned hm = MW(MK_HM, w, c);
                     if (hm) {
                         // one union per pair of runs: skip link r when link r-1 joins the same two runs
@@ -924,7 +907,7 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
                 if (lane == 31) s_scan[warp] = incl;
                 __syncthreads();
                 if (warp == 0) {
-                    unsigned ws = s_scan[lane];
+                    unsigned ws = lane < NT / 32 ? s_scan[lane] : 0u;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
                         const unsigned t = __shfl_up_sync(0xffffffffu, ws, d);
@@ -935,55 +918,53 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
                 __syncthreads();
                 const unsigned before = carry + (warp ? s_scan[32 + warp - 1] : 0u) + incl - cnt;
                 if (q < n_q) s_excl[q] = static_cast<uint16_t>(before);
-                carry += s_scan[32 + 31];
+                carry += s_scan[32 + NT / 32 - 1];
                 __syncthreads();
             }
             if (tid == 0) s_excl[n_q] = static_cast<uint16_t>(carry);
             __syncthreads();
         }
+        GS_PHASE(14);
         {
-            int q_lo = 0;
-            for (int lev = 0; lev < n_levels; ++lev) {
-                const int q_hi = q_lo + level_count(lev) * NWD;
-                const int t0 = s_excl[q_lo], t1 = s_excl[q_hi];
-                if (t1 > t0) {
-                    const int per = (t1 - t0 + NT - 1) / NT;
-                    int task = t0 + tid * per;
-                    const int task_end = min(task + per, t1);
-                    if (task < task_end) {
-                        int ql = q_lo, qh = q_hi - 1;  // largest q in the level with s_excl[q] <= task
-                        while (ql < qh) {
-                            const int mid = (ql + qh + 1) >> 1;
-                            if (static_cast<int>(s_excl[mid]) <= task) ql = mid;
-                            else qh = mid - 1;
+            // one balanced pass over all links in level order: thread t takes the tasks [t * per, (t + 1) * per)
+            const int t1 = s_excl[n_q];
+            if (t1 > 0) {
+                const int per = (t1 + NT - 1) / NT;
+                int task = tid * per;
+                const int task_end = min(task + per, t1);
+                if (task < task_end) {
+                    int ql = 0, qh = n_q - 1;  // largest q with s_excl[q] <= task
+                    while (ql < qh) {
+                        const int mid = (ql + qh + 1) >> 1;
+                        if (static_cast<int>(s_excl[mid]) <= task) ql = mid;
+                        else qh = mid - 1;
+                    }
+                    int q = ql;
+                    unsigned word = s_todo[q];
+                    for (int k = task - static_cast<int>(s_excl[q]); k > 0; --k) word &= word - 1;
+                    int cw = s_qcw[q], w = cw & 3, c = cw >> 2;
+                    for (; task < task_end; ++task) {
+                        while (word == 0u) {
+                            ++q;
+                            word = s_todo[q];
+                            cw = s_qcw[q];
+                            w = cw & 3;
+                            c = cw >> 2;
                         }
-                        int q = ql;
-                        unsigned word = s_todo[q];
-                        for (int k = task - static_cast<int>(s_excl[q]); k > 0; --k) word &= word - 1;
-                        int pb = q / NWD, w = q - pb * NWD, c = boundary_of(pb);
-                        for (; task < task_end; ++task) {
-                            while (word == 0u) {
-                                ++q;
-                                word = s_todo[q];
-                                pb = q / NWD;
-                                w = q - pb * NWD;
-                                c = boundary_of(pb);
-                            }
-                            const int i = __ffs(word) - 1;
-                            word &= word - 1;
-                            const unsigned below = 0xffffffffu >> (31 - i);
-                            // run starts of (32w + i, c) and (32w + i, c + 1): highest run-start bit at or below the row
-                            int wa = w, wb = w;
-                            unsigned ma = MW(MK_S, w, c) & below, mb = MW(MK_S, w, c + 1) & below;
-                            while (ma == 0u) ma = MW(MK_S, --wa, c);
-                            while (mb == 0u) mb = MW(MK_S, --wb, c + 1);
-                            uf16_unite(s_par, run_node(c, 32 * wa + 31 - __clz(ma)), run_node(c + 1, 32 * wb + 31 - __clz(mb)));
-                        }
+                        const int i = __ffs(word) - 1;
+                        word &= word - 1;
+                        const unsigned below = 0xffffffffu >> (31 - i);
+                        // run starts of (32w + i, c) and (32w + i, c + 1): highest run-start bit at or below the row
+                        int wa = w, wb = w;
+                        unsigned ma = MW(MK_S, w, c) & below, mb = MW(MK_S, w, c + 1) & below;
+                        while (ma == 0u) ma = MW(MK_S, --wa, c);
+                        while (mb == 0u) mb = MW(MK_S, --wb, c + 1);
+                        ++dbg_cnt[0];
+                        uf16_unite(s_par, run_node(c, 32 * wa + 31 - __clz(ma)), run_node(c + 1, 32 * wb + 31 - __clz(mb)), (A.stats & 2) ? dbg_cnt : nullptr);
                     }
                 }
-                q_lo = q_hi;
-                __syncthreads();
             }
+            __syncthreads();
         }
         GS_PHASE(15);
         for (int u = tid; u < n_units; u += NT) {
@@ -1156,7 +1137,7 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
                 s_grp[r * NG + gidx] = run;
                 run += __popc(s_rowmask[r * NG + gidx]);
             }
-            for (int k = 0; k < CL; ++k) cluster.map_shared_rank(s_rowcnt_all, k)[rank * MAX_H + r] = run;
+            for (int k = 0; k < CL; ++k) cluster.map_shared_rank(s_rowcnt_all, k)[rank * Hp + r] = run;
         }
 #undef MW
         GS_PHASE(12);
@@ -1169,7 +1150,7 @@ __global__ void __launch_bounds__(NT, 1) k_frame(const FusedArgs A) {
                 unsigned tot = 0, left = 0;
                 if (r < H)
                     for (int k = 0; k < CL; ++k) {
-                        const unsigned v = s_rowcnt_all[k * MAX_H + r];
+                        const unsigned v = s_rowcnt_all[k * Hp + r];
                         tot += v;
                         if (k < rank) left += v;
                     }
@@ -1269,7 +1250,8 @@ bool layout_for(const KParams& kp, int CL, int NW, Layout* L) {
     const size_t masks_bytes = align_up(static_cast<size_t>(MK_COUNT) * NW * CW * 8 + static_cast<size_t>(2) * H * L->NG * 4, 16);
     const size_t tag_bytes = align_up(std::max(range_bytes, static_cast<size_t>(H) * CW * 2), 16);
     const size_t angle_bytes = align_up(std::max(static_cast<size_t>(H) * L->S8, static_cast<size_t>(MAX_BLOCKS) * 3), 16);
-    const size_t misc_bytes = align_up(static_cast<size_t>(MAX_CL) * MAX_H * 4 + MAX_H * 4 + 14 * 8 + MAX_H + MAX_CL * 4 + (8 + 20 + 64) * 4 + 64, 16);
+    const size_t Hp = (static_cast<size_t>(H) + 7) & ~static_cast<size_t>(7);
+    const size_t misc_bytes = align_up(14 * 8 + static_cast<size_t>(MAX_CL) * Hp * 4 + Hp * 4 + Hp + MAX_CL * 4 + (8 + 20 + 64) * 4 + 64, 16);
     L->off_range = 0;
     L->off_tag = static_cast<unsigned>(range_bytes);
     L->off_angle = static_cast<unsigned>(range_bytes + tag_bytes);
@@ -1316,14 +1298,34 @@ int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const Sg
         }
     }
     if (!found) return 0;
-    auto kern = NW == 1 ? k_frame<1> : k_frame<2>;
+    // Two shapes: 512 threads with two CTAs (two frames) per SM, which overlaps one frame's barriers and serial phases
+    // with the other's work, when a slab fits half an SM's shared memory; else 1024 threads with one CTA per SM.
+    int max_smem_sm = 0;
+    e = cudaDeviceGetAttribute(&max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    int nt = 1024;
+    {
+        const char* mode = getenv("GS_FUSED_THREADS");  // "512" / "1024" forces a shape (experiments)
+        const size_t half = static_cast<size_t>(max_smem_sm) / 2 - 1024;  // 1 KB per CTA is reserved by the system
+        Layout l2;
+        bool found2 = false;
+        for (int CL = 1; CL <= MAX_CL; CL *= 2)
+            if (layout_for(kp, CL, NW, &l2) && l2.total <= half) { found2 = true; break; }
+        const bool want2 = mode ? atoi(mode) == 512 : false;  // measured equal on B200 (the kernel is not latency-bound per CTA); 1024 x 1 is the default
+        if (found2 && want2) {
+            lay = l2;
+            nt = 512;
+        }
+    }
+    const void* kern = nt == 512 ? (NW == 1 ? reinterpret_cast<const void*>(k_frame<1, 512>) : reinterpret_cast<const void*>(k_frame<2, 512>))
+                                 : (NW == 1 ? reinterpret_cast<const void*>(k_frame<1, 1024>) : reinterpret_cast<const void*>(k_frame<2, 1024>));
     // the attribute is per function, not per context: always ask for the device maximum
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e != cudaSuccess) return static_cast<int>(e);
     // how many clusters can be co-resident
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(n_sms / lay.CL * lay.CL));
-    cfg.blockDim = dim3(NT);
+    cfg.gridDim = dim3(static_cast<unsigned>((nt == 512 ? 2 : 1) * n_sms / lay.CL * lay.CL));
+    cfg.blockDim = dim3(nt);
     cfg.dynamicSmemBytes = lay.total;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1340,6 +1342,7 @@ int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const Sg
     }
     if (max_clusters < 1) return 0;
     fs.cluster = lay.CL;
+    fs.threads = nt;
     fs.cols_per_cta = lay.CW;
     fs.smem_bytes = lay.total;
     fs.n_sms = n_sms;
@@ -1433,6 +1436,8 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
         a.cw_magic = static_cast<unsigned>((0x100000000ull + lay.CW - 1) / lay.CW);
         a.ng_magic = static_cast<unsigned>((0x100000000ull + lay.NG - 1) / lay.NG);
         a.kp_dev = static_cast<const KParams*>(fs.d_const);
+        a.col_limit = c2r ? kp.W - 1 : kp.W;
+        a.col_wrap = (!c2r && kp.col_policy == GS_COL_WRAP) ? 1 : 0;
         // the fixed-point coordinates need 4 * quarter_fix < 2^31 and |altitude cells| * 2^FB < 2^31
         a.use_fast = (kp.W <= 8191 && alt_scale * 1.6 * two_fb < 2.0e9 && std::fabs(row0) * two_fb < 2.0e9 &&
                       a.row_margin < (1 << (FB - 2)) && a.col_margin < (1 << (FB - 2))) ? 1 : 0;
@@ -1442,7 +1447,7 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
                                            static_cast<size_t>(fs.max_clusters) * lay.CL * rcap * sizeof(uint2));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(n_clusters * lay.CL));
-    cfg.blockDim = dim3(NT);
+    cfg.blockDim = dim3(fs.threads);
     cfg.dynamicSmemBytes = lay.total;
     cfg.stream = L.stream;
     cudaLaunchAttribute attr[1];
@@ -1452,7 +1457,9 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    const cudaError_t e = NW == 1 ? cudaLaunchKernelEx(&cfg, k_frame<1>, a) : cudaLaunchKernelEx(&cfg, k_frame<2>, a);
+    cudaError_t e;
+    if (fs.threads == 512) e = NW == 1 ? cudaLaunchKernelEx(&cfg, k_frame<1, 512>, a) : cudaLaunchKernelEx(&cfg, k_frame<2, 512>, a);
+    else e = NW == 1 ? cudaLaunchKernelEx(&cfg, k_frame<1, 1024>, a) : cudaLaunchKernelEx(&cfg, k_frame<2, 1024>, a);
     if (e != cudaSuccess) return static_cast<int>(e);
     ++*L.n_launches;
     return 0;

@@ -94,6 +94,7 @@ struct FusedState {
     bool disabled = false;   // GS_OPT_FORCE_STAGED
     bool configured = false; // the configuration fits the fused kernel
     int cluster = 0;         // CTAs per frame
+    int threads = 1024;      // threads per CTA
     int cols_per_cta = 0;
     size_t smem_bytes = 0;
     int n_sms = 0;

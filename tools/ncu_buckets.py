@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Instruction / stall-sample shares of the fused kernel by phase (source line ranges are read from the GS_PHASE marks).
+
+    python tools/ncu_buckets.py gpurun_out/prof.ncu-rep [frames]
+"""
+import collections
+import csv
+import os
+import re
+import subprocess
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ncu_lines as T  # noqa: E402
+
+rep = sys.argv[1]
+frames = int(sys.argv[2]) if len(sys.argv) > 2 else 296
+src = open(os.path.join(T.ROOT, "groundsegmentationrosnode_b200", "csrc", "gs_fused.cu")).read().splitlines()
+marks = [(i + 1, int(re.search(r"GS_PHASE\((\d+)\)", l).group(1))) for i, l in enumerate(src) if re.match(r"\s+GS_PHASE\(\d+\);", l)]
+kernel_start = [i + 1 for i, l in enumerate(src) if "__global__ void __launch_bounds__(NT, 1) k_frame" in l][0]
+names = {0: "clear+deal", 1: "project rounds", 2: "wait rounds", 3: "remote", 4: "angle walk", 5: "wait angles", 6: "edges+seeds", 7: "wait edges",
+         8: "unions", 9: "boundary rounds", 10: "readout", 11: "label/dilate/transpose", 12: "wait rowcounts", 13: "output", 14: "flatten", 15: "seed flags"}
+
+
+def bucket(l):
+    if l is None:
+        return "other"
+    f, n = l
+    if f != "gs_fused.cu":
+        return "lib:" + f
+    if n < kernel_start:
+        for i in range(n - 1, -1, -1):
+            m = re.match(r"__device__ \S+ (?:\S+ )?(\w+)\(", src[i]) or re.match(r"(?:template.*)?struct (\w+)", src[i])
+            if m:
+                return "fn:" + m.group(1)
+        return "helpers"
+    cur = "prologue"
+    if n >= marks[0][0]:
+        cur = "clear+deal"
+    for ln, ph in marks:
+        if n >= ln:
+            cur = names.get(ph, str(ph))
+    return cur
+
+
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:k_frame"], capture_output=True, text=True).stdout.splitlines()
+rows = list(csv.reader(raw))
+hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
+hdr = rows[hi]
+body = [dict(zip(hdr, r)) for r in rows[hi + 1:] if len(r) == len(hdr)]
+lines = T.sass_lines("k_frameILi1")
+agg = collections.defaultdict(lambda: [0, 0])
+for d, l in zip(body, lines):
+    b = bucket(l)
+    agg[b][0] += int(d["Instructions Executed"] or 0)
+    agg[b][1] += int(d["# Samples"] or 0)
+ti = sum(v[0] for v in agg.values())
+ts = sum(v[1] for v in agg.values())
+print("total %.2f M warp-instructions per frame" % (ti / frames / 1e6))
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    print("%-28s inst %5.1f%% (%7.1fk/frame)   samples %5.1f%%" % (k, 100 * v[0] / ti, v[0] / frames / 1e3, 100 * v[1] / ts))
