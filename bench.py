@@ -35,6 +35,8 @@ from groundsegmentationrosnode_b200 import params as P, synth  # noqa: E402
 METRIC = "frames/s, 64x2048 cloud->range->ground->cloud (points/s alongside)"
 WORKLOAD = "C4: synthetic HDL-64E 64x2048 frames (~120k pts), pool of 64 distinct frames tiled to the batch"
 N_DISTINCT = 64
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_frame launch / frames in it (ncu --set full, profiles/r1_fused_ncu.md)
+TRAFFIC_BYTES_PER_FRAME = 2.99e6
 
 
 def rank_info():
@@ -286,10 +288,14 @@ def main():
                        "l2": "inputs (%.1f GB per step per GPU) are larger than L2; no flush needed" % (16.0 * n_points / 1e9),
                        "path": "staged kernels" if args.staged else "default (fused kernel when the configuration fits, else staged)",
                        "sharding": "frame-parallel, no collective"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": TRAFFIC_BYTES_PER_FRAME * F if (TRAFFIC_BYTES_PER_FRAME and not args.staged) else None,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_frame": bytes_per_step_gpu / F,
-                         "kernel": "whole step (%g launches per step); per-kernel shares in profiles/" % launches_per_step},
+                         "algorithmic_bytes_per_launch": bytes_per_step_gpu,
+                         "kernel": ("k_frame (fused persistent cluster kernel): the whole step is one launch" if launches_per_step <= 1.5
+                                    else "whole step (%g staged launches per step); per-kernel shares in profiles/" % launches_per_step),
+                         "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per frame x frames per launch (profiles/)"},
             "e2e": {"value": Fe_all * e_steps / e_sec, "unit": "frames/s", "points_per_s": e_pts_all * e_steps / e_sec,
                     "h2d_bytes_per_step": int(16 * e_points), "d2h_bytes_per_step": int(2 * Pn * Fe + 16 * e_out_records + 4 * Fe),
                     "frames_per_step": Fe, "api": "gs_process_batch_host (pinned host buffers, chunked copy/compute overlap)"},
