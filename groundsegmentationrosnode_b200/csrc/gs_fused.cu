@@ -26,6 +26,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <math_constants.h>
 
@@ -133,7 +134,11 @@ __device__ __forceinline__ void cas_max_u16(uint16_t* p, unsigned v) {
 }
 
 // Union-find over vertical runs, 16-bit parents in shared memory: bits 0..14 = parent index, bit 15 = "ground" flag
-// (meaningful on roots).  Roots hang under the smaller index, so the forest is acyclic without ranks.
+// (meaningful on roots).  A root is always hung under a root of higher priority, priority = a multiplicative hash of the
+// index (ties impossible: the hash is a bijection on 16 bits), so the forest is acyclic and — unlike linking by index,
+// where the simultaneous unions of neighbouring columns build a chain as long as the slab is wide — its expected height
+// is logarithmic (randomised linking); finds halve the paths they walk.
+__device__ __forceinline__ unsigned uf16_prio(int x) { return (static_cast<unsigned>(x) * 40503u) & 0xffffu; }  // odd multiplier: bijective mod 2^16
 __device__ __forceinline__ int uf16_find(volatile uint16_t* par, int x, unsigned* hops = nullptr) {
     // path halving: only non-root entries are rewritten (plain 16-bit stores), roots change through atomicCAS / atomicOr only
     for (;;) {
@@ -152,7 +157,7 @@ __device__ __forceinline__ void uf16_unite(uint16_t* par, int a, int b, unsigned
         a = uf16_find(par, a, dbg ? dbg + 2 : nullptr);
         b = uf16_find(par, b, dbg ? dbg + 2 : nullptr);
         if (a == b) return;
-        if (a < b) { const int t = a; a = b; b = t; }
+        if (uf16_prio(a) > uf16_prio(b)) { const int t = a; a = b; b = t; }  // a: lower priority, hangs under b
         unsigned* w = reinterpret_cast<unsigned*>(par) + (a >> 1);
         const int sh = (a & 1) * 16;
         const unsigned old = *reinterpret_cast<volatile unsigned*>(w);
@@ -571,13 +576,16 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         const int nmine = static_cast<int>(s_misc[0]);
 
         GS_PHASE(1);
-        // ================================================================================ P1: local rounds
+        // ================================================================================ P1: projection + pixel ownership
+        // "The last point in input order wins" (alfa_gs.cpp:291) as ONE 32-bit shared-memory atomicMax per point on the
+        // key (g << 16 | range), g = index / 32 + 1: a later group of 32 points always beats an earlier one and carries
+        // its range along; inside a group (= a warp) __match_any_sync keeps the highest lane.  No barriers, no rounds.
+        unsigned* s_key = reinterpret_cast<unsigned*>(s_range);  // [H][S16] u32 over the range + tag slabs, compacted to u16 below
         for (int qb = 0; qb < nmine * BLK; qb += NT * NPT) {
-            unsigned key[NPT], val[NPT];  // key: owner << 16 | slab address (0xffffffff = nothing to store); val: g << 16 | enc
             float4 cur_p[NPT];
             int cur_i[NPT];
 #pragma unroll
-            for (int j = 0; j < NPT; ++j) {  // all loads of the round are in flight before the first one is used
+            for (int j = 0; j < NPT; ++j) {  // all loads of the batch are in flight before the first one is used
                 const int q = qb + j * NT + tid;
                 int i = -1;
                 if (q < nmine * BLK) {
@@ -589,10 +597,9 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             }
 #pragma unroll
             for (int j = 0; j < NPT; ++j) {
-                key[j] = 0xffffffffu;
-                val[j] = 0;
                 const int i = cur_i[j];
-                unsigned k = 0x80000000u | lane;  // unique per lane: never matches
+                unsigned k = 0x80000000u | lane;  // owner << 16 | slab address; this value is unique per lane: never matches
+                unsigned val = 0;                 // g << 16 | encoded range
                 if (i >= 0) {
                     const float4 p4 = cur_p[j];
                     int row = -1, col = -1;
@@ -622,23 +629,16 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                         const int owner = min(static_cast<int>(__umulhi(static_cast<unsigned>(col), A.cw_magic)), CL - 1);
                         const int lc = col - owner * CW;
                         k = (static_cast<unsigned>(owner) << 16) | static_cast<unsigned>(row * S16 + lc);
-                        val[j] = ((static_cast<unsigned>(i >> 5) + 1u) << 16) | enc;
+                        val = ((static_cast<unsigned>(i >> 5) + 1u) << 16) | enc;
                     }
                 }
                 // the highest lane among the lanes that hit the same pixel holds the latest point of this group
                 const unsigned peers = __match_any_sync(0xffffffffu, k);
                 const bool winner = !(k & 0x80000000u) && (31 - __clz(peers)) == lane;
-                if (winner) {
-                    const int owner = static_cast<int>(k >> 16);
-                    if (owner == rank) {
-                        key[j] = k & 0xffffu;
-                        const unsigned g = val[j] >> 16;
-                        uint16_t* t = s_tag + key[j];
-                        if (*t < g) *t = static_cast<uint16_t>(g);
-                    }
-                }
+                const bool local = winner && static_cast<int>(k >> 16) == rank;
+                if (local) atomicMax(s_key + (k & 0xffffu), val);
                 // remote pixels: queue the record (warp-aggregated slot claim)
-                const bool remote = winner && static_cast<int>(k >> 16) != rank;
+                const bool remote = winner && !local;
                 const unsigned rm = __ballot_sync(0xffffffffu, remote);
                 if (rm) {
                     unsigned base = 0;
@@ -646,23 +646,11 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                     base = __shfl_sync(0xffffffffu, base, 0);
                     if (remote) {
                         const unsigned slot = base + __popc(rm & ((1u << lane) - 1u));
-                        if (slot < A.rcap) rlist[slot] = make_uint2(k, val[j]);
+                        if (slot < A.rcap) rlist[slot] = make_uint2(k, val);
                         if ((A.stats & 1)) ++st_remote;
                     }
                 }
             }
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < NPT; ++j)
-                if (key[j] != 0xffffffffu) {
-                    const unsigned g = val[j] >> 16;
-                    uint16_t* t = s_tag + key[j];
-                    if (*t < g) cas_max_u16(t, g);  // lost a same-round race to an earlier point
-                }
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < NPT; ++j)
-                if (key[j] != 0xffffffffu && s_tag[key[j]] == (val[j] >> 16)) s_range[key[j]] = static_cast<uint16_t>(val[j] & 0xffffu);
         }
         GS_PHASE(2);
         __threadfence();  // remote records and counts visible before the cluster-wide phase
@@ -677,17 +665,22 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                 const unsigned n = min(__ldcg(&rcount[rank]), A.rcap);
                 for (unsigned i = tid; i < n; i += NT) {
                     const uint2 rec = __ldcg(&rlist[i]);
-                    uint16_t* t = cluster.map_shared_rank(s_tag, rec.x >> 16) + (rec.x & 0xffffu);
-                    cas_max_u16(t, rec.y >> 16);
+                    atomicMax(cluster.map_shared_rank(s_key, rec.x >> 16) + (rec.x & 0xffffu), rec.y);
                 }
                 cluster.sync();  // #2
-                for (unsigned i = tid; i < n; i += NT) {
-                    const uint2 rec = __ldcg(&rlist[i]);
-                    const unsigned o = rec.x >> 16, a = rec.x & 0xffffu;
-                    if (cluster.map_shared_rank(s_tag, o)[a] == (rec.y >> 16)) cluster.map_shared_rank(s_range, o)[a] = static_cast<uint16_t>(rec.y & 0xffffu);
-                }
-                cluster.sync();  // #3
             }
+        }
+        // compact the keys to the u16 range slab in place (the low half of every key is the winner's range); the freed
+        // upper part (the tag slab) becomes the union-find forest later
+        {
+            const int n_px = H * S16;
+            for (int base = 0; base < n_px; base += NT) {
+                const int i = base + tid;
+                const unsigned v = i < n_px ? s_key[i] : 0u;
+                __syncthreads();  // every key of this chunk is read before its bytes are overwritten
+                if (i < n_px) s_range[i] = static_cast<uint16_t>(v);
+            }
+            __syncthreads();
         }
 
         // optional output: the range image
@@ -933,6 +926,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                 int task = tid * per;
                 const int task_end = min(task + per, t1);
                 if (task < task_end) {
+                    const long long dbg_t0 = (A.stats & 8) ? clock64() : 0;
                     int ql = 0, qh = n_q - 1;  // largest q with s_excl[q] <= task
                     while (ql < qh) {
                         const int mid = (ql + qh + 1) >> 1;
@@ -959,8 +953,15 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                         unsigned ma = MW(MK_S, w, c) & below, mb = MW(MK_S, w, c + 1) & below;
                         while (ma == 0u) ma = MW(MK_S, --wa, c);
                         while (mb == 0u) mb = MW(MK_S, --wb, c + 1);
-                        ++dbg_cnt[0];
-                        uf16_unite(s_par, run_node(c, 32 * wa + 31 - __clz(ma)), run_node(c + 1, 32 * wb + 31 - __clz(mb)), (A.stats & 2) ? dbg_cnt : nullptr);
+                        if (A.stats & 4) ++dbg_cnt[0];
+                        uf16_unite(s_par, run_node(c, 32 * wa + 31 - __clz(ma)), run_node(c + 1, 32 * wb + 31 - __clz(mb)), (A.stats & 4) ? dbg_cnt : nullptr);
+                    }
+                    if (A.stats & 8) {
+                        const unsigned long long dt = static_cast<unsigned long long>(clock64() - dbg_t0);
+                        atomicAdd(&A.cnt->phase[16], dt);
+                        atomicMax(&A.cnt->phase[17], dt);
+                        atomicAdd(&A.cnt->phase[18], static_cast<unsigned long long>(per));
+                        atomicAdd(&A.cnt->phase[19], 1ull);
                     }
                 }
             }
@@ -1341,6 +1342,8 @@ int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const Sg
         return 0;  // clusters of this size cannot be scheduled here: staged kernels
     }
     if (max_clusters < 1) return 0;
+    if (getenv("GS_DEBUG_PLAN")) fprintf(stderr, "gs fused plan: %d x %d image, %d threads, cluster %d, %d columns per CTA, %zu B smem, %d co-resident clusters on %d SMs\n",
+                                         kp.H, kp.W, nt, lay.CL, lay.CW, lay.total, max_clusters, n_sms);
     fs.cluster = lay.CL;
     fs.threads = nt;
     fs.cols_per_cta = lay.CW;
