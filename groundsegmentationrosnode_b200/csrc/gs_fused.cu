@@ -451,11 +451,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
     const int CWp = CW;                         // mask arrays are CW wide
     // forest index of the run that starts at row rs of local column c.  The row is rotated by 2c inside the column so that
     // runs starting at the same row in neighbouring columns (the ground does) fall into different shared-memory banks.
-    const bool h_pow2 = (H & (H - 1)) == 0;
-    auto run_node = [=](int c, int rs) -> int {
-        const int rot = rs + 2 * c;
-        return c * H + (h_pow2 ? (rot & (H - 1)) : (rot % H));
-    };
+    auto run_node = [=](int c, int rs) -> int { return c * H + ((rs + 2 * c) & (H - 1)); };  // H is a power of two (checked on the host)
 
     // ---- shared memory carve-up
     uint16_t* s_range = reinterpret_cast<uint16_t*>(smem_raw + A.off_range);
@@ -479,7 +475,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
     unsigned* s_rowbase = s_rowcnt_all + MAX_CL * Hp;                                   // [Hp]
     uint8_t* s_halo_angle = reinterpret_cast<uint8_t*>(s_rowbase + Hp);                 // [Hp]
     unsigned* s_flags = reinterpret_cast<unsigned*>(s_halo_angle + Hp);                 // [MAX_CL]
-    unsigned* s_misc = s_flags + MAX_CL;                                                // [0] nmine, [1] scratch
+    unsigned* s_misc = s_flags + 2 * MAX_CL;                                            // [0] nmine, [1] scratch   (s_flags: [2 parities][MAX_CL], written by the other CTAs)
     unsigned* s_halo32 = s_misc + 8;                                                    // [5][4] halo mask words
     unsigned* s_scan = s_halo32 + 20;                                                   // [64] block scan scratch
 
@@ -981,80 +977,72 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         }
         __syncthreads();
         GS_PHASE(9);
-        // Slab boundaries (and the column wrap of Label::WrapCols): exchange the ground masks of the boundary columns
-        // until no flag changes anywhere in the cluster.  Warp 0 owns my column 0, warp 1 my last column; lane l owns
-        // the rows [l*H/32, (l+1)*H/32).
-        for (;;) {
-            if (warp < 2) {
-                const int c = warp == 0 ? 0 : myCW - 1;
-                const Mask<NW> valid = ld_mask32<NW>(s_m32, MK_VALID, NWD, CW, c);
-                const Mask<NW> runs = ld_mask32<NW>(s_m32, MK_S, NWD, CW, c);
-                const int rlo = (lane * H) >> 5, rhi = ((lane + 1) * H) >> 5;
-                Mask<NW> g = Mask<NW>::zero();
-                for (Mask<NW> it = runs & Mask<NW>::low(rhi) & ~Mask<NW>::low(rlo); it.any(); it.clear_lowest()) {
-                    const int rs = it.lowest();
-                    const int root = uf16_find(s_par, run_node(c, rs));
-                    if (s_par[root] & 0x8000u) {
-                        const Mask<NW> later = runs & ~Mask<NW>::low(rs + 1);
-                        const int next = later.any() ? later.lowest() : H;
-                        g = g | (valid & Mask<NW>::low(next) & ~Mask<NW>::low(rs));
-                    }
-                }
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) {
-                    g.w0 |= __shfl_xor_sync(0xffffffffu, g.w0, d);
-                    if constexpr (NW == 2) g.w1 |= __shfl_xor_sync(0xffffffffu, g.w1, d);
-                }
-                if (lane == 0) {
-                    s_halo_masks[(5 + warp) * 2 + 0] = g.w0;
-                    if constexpr (NW == 2) s_halo_masks[(5 + warp) * 2 + 1] = g.w1;
-                }
+        // Slab boundaries (and the column wrap of Label::WrapCols): the CTAs publish the ground masks of their two boundary
+        // columns, import their neighbours' and flag the runs that ground reaches across the boundary, until a round in
+        // which nobody flagged anything.  One cluster barrier per round (publish slots are double-buffered).
+        uint16_t* s_broot = s_qcw + static_cast<size_t>(CW) * NWD + 2;  // [2][Hp] root of the run of (row, boundary column), 0xffff = empty pixel
+        unsigned* s_pub = s_scan;                                        // [2 parities][2 columns][4 words]
+        unsigned* s_chg = s_flags;                                       // [2 parities][MAX_CL], pushed by every CTA of the cluster
+        for (int t = tid; t < 2 * H; t += NT) {
+            const int b = t >= H ? 1 : 0, r = t - b * H;
+            const int c = b ? myCW - 1 : 0;
+            const int w = r >> 5, i = r & 31;
+            unsigned root = 0xffffu;
+            if ((MW(MK_VALID, w, c) >> i) & 1u) {
+                int wa = w;
+                unsigned ma = MW(MK_S, w, c) & (0xffffffffu >> (31 - i));
+                while (ma == 0u) ma = MW(MK_S, --wa, c);
+                root = static_cast<unsigned>(uf16_find(s_par, run_node(c, 32 * wa + 31 - __clz(ma))));
             }
-            cluster.sync();
-            bool changed = false;
-            if (warp < 2) {
-                Mask<NW> mine, theirs, link;
-                int c;
-                if (warp == 0) {  // my column 0 against the left neighbour's last column (link = its HM)
-                    c = 0;
-                    const unsigned long long* rm = cluster.map_shared_rank(s_halo_masks, left_rank);
-                    theirs.w0 = rm[6 * 2 + 0];
-                    mine.w0 = s_halo_masks[5 * 2 + 0];
-                    link.w0 = s_halo32[3 * 4 + 0] | (NWD > 1 ? static_cast<unsigned long long>(s_halo32[3 * 4 + 1]) << 32 : 0ull);
-                    if constexpr (NW == 2) {
-                        theirs.w1 = rm[6 * 2 + 1];
-                        mine.w1 = s_halo_masks[5 * 2 + 1];
-                        link.w1 = (NWD > 2 ? s_halo32[3 * 4 + 2] : 0u) | (NWD > 3 ? static_cast<unsigned long long>(s_halo32[3 * 4 + 3]) << 32 : 0ull);
+            s_broot[b * Hp + r] = static_cast<uint16_t>(root);
+        }
+        __syncthreads();
+        {
+            int changed_prev = 1;  // round 0 always runs
+            for (int round = 0;; ++round) {
+                const int pk = round & 1;
+                if (warp < 2) {  // publish: warp 0 = my column 0, warp 1 = my last column
+                    for (int w = 0; w < NWD; ++w) {
+                        const int r = 32 * w + lane;
+                        bool gnd = false;
+                        if (r < H) {
+                            const unsigned root = s_broot[warp * Hp + r];
+                            gnd = root != 0xffffu && (s_par[root] & 0x8000u) != 0;
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, gnd);
+                        if (lane == 0) s_pub[(pk * 2 + warp) * 4 + w] = m;
                     }
-                    if (lane == 0) {
-                        s_halo_masks[2 * 2 + 0] = theirs.w0;
-                        if constexpr (NW == 2) s_halo_masks[2 * 2 + 1] = theirs.w1;
-                    }
-                } else {  // my last column against the right neighbour's column 0 (link = my HM)
-                    c = myCW - 1;
-                    const unsigned long long* rm = cluster.map_shared_rank(s_halo_masks, right_rank);
-                    theirs.w0 = rm[5 * 2 + 0];
-                    mine.w0 = s_halo_masks[6 * 2 + 0];
-                    if constexpr (NW == 2) { theirs.w1 = rm[5 * 2 + 1]; mine.w1 = s_halo_masks[6 * 2 + 1]; }
-                    link = ld_mask32<NW>(s_m32, MK_HM, NWD, CW, c);
-                    if (lane == 0) {
-                        s_halo_masks[1 * 2 + 0] = theirs.w0;
-                        if constexpr (NW == 2) s_halo_masks[1 * 2 + 1] = theirs.w1;
+                } else if (warp == 2 && lane < CL) {
+                    cluster.map_shared_rank(s_chg, lane)[pk * MAX_CL + rank] = static_cast<unsigned>(changed_prev);
+                }
+                cluster.sync();
+                unsigned anyone = 0;
+                for (int k = 0; k < CL; ++k) anyone |= s_chg[pk * MAX_CL + k];
+                if (!anyone) break;
+                bool changed = false;
+                if (warp < 2) {
+                    // warp 0: my column 0 against the left neighbour's last column (link = its HM, static halo slot 3)
+                    // warp 1: my last column against the right neighbour's column 0 (link = my HM)
+                    const int nb_rank = warp == 0 ? left_rank : right_rank;
+                    const unsigned* their_pub = cluster.map_shared_rank(s_pub, nb_rank) + (pk * 2 + (warp == 0 ? 1 : 0)) * 4;
+                    const int c = warp == 0 ? 0 : myCW - 1;
+                    for (int w = 0; w < NWD; ++w) {
+                        const unsigned theirs = their_pub[w];
+                        const unsigned mine = s_pub[(pk * 2 + warp) * 4 + w];
+                        const unsigned link = warp == 0 ? s_halo32[3 * 4 + w] : MW(MK_HM, w, c);
+                        if (lane == 0) s_halo32[(warp == 0 ? 2 : 1) * 4 + w] = theirs;  // kept for the label stage (gl / gr)
+                        const unsigned in = theirs & link & ~mine;  // ground reaches these pixels of mine across the boundary
+                        if ((in >> lane) & 1u) {
+                            const unsigned root = s_broot[warp * Hp + 32 * w + lane];
+                            unsigned* wp = reinterpret_cast<unsigned*>(s_par) + (root >> 1);
+                            const int sh = (root & 1u) * 16;
+                            const unsigned old = atomicOr(wp, 0x8000u << sh);
+                            changed |= ((old >> sh) & 0x8000u) == 0;
+                        }
                     }
                 }
-                const int rlo = (lane * H) >> 5, rhi = ((lane + 1) * H) >> 5;
-                const Mask<NW> runs = ld_mask32<NW>(s_m32, MK_S, NWD, CW, c);
-                // ground reaches these pixels of mine across the boundary
-                for (Mask<NW> in = theirs & link & ~mine & Mask<NW>::low(rhi) & ~Mask<NW>::low(rlo); in.any(); in.clear_lowest())
-                    changed |= uf16_flag_root(s_par, run_node(c, (runs & Mask<NW>::low(in.lowest() + 1)).top()));
+                changed_prev = __syncthreads_or(changed ? 1 : 0);
             }
-            const int any_change = __syncthreads_or(changed ? 1 : 0);
-            if (tid < CL) cluster.map_shared_rank(s_flags, tid)[rank] = any_change ? 1u : 0u;
-            cluster.sync();
-            unsigned anyone = 0;
-            for (int k = 0; k < CL; ++k) anyone |= s_flags[k];
-            if (!anyone) break;
-            // (the next round's first cluster.sync orders these flag reads before the flags are rewritten)
         }
         GS_PHASE(10);
         // read the ground mask of every unit out of the forest
@@ -1094,10 +1082,10 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             const Mask<NW> ha = ld_mask32<NW>(s_m32, MK_HA, NWD, CW, c);
             Mask<NW> gl, hal, gr;
             if (c == 0) {
-                gl.w0 = s_halo_masks[2 * 2 + 0];
+                gl.w0 = s_halo32[2 * 4 + 0] | (NWD > 1 ? static_cast<unsigned long long>(s_halo32[2 * 4 + 1]) << 32 : 0ull);
                 hal.w0 = s_halo32[4 * 4 + 0] | (NWD > 1 ? static_cast<unsigned long long>(s_halo32[4 * 4 + 1]) << 32 : 0ull);
                 if constexpr (NW == 2) {
-                    gl.w1 = s_halo_masks[2 * 2 + 1];
+                    gl.w1 = (NWD > 2 ? s_halo32[2 * 4 + 2] : 0u) | (NWD > 3 ? static_cast<unsigned long long>(s_halo32[2 * 4 + 3]) << 32 : 0ull);
                     hal.w1 = (NWD > 2 ? s_halo32[4 * 4 + 2] : 0u) | (NWD > 3 ? static_cast<unsigned long long>(s_halo32[4 * 4 + 3]) << 32 : 0ull);
                 }
             } else {
@@ -1105,8 +1093,8 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                 hal = ld_mask32<NW>(s_m32, MK_HA, NWD, CW, c - 1);
             }
             if (c == myCW - 1) {
-                gr.w0 = s_halo_masks[1 * 2 + 0];
-                if constexpr (NW == 2) gr.w1 = s_halo_masks[1 * 2 + 1];
+                gr.w0 = s_halo32[1 * 4 + 0] | (NWD > 1 ? static_cast<unsigned long long>(s_halo32[1 * 4 + 1]) << 32 : 0ull);
+                if constexpr (NW == 2) gr.w1 = (NWD > 2 ? s_halo32[1 * 4 + 2] : 0u) | (NWD > 3 ? static_cast<unsigned long long>(s_halo32[1 * 4 + 3]) << 32 : 0ull);
             } else {
                 gr = ld_mask32<NW>(s_m32, MK_G, NWD, CW, c + 1);
             }
@@ -1252,7 +1240,7 @@ bool layout_for(const KParams& kp, int CL, int NW, Layout* L) {
     const size_t tag_bytes = align_up(std::max(range_bytes, static_cast<size_t>(H) * CW * 2), 16);
     const size_t angle_bytes = align_up(std::max(static_cast<size_t>(H) * L->S8, static_cast<size_t>(MAX_BLOCKS) * 3), 16);
     const size_t Hp = (static_cast<size_t>(H) + 7) & ~static_cast<size_t>(7);
-    const size_t misc_bytes = align_up(14 * 8 + static_cast<size_t>(MAX_CL) * Hp * 4 + Hp * 4 + Hp + MAX_CL * 4 + (8 + 20 + 64) * 4 + 64, 16);
+    const size_t misc_bytes = align_up(14 * 8 + static_cast<size_t>(MAX_CL) * Hp * 4 + Hp * 4 + Hp + 2 * MAX_CL * 4 + (8 + 20 + 64) * 4 + 64, 16);
     L->off_range = 0;
     L->off_tag = static_cast<unsigned>(range_bytes);
     L->off_angle = static_cast<unsigned>(range_bytes + tag_bytes);
@@ -1283,7 +1271,7 @@ int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const Sg
     // what the fused kernel covers; everything else runs on the staged kernels
     if (smooth || repair) return 0;
     if (kp.pixel_policy != GS_PIXEL_LAST) return 0;
-    if (kp.H > MAX_H || kp.W < 2) return 0;
+    if (kp.H > MAX_H || kp.W < 2 || (kp.H & (kp.H - 1)) != 0) return 0;  // beam counts that are powers of two (16 / 32 / 64 / 128)
     const int NW = kp.H <= 64 ? 1 : 2;
     int max_smem = 0, n_sms = 0;
     cudaError_t e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
