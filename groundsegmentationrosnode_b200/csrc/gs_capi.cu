@@ -412,7 +412,7 @@ int run_wave(gs_ctx* ctx, const void* d_points, size_t stride, const long long* 
     if (stride == 16 && (reinterpret_cast<uintptr_t>(d_points) & 15) == 0 && fused_supported(ctx->fused) && max_points <= fused_max_points()) {
         const Launch L = launch_of(ctx);
         const int rc = fused_run(ctx->fused, L, static_cast<const float4*>(d_points), d_offsets, frames, max_points, range_out, angle_out, res_out,
-                                 reinterpret_cast<float4*>(xyz_out), counts_out, ctx->d_cnt, (ctx->collect_stats ? 1 : 0) | (ctx->phase_timing ? 2 : 0) | (getenv("GS_DEBUG_UF") ? atoi(getenv("GS_DEBUG_UF")) : 0));
+                                 reinterpret_cast<float4*>(xyz_out), counts_out, ctx->d_cnt, (ctx->collect_stats ? 1 : 0) | (ctx->phase_timing ? 2 : 0));
         if (rc) return fail(ctx, GS_ECUDA, "fused kernel launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(rc)));
         return GS_OK;
     }
@@ -580,7 +580,7 @@ int gs_get_phase_cycles(gs_ctx* ctx, uint64_t* out16) {
     const int rc = fetch_counters(ctx);
     if (rc) return rc;
     for (int k = 0; k < 16; ++k) out16[k] = ctx->h_cnt->phase[k];
-    if (getenv("GS_DEBUG_UF")) fprintf(stderr, "uf debug: [16] %llu [17] %llu [18] %llu [19] %llu\n", ctx->h_cnt->phase[16], ctx->h_cnt->phase[17], ctx->h_cnt->phase[18], ctx->h_cnt->phase[19]);
+
     return GS_OK;
 }
 

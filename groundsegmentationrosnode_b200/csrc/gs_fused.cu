@@ -139,10 +139,9 @@ __device__ __forceinline__ void cas_max_u16(uint16_t* p, unsigned v) {
 // where the simultaneous unions of neighbouring columns build a chain as long as the slab is wide — its expected height
 // is logarithmic (randomised linking); finds halve the paths they walk.
 __device__ __forceinline__ unsigned uf16_prio(int x) { return (static_cast<unsigned>(x) * 40503u) & 0xffffu; }  // odd multiplier: bijective mod 2^16
-__device__ __forceinline__ int uf16_find(volatile uint16_t* par, int x, unsigned* hops = nullptr) {
+__device__ __forceinline__ int uf16_find(volatile uint16_t* par, int x) {
     // path halving: only non-root entries are rewritten (plain 16-bit stores), roots change through atomicCAS / atomicOr only
     for (;;) {
-        if (hops) ++*hops;
         const int p = par[x] & 0x7fff;
         if (p == x) return x;
         const int gp = par[p] & 0x7fff;
@@ -151,11 +150,10 @@ __device__ __forceinline__ int uf16_find(volatile uint16_t* par, int x, unsigned
         x = gp;
     }
 }
-__device__ __forceinline__ void uf16_unite(uint16_t* par, int a, int b, unsigned* dbg = nullptr) {
+__device__ __forceinline__ void uf16_unite(uint16_t* par, int a, int b) {
     for (;;) {
-        if (dbg) ++dbg[1];
-        a = uf16_find(par, a, dbg ? dbg + 2 : nullptr);
-        b = uf16_find(par, b, dbg ? dbg + 2 : nullptr);
+        a = uf16_find(par, a);
+        b = uf16_find(par, b);
         if (a == b) return;
         if (uf16_prio(a) > uf16_prio(b)) { const int t = a; a = b; b = t; }  // a: lower priority, hangs under b
         unsigned* w = reinterpret_cast<unsigned*>(par) + (a >> 1);
@@ -509,7 +507,6 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
     // phase timing (GS_OPT_COLLECT_STATS): thread 0 of every CTA accumulates clock64() deltas per phase
     long long t_mark = 0;
     int t_phase = 0;
-    unsigned dbg_cnt[3] = {0, 0, 0};  // unions requested, unite loop iterations, find hops
 #define GS_PHASE(next)                                                        \
     do {                                                                      \
         if ((A.stats & 2) && tid == 0) {                                      \
@@ -915,15 +912,28 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         }
         GS_PHASE(14);
         {
-            // one balanced pass over all links in level order: thread t takes the tasks [t * per, (t + 1) * per)
-            const int t1 = s_excl[n_q];
-            if (t1 > 0) {
-                const int per = (t1 + NT - 1) / NT;
-                int task = tid * per;
-                const int task_end = min(task + per, t1);
+            // Balanced passes over the links in level order: in a pass thread t takes the tasks [ta + t*per, ta + (t+1)*per).
+            // The low levels (94 % of the links, small trees) go first; the few links of the high levels, which join the
+            // big components and walk the deepest trees, are spread over all threads in passes of their own so that no
+            // thread gets a long serial chain of slow finds.
+            int q_cut[4];
+            {
+                int q = 0, k = 0;
+                for (; k < min(4, n_levels); ++k) q += level_count(k) * NWD;
+                q_cut[0] = 0;
+                q_cut[1] = q;
+                for (; k < min(6, n_levels); ++k) q += level_count(k) * NWD;
+                q_cut[2] = q;
+                q_cut[3] = n_q;
+            }
+            for (int pass = 0; pass < 3; ++pass) {
+                const int ta = s_excl[q_cut[pass]], tb = s_excl[q_cut[pass + 1]];
+                if (tb <= ta) continue;  // uniform
+                const int per = (tb - ta + NT - 1) / NT;
+                int task = ta + tid * per;
+                const int task_end = min(task + per, tb);
                 if (task < task_end) {
-                    const long long dbg_t0 = (A.stats & 8) ? clock64() : 0;
-                    int ql = 0, qh = n_q - 1;  // largest q with s_excl[q] <= task
+                    int ql = q_cut[pass], qh = q_cut[pass + 1] - 1;  // largest q of the pass with s_excl[q] <= task
                     while (ql < qh) {
                         const int mid = (ql + qh + 1) >> 1;
                         if (static_cast<int>(s_excl[mid]) <= task) ql = mid;
@@ -949,19 +959,11 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                         unsigned ma = MW(MK_S, w, c) & below, mb = MW(MK_S, w, c + 1) & below;
                         while (ma == 0u) ma = MW(MK_S, --wa, c);
                         while (mb == 0u) mb = MW(MK_S, --wb, c + 1);
-                        if (A.stats & 4) ++dbg_cnt[0];
-                        uf16_unite(s_par, run_node(c, 32 * wa + 31 - __clz(ma)), run_node(c + 1, 32 * wb + 31 - __clz(mb)), (A.stats & 4) ? dbg_cnt : nullptr);
-                    }
-                    if (A.stats & 8) {
-                        const unsigned long long dt = static_cast<unsigned long long>(clock64() - dbg_t0);
-                        atomicAdd(&A.cnt->phase[16], dt);
-                        atomicMax(&A.cnt->phase[17], dt);
-                        atomicAdd(&A.cnt->phase[18], static_cast<unsigned long long>(per));
-                        atomicAdd(&A.cnt->phase[19], 1ull);
+                        uf16_unite(s_par, run_node(c, 32 * wa + 31 - __clz(ma)), run_node(c + 1, 32 * wb + 31 - __clz(mb)));
                     }
                 }
+                __syncthreads();
             }
-            __syncthreads();
         }
         GS_PHASE(15);
         for (int u = tid; u < n_units; u += NT) {
@@ -1199,11 +1201,6 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         if (st_remote) atomicAdd(&A.cnt->remote, st_remote);
         if (st_fallback) atomicAdd(&A.cnt->slow_path, st_fallback);
         if (st_mismatch) atomicAdd(&A.cnt->fast_mismatch, st_mismatch);
-    }
-    if (A.stats & 2) {
-        if (dbg_cnt[0]) atomicAdd(&A.cnt->phase[16], static_cast<unsigned long long>(dbg_cnt[0]));
-        if (dbg_cnt[1]) atomicAdd(&A.cnt->phase[17], static_cast<unsigned long long>(dbg_cnt[1]));
-        if (dbg_cnt[2]) atomicAdd(&A.cnt->phase[18], static_cast<unsigned long long>(dbg_cnt[2]));
     }
     cluster.sync();  // no CTA exits while a neighbour may still address its shared memory
 }

@@ -49,13 +49,20 @@ hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 hdr = rows[hi]
 body = [dict(zip(hdr, r)) for r in rows[hi + 1:] if len(r) == len(hdr)]
 lines = T.sass_lines("k_frameILi1")
-agg = collections.defaultdict(lambda: [0, 0])
+STALLS = ["stall_barrier", "stall_short_sb", "stall_wait", "stall_long_sb", "stall_not_selected", "stall_branch_resolving", "stall_math", "stall_mio"]
+agg = collections.defaultdict(lambda: [0, 0] + [0] * len(STALLS))
 for d, l in zip(body, lines):
     b = bucket(l)
     agg[b][0] += int(d["Instructions Executed"] or 0)
     agg[b][1] += int(d["# Samples"] or 0)
+    for k, st in enumerate(STALLS):
+        agg[b][2 + k] += int(d.get(st) or 0)
 ti = sum(v[0] for v in agg.values())
 ts = sum(v[1] for v in agg.values())
 print("total %.2f M warp-instructions per frame" % (ti / frames / 1e6))
+print("%-28s %-26s %-9s | share of all samples by stall reason: %s" % ("phase", "instructions", "samples", " ".join(x.replace("stall_", "")[:8] for x in STALLS)))
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    print("%-28s inst %5.1f%% (%7.1fk/frame)   samples %5.1f%%" % (k, 100 * v[0] / ti, v[0] / frames / 1e3, 100 * v[1] / ts))
+    if v[1] * 200 < ts:
+        continue
+    print("%-28s inst %5.1f%% (%7.1fk/frame)   samples %5.1f%% | %s" % (k, 100 * v[0] / ti, v[0] / frames / 1e3, 100 * v[1] / ts,
+                                                                     " ".join("%8.1f" % (100.0 * x / ts) for x in v[2:])))
