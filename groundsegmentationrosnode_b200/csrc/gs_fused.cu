@@ -80,6 +80,7 @@ struct FusedArgs {
     unsigned ng_magic;         // ceil(2^32 / NG)
     const KParams* kp_dev;     // device-memory copy of kp for the out-of-line exact path
     int col_limit, col_wrap;   // largest column the fast path may return; GS_COL_WRAP
+    double range_lo_in, range_hi_in, range_lo_out, range_hi_out;  // range gates -/+ 1e-9 m
     int use_fast;
 };
 
@@ -358,8 +359,19 @@ __device__ __noinline__ Proj project_point_d(const KParams* __restrict__ kpp, fl
 __device__ __forceinline__ int project_fast(const FusedArgs& A, float fx, float fy, float fz, int* row_out, int* col_out, unsigned* enc_out) {
     const KParams& kp = A.kp;
     const double x = fx, y = fy, z = fz;
-    const double range = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));  // utils.h:41-43
-    if (!(range >= kp.min_range && range <= kp.max_range)) return isfinite(range) ? 1 : 2;  // alfa_gs.cpp:261 (non-finite: exact path decides)
+    // range = sqrt(x*x + y*y + z*z) to ~5e-16 relative (the reference's value, utils.h:41-43, differs from it by rounding
+    // only): fused sum of squares, float rsqrt seed, two Newton steps in double.  11 FP64 operations instead of the ~28 of
+    // three products, two sums and a correctly rounded square root; every decision taken on it keeps a 1e-9 m margin.
+    const double s2 = __fma_rn(x, x, __fma_rn(y, y, __dmul_rn(z, z)));
+    double rs = static_cast<double>(rsqrtf(static_cast<float>(s2)));
+    const double hs = __dmul_rn(0.5, s2);
+    rs = __dmul_rn(rs, __fma_rn(-__dmul_rn(hs, rs), rs, 1.5));
+    rs = __dmul_rn(rs, __fma_rn(-__dmul_rn(hs, rs), rs, 1.5));
+    const double range = __dmul_rn(s2, rs);
+    if (!(range > A.range_lo_in && range < A.range_hi_in)) {            // alfa_gs.cpp:261
+        if (range < A.range_lo_out || range > A.range_hi_out) return 1;  // certainly outside the gates
+        return 2;                                                        // within 1e-9 m of a gate, zero or not finite: exact path
+    }
     const double u = __fma_rn(__dsub_rn(range, kp.min_range), A.enc_scale, 1.0);
     const int e = __double2int_rz(u);
     const double uf = u - static_cast<double>(e);
@@ -571,9 +583,11 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         GS_PHASE(1);
         // ================================================================================ P1: projection + pixel ownership
         // "The last point in input order wins" (alfa_gs.cpp:291) as ONE 32-bit shared-memory atomicMax per point on the
-        // key (g << 16 | range), g = index / 32 + 1: a later group of 32 points always beats an earlier one and carries
-        // its range along; inside a group (= a warp) __match_any_sync keeps the highest lane.  No barriers, no rounds.
+        // key (g << 16 | range), g = (index >> tag_shift) + 1: a later point always beats an earlier one and carries its
+        // range along; points with the same tag sit in adjacent lanes and are resolved with shuffles.  No barriers.
         unsigned* s_key = reinterpret_cast<unsigned*>(s_range);  // [H][S16] u32 over the range + tag slabs, compacted to u16 below
+        int tag_shift = 0;  // order tag = index >> tag_shift, the smallest shift that fits 16 bits (uniform per frame)
+        while ((((N - 1) >> tag_shift) + 1) > 65535) ++tag_shift;
         for (int qb = 0; qb < nmine * BLK; qb += NT * NPT) {
             float4 cur_p[NPT];
             int cur_i[NPT];
@@ -622,12 +636,17 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                         const int owner = min(static_cast<int>(__umulhi(static_cast<unsigned>(col), A.cw_magic)), CL - 1);
                         const int lc = col - owner * CW;
                         k = (static_cast<unsigned>(owner) << 16) | static_cast<unsigned>(row * S16 + lc);
-                        val = ((static_cast<unsigned>(i >> 5) + 1u) << 16) | enc;
+                        val = ((static_cast<unsigned>(i >> tag_shift) + 1u) << 16) | enc;
                     }
                 }
-                // the highest lane among the lanes that hit the same pixel holds the latest point of this group
-                const unsigned peers = __match_any_sync(0xffffffffu, k);
-                const bool winner = !(k & 0x80000000u) && (31 - __clz(peers)) == lane;
+                // points that share an order tag are 2^tag_shift consecutive lanes: the highest lane among those that hit the
+                // same pixel holds the latest point (xor-shuffles over the group; __match_any_sync would do the same for a
+                // whole warp but costs ~100 cycles of the address-divergence unit per call when all keys differ)
+                bool winner = !(k & 0x80000000u);
+                for (int d = 1; d < (1 << tag_shift); ++d) {
+                    const unsigned other = __shfl_xor_sync(0xffffffffu, k, d);
+                    if (other == k && (lane ^ d) > lane) winner = false;
+                }
                 const bool local = winner && static_cast<int>(k >> 16) == rank;
                 if (local) atomicMax(s_key + (k & 0xffffu), val);
                 // remote pixels: queue the record (warp-aggregated slot claim)
@@ -1425,6 +1444,10 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
         a.ng_magic = static_cast<unsigned>((0x100000000ull + lay.NG - 1) / lay.NG);
         a.kp_dev = static_cast<const KParams*>(fs.d_const);
         a.col_limit = c2r ? kp.W - 1 : kp.W;
+        a.range_lo_in = kp.min_range + 1e-9;
+        a.range_hi_in = kp.max_range - 1e-9;
+        a.range_lo_out = kp.min_range - 1e-9;
+        a.range_hi_out = kp.max_range + 1e-9;
         a.col_wrap = (!c2r && kp.col_policy == GS_COL_WRAP) ? 1 : 0;
         // the fixed-point coordinates need 4 * quarter_fix < 2^31 and |altitude cells| * 2^FB < 2^31
         a.use_fast = (kp.W <= 8191 && alt_scale * 1.6 * two_fb < 2.0e9 && std::fabs(row0) * two_fb < 2.0e9 &&
