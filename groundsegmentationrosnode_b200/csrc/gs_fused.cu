@@ -685,12 +685,15 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         // compact the keys to the u16 range slab in place (the low half of every key is the winner's range); the freed
         // upper part (the tag slab) becomes the union-find forest later
         {
-            const int n_px = H * S16;
-            for (int base = 0; base < n_px; base += NT) {
+            const int n_quads = (H * S16) >> 2;  // H is a power of two >= 16 and S16 is even: the slab is a whole number of quads
+            const uint4* k4 = reinterpret_cast<const uint4*>(s_key);
+            uint2* r2 = reinterpret_cast<uint2*>(s_range);
+            for (int base = 0; base < n_quads; base += NT) {
                 const int i = base + tid;
-                const unsigned v = i < n_px ? s_key[i] : 0u;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (i < n_quads) v = k4[i];
                 __syncthreads();  // every key of this chunk is read before its bytes are overwritten
-                if (i < n_px) s_range[i] = static_cast<uint16_t>(v);
+                if (i < n_quads) r2[i] = make_uint2((v.x & 0xffffu) | (v.y << 16), (v.z & 0xffffu) | (v.w << 16));
             }
             __syncthreads();
         }
@@ -1294,58 +1297,51 @@ int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const Sg
     if (e != cudaSuccess) return static_cast<int>(e);
     e = cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return static_cast<int>(e);
-    Layout lay;
-    bool found = false;
-    for (int CL = 1; CL <= MAX_CL; CL *= 2) {
-        if (layout_for(kp, CL, NW, &lay) && lay.total <= static_cast<size_t>(max_smem)) {
-            found = true;
-            break;
-        }
-    }
-    if (!found) return 0;
-    // Two shapes: 512 threads with two CTAs (two frames) per SM, which overlaps one frame's barriers and serial phases
-    // with the other's work, when a slab fits half an SM's shared memory; else 1024 threads with one CTA per SM.
+    // Pick the cluster size (1..8 CTAs per frame, not only powers of two) that keeps the most SMs busy: clusters are placed
+    // inside one GPC, so e.g. clusters of 4 strand 16 of a B200's 148 SMs while clusters of 6 strand 4.  Ties go to the
+    // smaller cluster (fewer cross-CTA exchanges).  GS_FUSED_CLUSTER=n forces a size, GS_FUSED_THREADS=512 the two-CTAs-per-SM shape.
     int max_smem_sm = 0;
     e = cudaDeviceGetAttribute(&max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
     if (e != cudaSuccess) return static_cast<int>(e);
-    int nt = 1024;
-    {
-        const char* mode = getenv("GS_FUSED_THREADS");  // "512" / "1024" forces a shape (experiments)
-        const size_t half = static_cast<size_t>(max_smem_sm) / 2 - 1024;  // 1 KB per CTA is reserved by the system
-        Layout l2;
-        bool found2 = false;
-        for (int CL = 1; CL <= MAX_CL; CL *= 2)
-            if (layout_for(kp, CL, NW, &l2) && l2.total <= half) { found2 = true; break; }
-        const bool want2 = mode ? atoi(mode) == 512 : false;  // measured equal on B200 (the kernel is not latency-bound per CTA); 1024 x 1 is the default
-        if (found2 && want2) {
-            lay = l2;
-            nt = 512;
-        }
-    }
+    const char* mode = getenv("GS_FUSED_THREADS");
+    const char* force_cl = getenv("GS_FUSED_CLUSTER");
+    const int nt = (mode && atoi(mode) == 512) ? 512 : 1024;
+    const size_t smem_cap = nt == 512 ? static_cast<size_t>(max_smem_sm) / 2 - 1024 : static_cast<size_t>(max_smem);
     const void* kern = nt == 512 ? (NW == 1 ? reinterpret_cast<const void*>(k_frame<1, 512>) : reinterpret_cast<const void*>(k_frame<2, 512>))
                                  : (NW == 1 ? reinterpret_cast<const void*>(k_frame<1, 1024>) : reinterpret_cast<const void*>(k_frame<2, 1024>));
     // the attribute is per function, not per context: always ask for the device maximum
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e != cudaSuccess) return static_cast<int>(e);
-    // how many clusters can be co-resident
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>((nt == 512 ? 2 : 1) * n_sms / lay.CL * lay.CL));
-    cfg.blockDim = dim3(nt);
-    cfg.dynamicSmemBytes = lay.total;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = static_cast<unsigned>(lay.CL);
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    int max_clusters = 0;
-    e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        return 0;  // clusters of this size cannot be scheduled here: staged kernels
+    Layout lay;
+    int max_clusters = 0, best_sms = 0;
+    for (int CL = 1; CL <= MAX_CL; ++CL) {
+        if (force_cl && atoi(force_cl) != CL) continue;
+        Layout l;
+        if (!layout_for(kp, CL, NW, &l) || l.total > smem_cap) continue;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(static_cast<unsigned>((nt == 512 ? 2 : 1) * n_sms / CL * CL));
+        cfg.blockDim = dim3(nt);
+        cfg.dynamicSmemBytes = l.total;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = static_cast<unsigned>(CL);
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        if (getenv("GS_DEBUG_PLAN")) fprintf(stderr, "gs fused candidate: cluster %d, %d columns per CTA, %zu B smem, %d co-resident clusters = %d CTAs\n", CL, l.CW, l.total, n, n * CL);
+        if (n * CL > best_sms) {
+            best_sms = n * CL;
+            max_clusters = n;
+            lay = l;
+        }
     }
-    if (max_clusters < 1) return 0;
+    if (max_clusters < 1) return 0;  // no cluster shape fits here: staged kernels
     if (getenv("GS_DEBUG_PLAN")) fprintf(stderr, "gs fused plan: %d x %d image, %d threads, cluster %d, %d columns per CTA, %zu B smem, %d co-resident clusters on %d SMs\n",
                                          kp.H, kp.W, nt, lay.CL, lay.CW, lay.total, max_clusters, n_sms);
     fs.cluster = lay.CL;
