@@ -81,6 +81,8 @@ struct FusedArgs {
     const KParams* kp_dev;     // device-memory copy of kp for the out-of-line exact path
     int col_limit, col_wrap;   // largest column the fast path may return; GS_COL_WRAP
     double range_lo_in, range_hi_in, range_lo_out, range_hi_out;  // range gates -/+ 1e-9 m
+    float sg_t[11];            // Savitzky-Golay taps (cloud2range_node.cpp:470), sg_ws = 0: no smoothing
+    int sg_ws;
     int use_fast;
 };
 
@@ -785,6 +787,30 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             }
         }
         __syncthreads();
+        if (A.sg_ws > 0) {
+            // Alfa_GS::SavitskyGolaySmoothing (alfa_gs.cpp:705-713) = cv::filter2D with a ws x 1 kernel and BORDER_REFLECT101:
+            // float32 accumulation in tap order, round half to even, saturate (pinned against OpenCV in tests/golden).
+            // Smoothed angles stay below 256 (157 x the positive tap sum 1.19).  Filter into the (idle) tag slab, copy back.
+            uint8_t* tmp = reinterpret_cast<uint8_t*>(s_tag);
+            const int half = A.sg_ws >> 1;
+            for (int i = tid; i < H * myCW; i += NT) {
+                const int r = i / myCW, c = i - r * myCW;
+                float acc = 0.0f;
+                for (int k = 0; k < A.sg_ws; ++k) {
+                    int rr = r + k - half;
+                    while (rr < 0 || rr >= H) rr = rr < 0 ? -rr : 2 * H - 2 - rr;
+                    acc = __fadd_rn(acc, __fmul_rn(A.sg_t[k], static_cast<float>(s_angle[rr * S8 + c])));
+                }
+                const int v = __float2int_rn(acc);
+                tmp[r * S8 + c] = static_cast<uint8_t>(max(0, min(255, v)));
+            }
+            __syncthreads();
+            for (int i = tid; i < H * myCW; i += NT) {
+                const int r = i / myCW, c = i - r * myCW;
+                s_angle[r * S8 + c] = tmp[r * S8 + c];
+            }
+            __syncthreads();
+        }
         if (A.angle_out) {
             uint16_t* out = A.angle_out + static_cast<size_t>(f) * kp.P;
             for (int i = tid; i < H * myCW; i += NT) {
@@ -1288,7 +1314,7 @@ int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const Sg
     fs.repair = repair;
     fs.configured = false;
     // what the fused kernel covers; everything else runs on the staged kernels
-    if (smooth || repair) return 0;
+    if (repair) return 0;  // RepairGaps (N2) runs on the staged kernels
     if (kp.pixel_policy != GS_PIXEL_LAST) return 0;
     if (kp.H > MAX_H || kp.W < 2 || (kp.H & (kp.H - 1)) != 0) return 0;  // beam counts that are powers of two (16 / 32 / 64 / 128)
     const int NW = kp.H <= 64 ? 1 : 2;
@@ -1440,6 +1466,8 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
         a.ng_magic = static_cast<unsigned>((0x100000000ull + lay.NG - 1) / lay.NG);
         a.kp_dev = static_cast<const KParams*>(fs.d_const);
         a.col_limit = c2r ? kp.W - 1 : kp.W;
+        a.sg_ws = fs.smooth ? fs.sg.ws : 0;
+        for (int k = 0; k < 11; ++k) a.sg_t[k] = fs.sg.t[k];
         a.range_lo_in = kp.min_range + 1e-9;
         a.range_hi_in = kp.max_range - 1e-9;
         a.range_lo_out = kp.min_range - 1e-9;

@@ -78,8 +78,11 @@ def test_full_pipeline_matches_oracle(ctxs, oracle, name, staged):
         pts = synth.make_frame(p, synth.SEED0 + seed, shuffle=(seed == 1))
         want = oracle.process_frame(p, pts)
         ctx.reset_stats()
+        launches0 = ctx.stats().kernel_launches
         got = ctx.process_frame(pts)
         st = ctx.stats()
+        # every preset here is one the fused kernel covers: the whole frame is ONE launch; the staged path is 9-10
+        assert (st.kernel_launches - launches0 == 1) == (not staged)
         _, ne_p, _ = oracle.create_range_image(p, pts, with_counts=True)
         assert st.near_edge_project == ne_p
         # with statistics on, the fused kernel evaluates the exact arithmetic beside every fast result it accepts
