@@ -24,7 +24,8 @@ EXPORTS = [
     "gs_get_derived", "gs_set_stream", "gs_set_chunk_frames", "gs_set_option", "gs_get_stats", "gs_reset_stats", "gs_get_phase_cycles",
     "gs_last_error", "gs_project", "gs_angle_image", "gs_smooth", "gs_repair_gaps", "gs_erase_ground",
     "gs_label_one_component", "gs_label_components", "gs_backproject", "gs_process_frame", "gs_process_batch_device",
-    "gs_process_batch_host", "gs_synchronize",
+    "gs_process_batch_host", "gs_synchronize", "gs_unpack_points", "gs_process_cloud2", "gs_pack_cloud_xyzrgb",
+    "gs_get_camera_info",
 ]
 
 
@@ -81,6 +82,11 @@ def load(build_if_missing=False):
     L.gs_process_batch_device.argtypes = [C.c_void_p, vp, i64p, C.c_int, vp, vp, vp, vp, vp]
     L.gs_process_batch_host.argtypes = [C.c_void_p, vp, i64p, C.c_int, vp, vp, C.c_uint64, i64p]
     L.gs_synchronize.argtypes = [C.c_void_p]
+    L.gs_unpack_points.argtypes = [C.c_void_p, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_int, f32p]
+    L.gs_process_cloud2.argtypes = [C.c_void_p, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u16p, u16p, u16p, f32p,
+                                    C.POINTER(C.c_uint32)]
+    L.gs_pack_cloud_xyzrgb.argtypes = [C.c_void_p, f32p, C.c_uint32, vp]
+    L.gs_get_camera_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -255,6 +261,38 @@ class Context:
         self._ck(self._L.gs_process_frame(self._h, _ptr(pts), pts.shape[0], pts.strides[0] if pts.shape[0] else 16, _ptr(rng),
                                           _ptr(ang), _ptr(res), _ptr(xyz), C.byref(n)))
         return dict(range=rng, angle=ang, no_ground=res, xyz=xyz[: n.value].copy())
+
+    # ---- wire formats (N1)
+    def unpack_points(self, data, point_step, off_x, off_y, off_z, off_intensity=-1, big_endian=False):
+        """PointCloud2-style byte buffer -> (n, 4) float32 {x, y, z, intensity}"""
+        raw = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+        n = raw.shape[0] // point_step
+        out = np.empty((n, 4), np.float32)
+        self._ck(self._L.gs_unpack_points(self._h, _ptr(raw), n, point_step, off_x, off_y, off_z, off_intensity, int(big_endian), _ptr(out)))
+        return out
+
+    def process_cloud2(self, data, point_step, off_x, off_y, off_z, big_endian=False):
+        H, W = self.shape
+        raw = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+        n_pts = raw.shape[0] // point_step
+        rng, ang, res = (np.empty((H, W), np.uint16) for _ in range(3))
+        xyz = np.empty((H * W, 4), np.float32)
+        n = C.c_uint32(0)
+        self._ck(self._L.gs_process_cloud2(self._h, _ptr(raw), n_pts, point_step, off_x, off_y, off_z, int(big_endian), _ptr(rng), _ptr(ang),
+                                           _ptr(res), _ptr(xyz), C.byref(n)))
+        return dict(range=rng, angle=ang, no_ground=res, xyz=xyz[: n.value].copy())
+
+    def pack_cloud_xyzrgb(self, xyz4):
+        a = np.ascontiguousarray(xyz4, dtype=np.float32)
+        out = np.zeros((a.shape[0], 32), np.uint8)
+        self._ck(self._L.gs_pack_cloud_xyzrgb(self._h, _ptr(a), a.shape[0], _ptr(out)))
+        return out
+
+    def camera_info(self):
+        h, w = C.c_int32(0), C.c_int32(0)
+        K = (C.c_double * 9)()
+        self._ck(self._L.gs_get_camera_info(self._h, C.byref(h), C.byref(w), K))
+        return h.value, w.value, [float(x) for x in K]
 
     # ---- batch API
     def process_batch_device(self, d_points, h_offsets, n_frames, d_range=0, d_angle=0, d_no_ground=0, d_xyz4=0, d_counts=0):

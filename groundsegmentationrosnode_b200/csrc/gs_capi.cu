@@ -761,6 +761,10 @@ int gs_backproject(gs_ctx* ctx, const uint16_t* image, float* xyz4_out, uint32_t
 int gs_process_frame(gs_ctx* ctx, const void* points, size_t n_points, size_t stride_bytes, uint16_t* range_out,
                      uint16_t* angle_out, uint16_t* no_ground_out, float* xyz4_out, uint32_t* n_out) {
     if (!ctx || (n_points && !points) || stride_bytes < 12 || (stride_bytes & 3)) return fail(ctx, GS_EINVAL, "gs_process_frame: bad arguments");
+    // records wider than 16 bytes (pcl::PointXYZRGB, alfa_gs.h:25) are repacked on the device and take the same fused kernel
+    if (stride_bytes != 16)
+        return gs_process_cloud2(ctx, points, n_points, static_cast<uint32_t>(stride_bytes), 0, 4, 8, 0, range_out, angle_out, no_ground_out,
+                                 xyz4_out, n_out);
     cudaSetDevice(ctx->device);
     int rc;
     if ((rc = ensure_stage(ctx)) || (rc = ensure_points(ctx, n_points * stride_bytes)) || (rc = ensure_offsets(ctx, 2))) return rc;
@@ -784,6 +788,95 @@ int gs_process_frame(gs_ctx* ctx, const void* points, size_t n_points, size_t st
         CU(cudaStreamSynchronize(ctx->stream));
     }
     if (n_out) *n_out = n;
+    return GS_OK;
+}
+
+// ---- wire formats (N1) -------------------------------------------------------------------------
+namespace {
+// device-side unpack of a PointCloud2-style host buffer into ctx->d_points as packed float4 (staging behind it)
+int unpack_to_device(gs_ctx* ctx, const void* data, size_t n, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz, int32_t oi, int big_endian) {
+    const size_t raw = n * static_cast<size_t>(step), packed = n * 16;
+    const size_t raw_off = (packed + 255) & ~static_cast<size_t>(255);
+    int rc;
+    if ((rc = ensure_points(ctx, raw_off + raw))) return rc;
+    unsigned char* base = static_cast<unsigned char*>(ctx->d_points);
+    if (n) CU(cudaMemcpyAsync(base + raw_off, data, raw, cudaMemcpyHostToDevice, ctx->stream));
+    launch_unpack_points(launch_of(ctx), base + raw_off, n, step, ox, oy, oz, oi, big_endian, reinterpret_cast<float*>(base));
+    CU(cudaGetLastError());
+    return GS_OK;
+}
+bool bad_fields(size_t n, const void* data, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz, int32_t oi) {
+    if (n && !data) return true;
+    if (step < 12) return true;
+    if (ox + 4 > step || oy + 4 > step || oz + 4 > step) return true;
+    if (oi >= 0 && static_cast<uint32_t>(oi) + 4 > step) return true;
+    return false;
+}
+}  // namespace
+
+int gs_unpack_points(gs_ctx* ctx, const void* data, size_t n_points, uint32_t point_step, uint32_t off_x, uint32_t off_y, uint32_t off_z,
+                     int32_t off_intensity, int is_bigendian, float* xyzi_out) {
+    if (!ctx || !xyzi_out || bad_fields(n_points, data, point_step, off_x, off_y, off_z, off_intensity)) return fail(ctx, GS_EINVAL, "gs_unpack_points: bad arguments");
+    cudaSetDevice(ctx->device);
+    int rc;
+    if ((rc = unpack_to_device(ctx, data, n_points, point_step, off_x, off_y, off_z, off_intensity, is_bigendian))) return rc;
+    if (n_points) CU(cudaMemcpyAsync(xyzi_out, ctx->d_points, n_points * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GS_OK;
+}
+
+int gs_process_cloud2(gs_ctx* ctx, const void* data, size_t n_points, uint32_t point_step, uint32_t off_x, uint32_t off_y, uint32_t off_z,
+                      int is_bigendian, uint16_t* range_out, uint16_t* angle_out, uint16_t* no_ground_out, float* xyz4_out, uint32_t* n_out) {
+    if (!ctx || bad_fields(n_points, data, point_step, off_x, off_y, off_z, -1)) return fail(ctx, GS_EINVAL, "gs_process_cloud2: bad arguments");
+    cudaSetDevice(ctx->device);
+    int rc;
+    if ((rc = ensure_stage(ctx)) || (rc = ensure_offsets(ctx, 2))) return rc;
+    const KParams& kp = ctx->kp;
+    const size_t bytes = static_cast<size_t>(kp.P) * 2;
+    const long long offs[2] = {0, static_cast<long long>(n_points)};
+    CU(cudaMemcpyAsync(ctx->d_offsets, offs, sizeof(offs), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = unpack_to_device(ctx, data, n_points, point_step, off_x, off_y, off_z, -1, is_bigendian))) return rc;
+    if ((rc = ensure_scratch(ctx, 1))) return rc;
+    if ((rc = run_wave(ctx, ctx->d_points, 16, ctx->d_offsets, 1, static_cast<long long>(n_points), ctx->d_a, ctx->d_b, ctx->d_c, ctx->d_xyz,
+                       ctx->sc.counts)))
+        return rc;
+    if (range_out) CU(cudaMemcpyAsync(range_out, ctx->d_a, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (angle_out) CU(cudaMemcpyAsync(angle_out, ctx->d_b, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (no_ground_out) CU(cudaMemcpyAsync(no_ground_out, ctx->d_c, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned n = 0;
+    CU(cudaMemcpyAsync(&n, ctx->sc.counts, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (xyz4_out && n) {
+        CU(cudaMemcpyAsync(xyz4_out, ctx->d_xyz, static_cast<size_t>(n) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (n_out) *n_out = n;
+    return GS_OK;
+}
+
+int gs_pack_cloud_xyzrgb(gs_ctx* ctx, const float* xyz4, uint32_t n_points, void* out32) {
+    if (!ctx || (n_points && (!xyz4 || !out32))) return fail(ctx, GS_EINVAL, "gs_pack_cloud_xyzrgb: bad arguments");
+    if (n_points == 0) return GS_OK;
+    cudaSetDevice(ctx->device);
+    int rc;
+    const size_t in_bytes = static_cast<size_t>(n_points) * 16, out_off = (in_bytes + 255) & ~static_cast<size_t>(255);
+    if ((rc = ensure_points(ctx, out_off + static_cast<size_t>(n_points) * 32))) return rc;
+    unsigned char* base = static_cast<unsigned char*>(ctx->d_points);
+    CU(cudaMemcpyAsync(base, xyz4, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    launch_pack_xyzrgb(launch_of(ctx), reinterpret_cast<const float*>(base), n_points, base + out_off);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out32, base + out_off, static_cast<size_t>(n_points) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GS_OK;
+}
+
+int gs_get_camera_info(const gs_ctx* ctx, int32_t* height, int32_t* width, double* K9) {
+    if (!ctx || !height || !width || !K9) return GS_EINVAL;
+    *height = ctx->der.n_rows;
+    *width = ctx->der.n_cols;
+    const double k[9] = {ctx->params.min_angle, ctx->params.max_angle, ctx->params.min_range, ctx->params.max_range, ctx->der.d_azimuth,
+                         ctx->der.d_altitude, 0, 0, 0};
+    for (int i = 0; i < 9; ++i) K9[i] = k[i];
     return GS_OK;
 }
 

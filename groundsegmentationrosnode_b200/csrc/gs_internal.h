@@ -66,6 +66,9 @@ struct Launch {
 };
 
 // ---- launchers (gs_kernels.cu).  `frames` slabs are processed per call; arrays are [frames][P] unless noted. ----
+void launch_unpack_points(const Launch& L, const void* data, size_t n, unsigned step, unsigned ox, unsigned oy, unsigned oz, int oi, int big_endian,
+                          float* xyzi_out);
+void launch_pack_xyzrgb(const Launch& L, const float* xyz4, unsigned n, void* out);
 void launch_project(const Launch& L, const KParams& kp, const void* points, size_t stride, const long long* d_offsets,
                     int frames, long long max_points, unsigned long long* keys, Counters* cnt, bool stats);
 void launch_finalize(const Launch& L, const KParams& kp, int frames, unsigned long long* keys, uint16_t* range);

@@ -526,11 +526,62 @@ __global__ void __launch_bounds__(256) k_backproject(const uint16_t* __restrict_
     if (r == kp.H - 1 && threadIdx.x == 0) counts[f] = running;
 }
 
+// ------------------------------------------------------------------------------------------------
+// N1 — wire formats either side of the path.  sensor_msgs/PointCloud2 carries points as `point_step`-byte records with
+// float32 fields at arbitrary offsets (pcl::fromROSMsg, alfa_node.cpp:311); the pipeline wants packed 16-byte XYZI.
+// The cloud going out (pcl::toROSMsg, alfa_node.cpp:35-41) is PointXYZ (= our {x,y,z,1} records) or PointXYZRGB (32 bytes).
+// Both are pure bandwidth kernels.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float load_f32(const unsigned char* p, bool aligned, bool swap) {
+    unsigned v;
+    if (aligned) v = *reinterpret_cast<const unsigned*>(p);
+    else v = static_cast<unsigned>(p[0]) | (static_cast<unsigned>(p[1]) << 8) | (static_cast<unsigned>(p[2]) << 16) | (static_cast<unsigned>(p[3]) << 24);
+    if (swap) v = __byte_perm(v, 0, 0x0123);
+    return __uint_as_float(v);
+}
+
+__global__ void __launch_bounds__(256) k_unpack_points(const unsigned char* __restrict__ data, size_t n, unsigned step, unsigned ox, unsigned oy,
+                                                       unsigned oz, int oi, int big_endian, float4* __restrict__ out) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned char* p = data + i * step;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(data) | step | ox | oy | oz | (oi >= 0 ? static_cast<unsigned>(oi) : 0u)) & 3u) == 0;
+    float4 q;
+    q.x = load_f32(p + ox, aligned, big_endian != 0);
+    q.y = load_f32(p + oy, aligned, big_endian != 0);
+    q.z = load_f32(p + oz, aligned, big_endian != 0);
+    q.w = oi >= 0 ? load_f32(p + oi, aligned, big_endian != 0) : 0.0f;
+    out[i] = q;
+}
+
+// {x, y, z, 1} -> pcl::PointXYZRGB: x y z 1.0 | b g r a = 0 0 0 255 | 12 bytes of padding   (CameraCb's points, alfa_gs.cpp:1055-1058)
+__global__ void __launch_bounds__(256) k_pack_xyzrgb(const float4* __restrict__ xyz4, unsigned n, uint4* __restrict__ out) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 q = xyz4[i];
+    out[2 * i] = make_uint4(__float_as_uint(q.x), __float_as_uint(q.y), __float_as_uint(q.z), __float_as_uint(1.0f));
+    out[2 * i + 1] = make_uint4(0xff000000u, 0u, 0u, 0u);
+}
+
 inline dim3 pixel_grid(const KParams& kp, int frames) { return dim3((kp.P + 255) / 256, frames); }
 
 }  // namespace
 
 #define GS_COUNT(L) (++*(L).n_launches)
+
+void launch_unpack_points(const Launch& L, const void* data, size_t n, unsigned step, unsigned ox, unsigned oy, unsigned oz, int oi, int big_endian,
+                          float* xyzi_out) {
+    if (n == 0) return;
+    k_unpack_points<<<static_cast<unsigned>((n + 255) / 256), 256, 0, L.stream>>>(static_cast<const unsigned char*>(data), n, step, ox, oy, oz, oi,
+                                                                                 big_endian, reinterpret_cast<float4*>(xyzi_out));
+    GS_COUNT(L);
+}
+
+void launch_pack_xyzrgb(const Launch& L, const float* xyz4, unsigned n, void* out) {
+    if (n == 0) return;
+    k_pack_xyzrgb<<<(n + 255) / 256, 256, 0, L.stream>>>(reinterpret_cast<const float4*>(xyz4), n, static_cast<uint4*>(out));
+    GS_COUNT(L);
+}
 
 void launch_project(const Launch& L, const KParams& kp, const void* points, size_t stride, const long long* d_offsets, int frames,
                     long long max_points, unsigned long long* keys, Counters* cnt, bool stats) {

@@ -189,6 +189,25 @@ int gs_process_frame(gs_ctx* ctx, const void* points, size_t n_points, size_t st
                      uint16_t* range_out, uint16_t* angle_out, uint16_t* no_ground_out,
                      float* xyz4_out, uint32_t* n_out);
 
+/* ---- wire formats either side of the path ----------------------------------- */
+/* sensor_msgs/PointCloud2 -> packed {x, y, z, intensity} float records: what pcl::fromROSMsg does for the node
+ * (alfa_node.cpp:311).  data: n_points records of point_step bytes with float32 fields at the given byte offsets
+ * (off_intensity < 0: none, 0 is stored).  HOST buffers. */
+int gs_unpack_points(gs_ctx* ctx, const void* data, size_t n_points, uint32_t point_step, uint32_t off_x,
+                     uint32_t off_y, uint32_t off_z, int32_t off_intensity, int is_bigendian, float* xyzi_out);
+/* the whole path on a PointCloud2-style buffer (fields unpacked on the device, then the fused kernel) */
+int gs_process_cloud2(gs_ctx* ctx, const void* data, size_t n_points, uint32_t point_step, uint32_t off_x,
+                      uint32_t off_y, uint32_t off_z, int is_bigendian, uint16_t* range_out, uint16_t* angle_out,
+                      uint16_t* no_ground_out, float* xyz4_out, uint32_t* n_out);
+/* {x, y, z, 1} records -> 32-byte pcl::PointXYZRGB records (x y z 1.0 | b g r a = 0 0 0 255 | padding), the cloud
+ * Alfa_GS::CameraCb builds for pcl::toROSMsg (alfa_gs.cpp:1055-1058, alfa_node.cpp:35-41).  The {x, y, z, 1} records
+ * themselves are already pcl::PointXYZ (range2cloud_node.cpp:89). */
+int gs_pack_cloud_xyzrgb(gs_ctx* ctx, const float* xyz4, uint32_t n_points, void* out32);
+/* sensor_msgs/CameraInfo fields the nodes publish with the mono16 image (alfa_gs.cpp:55-63, cloud2range_node.cpp:319-328):
+ * K[0..5] = min_angle, max_angle, min_range, max_range, d_azimuth, d_altitude.  The image itself needs no conversion:
+ * the u16 row-major buffers of this API are the mono16 payload (step = 2 * width). */
+int gs_get_camera_info(const gs_ctx* ctx, int32_t* height, int32_t* width, double* K9);
+
 /* ---- batch API: frames are independent (alfa_gs.cpp:196-239 holds no cross-frame state) ---- */
 /* DEVICE buffers.  points: packed 16-byte XYZI records of all frames; offsets (HOST, n_frames+1
  * entries, in points) delimit frames.  no_ground_out: n_frames * P u16;  xyz4_out: n_frames * P

@@ -369,3 +369,42 @@ def test_full_size_properties(ctxs):
     assert bool(((d_res == 0) | (d_res == d_rng)).all())
     n0 = int(d_cnt[0])
     assert bool((d_xyz[0, :n0, 3] == 1.0).all())
+
+
+def test_wire_formats(ctxs, oracle):
+    """N1: PointCloud2-style records with fields at arbitrary offsets in, PointXYZRGB records and
+    CameraInfo out — what pcl::fromROSMsg / pcl::toROSMsg / the CameraInfo block do around the path
+    (alfa_node.cpp:311, :35-41; alfa_gs.cpp:55-63)."""
+    p = P.preset(P.GS_PRESET_HDL64E_2048)
+    ctx = ctxs(p)
+    pts = synth.make_frame(p, synth.SEED0 + 90)
+    n = pts.shape[0]
+    # a velodyne-driver style layout: x@0 y@4 z@8 intensity@16 ring(u16)@20, point_step 22 -> unaligned records
+    for step, ox, oy, oz, oi, big in ((22, 0, 4, 8, 16, False), (32, 4, 12, 20, 0, False), (16, 8, 0, 4, 12, True)):
+        raw = np.zeros((n, step), np.uint8)
+        dt = ">f4" if big else "<f4"
+        for col, off in ((0, ox), (1, oy), (2, oz), (3, oi)):
+            raw[:, off:off + 4] = pts[:, col].astype(dt).view(np.uint8).reshape(n, 4)
+        got = ctx.unpack_points(raw, step, ox, oy, oz, oi, big_endian=big)
+        assert np.array_equal(got.view(np.uint32), pts.view(np.uint32))
+        out = ctx.process_cloud2(raw, step, ox, oy, oz, big_endian=big)
+        want = oracle.process_frame(p, pts)
+        for k in ("range", "angle", "no_ground"):
+            assert np.array_equal(out[k], want[k]), k
+        assert np.array_equal(out["xyz"], want["xyz"])
+    # 32-byte pcl::PointXYZRGB input through gs_process_frame takes the fused kernel as well (one unpack + one fused launch)
+    wide = np.zeros((n, 8), np.float32)
+    wide[:, :3] = pts[:, :3]
+    l0 = ctx.stats().kernel_launches
+    out = ctx.process_frame(wide)
+    assert ctx.stats().kernel_launches - l0 == 2
+    assert np.array_equal(out["no_ground"], want["no_ground"]) and np.array_equal(out["xyz"], want["xyz"])
+    # cloud out: PointXYZRGB records as Alfa_GS::CameraCb builds them
+    rec = ctx.pack_cloud_xyzrgb(want["xyz"])
+    assert rec.shape == (want["xyz"].shape[0], 32)
+    assert np.array_equal(rec[:, :12].copy().view(np.float32).reshape(-1, 3), want["xyz"][:, :3])
+    assert np.array_equal(rec[:, 12:16].copy().view(np.float32).reshape(-1), np.ones(rec.shape[0], np.float32))
+    assert np.all(rec[:, 16:19] == 0) and np.all(rec[:, 19] == 255) and np.all(rec[:, 20:] == 0)
+    h, w, K = ctx.camera_info()
+    d = oracle.derive(p)
+    assert (h, w) == (64, 2048) and K[:6] == [p.min_angle, p.max_angle, p.min_range, p.max_range, d.d_azimuth, d.d_altitude]
