@@ -743,8 +743,11 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                     }
                 }
                 unsigned vbits = 0;
-                for (int r = hi; r >= lo; --r) {
-                    const unsigned e = s_range[r * S16 + c];
+                const uint16_t* p_rng = s_range + hi * S16 + c;
+                uint8_t* p_ang = s_angle + hi * S8 + c;
+#pragma unroll 4
+                for (int r = hi; r >= lo; --r, p_rng -= S16, p_ang -= S8) {
+                    const unsigned e = *p_rng;
                     unsigned a_out = 0;
                     if (e) {
                         vbits |= 1u << (r - lo);
@@ -780,7 +783,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                         p_x = __fmul_rn(rf, cy);
                         has_prev = true;
                     }
-                    s_angle[r * S8 + c] = static_cast<uint8_t>(a_out);
+                    *p_ang = static_cast<uint8_t>(a_out);
                 }
                 // valid bits of this segment -> the column's VALID mask word
                 s_m32[(MK_VALID * NWD + wseg) * CW + c] = vbits;
