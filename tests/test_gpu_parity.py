@@ -335,7 +335,7 @@ def test_set_params_recomputes_derived(ctxs, oracle):
         assert np.array_equal(got["xyz"], want["xyz"])
 
 
-def test_full_size_properties(ctxs):
+def test_full_size_properties(ctxs, oracle):
     """Size-independent properties on a C4-style batch (no oracle at this size): idempotence of the batch call,
     frame independence (a frame's result does not depend on its neighbours in the batch), counts == non-zero pixels,
     no-ground image is a subset of the range image, back-projection of the range image has one point per pixel."""
@@ -346,7 +346,7 @@ def test_full_size_properties(ctxs):
     H, W = ctx.shape
     Pn = H * W
     pool, offs = synth.make_pool(p, 4, seed0=synth.SEED0 + 60)
-    F = 64
+    F = 600  # several frames per resident cluster: the persistent kernel re-uses its shared-memory state across frames
     pts, offsets = synth.tile_pool(pool, offs, F)
     d_pts = torch.from_numpy(pts).cuda()
     outs = []
@@ -369,6 +369,10 @@ def test_full_size_properties(ctxs):
     assert bool(((d_res == 0) | (d_res == d_rng)).all())
     n0 = int(d_cnt[0])
     assert bool((d_xyz[0, :n0, 3] == 1.0).all())
+    for i in range(4):  # and the four distinct frames equal the oracle
+        w = oracle.process_frame(p, pool[offs[i]:offs[i + 1]])
+        assert np.array_equal(d_res[i].cpu().numpy().view(np.uint16), w["no_ground"])
+        assert np.array_equal(d_xyz[i, : int(d_cnt[i])].cpu().numpy(), w["xyz"])
 
 
 def test_wire_formats(ctxs, oracle):
@@ -408,3 +412,42 @@ def test_wire_formats(ctxs, oracle):
     h, w, K = ctx.camera_info()
     d = oracle.derive(p)
     assert (h, w) == (64, 2048) and K[:6] == [p.min_angle, p.max_angle, p.min_range, p.max_range, d.d_azimuth, d.d_altitude]
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_sensor_configurations(oracle, seed):
+    """Random sensor shapes and thresholds through the fused kernel (uneven last slab, odd widths, every cluster size the
+    plan search picks, both variants, smoothing on/off, keep-ground mode, shuffled and sparse clouds) against the oracle."""
+    rng = np.random.default_rng(7000 + seed)
+    H = int(rng.choice([16, 32, 64, 128]))
+    W = int(rng.choice([517, 900, 1000, 1024, 1500, 1800, 2000, 2048, 2500]))
+    if H == 128:
+        W = min(W, 2048)
+    lo = -float(rng.uniform(0.2, 0.5))
+    hi = float(rng.uniform(0.05, 0.4))
+    variant = int(rng.integers(0, 2))
+    smoothing = int(rng.integers(0, 2))
+    ws = int(rng.choice([5, 7, 9, 11]))
+    p = P.GsParams(n_beams=H, rpm=600, sample_freq=W * 10, min_angle=lo, max_angle=hi, min_range=float(rng.uniform(0.3, 1.0)),
+                   max_range=float(rng.uniform(60, 150)), ground_angle_threshold=float(rng.uniform(0.03, 0.2)),
+                   start_angle_threshold=float(rng.uniform(0.2, 0.8)), window_size=ws, erase_ground=int(rng.integers(0, 2)),
+                   variant=variant, pixel_policy=P.GS_PIXEL_LAST, col_policy=int(rng.integers(0, 2)), smoothing=smoothing, repair_gaps=0)
+    assert p.shape == (H, W)
+    pts = synth.make_frame(p, synth.SEED0 + 500 + seed, dropout=float(rng.choice([0.0, 0.05, 0.3, 0.8])), shuffle=bool(rng.integers(0, 2)),
+                           jitter=float(rng.choice([0.3, 0.45])))
+    want = oracle.process_frame(p, pts)
+    with capi.Context(p) as ctx:
+        ctx.set_option(capi.GS_OPT_COLLECT_STATS, 1)
+        l0 = ctx.stats().kernel_launches
+        got = ctx.process_frame(pts)
+        st = ctx.stats()
+        assert st.kernel_launches - l0 == 1, "the fused kernel should cover this configuration"
+        assert st.fast_path_mismatches == 0
+        for k in ("range", "angle", "no_ground"):
+            assert np.array_equal(got[k], want[k]), k
+        assert np.array_equal(got["xyz"], want["xyz"])
+        ctx.set_option(capi.GS_OPT_FORCE_STAGED, 1)
+        got2 = ctx.process_frame(pts)
+        for k in ("range", "angle", "no_ground"):
+            assert np.array_equal(got2[k], want[k]), "staged " + k
+        assert np.array_equal(got2["xyz"], want["xyz"])
