@@ -88,6 +88,48 @@ struct FusedArgs {
 
 constexpr int FB = 18;  // fractional bits of the fixed-point cell coordinates
 
+// Shared-memory layout of one CTA: a pure function of (H, CW, NW) so that it can be evaluated at compile time for the
+// specialised instantiations of k_frame (constant strides and offsets fold into the addressing) and at run time otherwise.
+struct Layout {
+    int CL, CW, S16, S8, NG;
+    unsigned off_range, off_tag, off_angle, off_masks, off_misc, off_lut;
+    size_t total;
+    bool ok;
+};
+constexpr int MK_KINDS = 8;  // == MK_COUNT (static_assert below)
+__host__ __device__ constexpr size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+__host__ __device__ constexpr size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
+__host__ __device__ constexpr Layout layout_hcw(int H, int CW, int NW) {
+    Layout L{};
+    L.CL = 0;
+    L.CW = CW;
+    L.S16 = CW + 2 + ((CW & 1) ? 1 : 0);  // odd word stride: a column-major walk over rows hits distinct banks
+    if (((L.S16 / 2) & 1) == 0) L.S16 += 2;
+    L.S8 = static_cast<int>(align_up(static_cast<size_t>(CW) + 4, 4));
+    if (((L.S8 / 4) & 1) == 0) L.S8 += 4;
+    L.NG = (CW + 31) / 32;
+    L.ok = static_cast<size_t>(H) * L.S16 <= 65535   // slab addresses are 16-bit
+           && static_cast<size_t>(H) * CW <= 32768;  // run indices are 15-bit
+    const size_t range_bytes = align_up(static_cast<size_t>(H) * L.S16 * 2, 16);
+    const size_t masks_bytes = align_up(static_cast<size_t>(MK_KINDS) * NW * CW * 8 + static_cast<size_t>(2) * H * L.NG * 4, 16);
+    const size_t tag_bytes = align_up(max_sz(range_bytes, static_cast<size_t>(H) * CW * 2), 16);
+    const size_t angle_bytes = align_up(max_sz(static_cast<size_t>(H) * L.S8, static_cast<size_t>(4096) * 3), 16);  // 4096 = MAX_BLOCKS
+    const size_t Hp = (static_cast<size_t>(H) + 7) & ~static_cast<size_t>(7);
+    const size_t misc_bytes = align_up(14 * 8 + static_cast<size_t>(8) * Hp * 4 + Hp * 4 + Hp + 2 * 8 * 4 + (8 + 20 + 64) * 4 + 64, 16);  // 8 = MAX_CL
+    L.off_range = 0;
+    L.off_tag = static_cast<unsigned>(range_bytes);
+    L.off_angle = static_cast<unsigned>(range_bytes + tag_bytes);
+    L.off_masks = static_cast<unsigned>(range_bytes + tag_bytes + angle_bytes);
+    L.off_misc = static_cast<unsigned>(range_bytes + tag_bytes + angle_bytes + masks_bytes);
+    // per-CTA copies of the lookup tables: cos/sin(azimuth) of my columns, cos/sin(altitude), sin/cos(angle_y) as double and float
+    const size_t lut_bytes = align_up(static_cast<size_t>(2) * CW * 8 + static_cast<size_t>(4) * H * 8 + static_cast<size_t>(2) * H * 4, 16);
+    L.off_lut = static_cast<unsigned>(range_bytes + tag_bytes + angle_bytes + masks_bytes + misc_bytes);
+    L.total = range_bytes + tag_bytes + angle_bytes + masks_bytes + misc_bytes + lut_bytes;
+    return L;
+}
+
+
+
 // ---- small helpers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double decode_range_d(const KParams& kp, unsigned enc) {
     // static_cast<double>(enc - 1) / 65534 * (max_range - min_range) + min_range   (alfa_gs.cpp:359-360, :1042-1045)
@@ -271,6 +313,7 @@ __device__ __forceinline__ Mask<NW> vfill(Mask<NW> g, Mask<NW> link, int H) {
 
 // mask storage in shared memory: [kind][word][column], u64 words
 enum { MK_VALID = 0, MK_VA, MK_HA, MK_V, MK_HM, MK_G, MK_KEEP, MK_S, MK_COUNT };
+static_assert(MK_COUNT == MK_KINDS, "layout_hcw sizes the mask region for MK_KINDS kinds");
 
 // Row masks live in shared memory as 32-bit words: m32[(kind * NWD + w) * CW + c] holds rows 32w .. 32w+31 of column c.
 template <int NW>
@@ -447,30 +490,37 @@ struct Smem {
 // ====================================================================================================================
 // the kernel
 // ====================================================================================================================
-template <int NW, int NT>  // NW: 64-bit words per column mask (H <= 64 * NW); NT: threads per CTA (1024 x 1 CTA/SM or 512 x 2 CTAs/SM)
+// NW: 64-bit words per column mask (H <= 64 * NW); NT: threads per CTA (1024 x 1 CTA/SM or 512 x 2 CTAs/SM);
+// HT, CWT: image rows and columns per CTA fixed at compile time (0 = read from the arguments): the BASELINE sensor shapes
+// get instantiations whose strides, offsets and trip counts are constants.
+template <int NW, int NT, int HT, int CWT>
 __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs A) {
+    constexpr bool SPEC = HT > 0;
+    constexpr Layout LC = layout_hcw(SPEC ? HT : 64, SPEC ? CWT : 512, NW);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
     const KParams& kp = A.kp;
-    const int CL = A.CL, CW = A.CW, H = kp.H, W = kp.W;
+    const int CL = A.CL, CW = SPEC ? CWT : A.CW, H = SPEC ? HT : kp.H, W = kp.W;
     const int rank = static_cast<int>(cluster.block_rank());
     const int cluster_id = blockIdx.x / CL;
     const int n_clusters = gridDim.x / CL;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col0 = rank * CW;                 // first global column of my slab
     const int myCW = min(CW, W - col0);         // columns I own (> 0 by construction)
-    const int S16 = A.S16, S8 = A.S8, NG = A.NG;
+    const int S16 = SPEC ? LC.S16 : A.S16, S8 = SPEC ? LC.S8 : A.S8, NG = SPEC ? LC.NG : A.NG;
+    const unsigned off_range = SPEC ? LC.off_range : A.off_range, off_tag = SPEC ? LC.off_tag : A.off_tag, off_angle = SPEC ? LC.off_angle : A.off_angle;
+    const unsigned off_masks = SPEC ? LC.off_masks : A.off_masks, off_misc = SPEC ? LC.off_misc : A.off_misc, off_lut = SPEC ? LC.off_lut : A.off_lut;
     const int CWp = CW;                         // mask arrays are CW wide
     // forest index of the run that starts at row rs of local column c.  The row is rotated by 2c inside the column so that
     // runs starting at the same row in neighbouring columns (the ground does) fall into different shared-memory banks.
     auto run_node = [=](int c, int rs) -> int { return c * H + ((rs + 2 * c) & (H - 1)); };  // H is a power of two (checked on the host)
 
     // ---- shared memory carve-up
-    uint16_t* s_range = reinterpret_cast<uint16_t*>(smem_raw + A.off_range);
-    uint16_t* s_tag = reinterpret_cast<uint16_t*>(smem_raw + A.off_tag);
-    uint8_t* s_angle = smem_raw + A.off_angle;
+    uint16_t* s_range = reinterpret_cast<uint16_t*>(smem_raw + off_range);
+    uint16_t* s_tag = reinterpret_cast<uint16_t*>(smem_raw + off_tag);
+    uint8_t* s_angle = smem_raw + off_angle;
     const int NWD = (H + 31) >> 5;  // 32-row words per column
-    unsigned* s_m32 = reinterpret_cast<unsigned*>(smem_raw + A.off_masks);  // [MK_COUNT][NWD][CW]
+    unsigned* s_m32 = reinterpret_cast<unsigned*>(smem_raw + off_masks);  // [MK_COUNT][NWD][CW]
     uint16_t* s_par = s_tag;  // [CW][H] union-find parents of the vertical runs (the tag slab is dead after the projection)
     unsigned* s_rowmask = s_m32 + static_cast<size_t>(MK_COUNT) * NWD * CW;  // [H][NG]
     // scratch of the labelling stage in the angle slab (dead once the links are computed): link words to unite and their scan
@@ -480,7 +530,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
     unsigned* s_grp = s_rowmask + H * NG;                                                                  // [H][NG]
     uint8_t* s_assign = s_angle;                                                                           // [MAX_BLOCKS]
     uint16_t* s_mylist = reinterpret_cast<uint16_t*>(s_angle + MAX_BLOCKS);                                // [MAX_BLOCKS]
-    unsigned char* misc = smem_raw + A.off_misc;
+    unsigned char* misc = smem_raw + off_misc;
     const int Hp = (H + 7) & ~7;
     unsigned long long* s_halo_masks = reinterpret_cast<unsigned long long*>(misc);     // [7][2]
     unsigned* s_rowcnt_all = reinterpret_cast<unsigned*>(s_halo_masks + 14);            // [MAX_CL][Hp]
@@ -492,7 +542,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
     unsigned* s_scan = s_halo32 + 20;                                                   // [64] block scan scratch
 
     // lookup tables: shared-memory copies made once per CTA (the persistent kernel reuses them for every frame)
-    double* s_cos_az = reinterpret_cast<double*>(smem_raw + A.off_lut);  // [CW]
+    double* s_cos_az = reinterpret_cast<double*>(smem_raw + off_lut);  // [CW]
     double* s_sin_az = s_cos_az + CW;                                    // [CW]
     double* s_cos_alt = s_sin_az + CW;                                   // [H]
     double* s_sin_alt = s_cos_alt + H;
@@ -1261,44 +1311,14 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
 // ====================================================================================================================
 namespace {
 
-struct Layout {
-    int CL, CW, S16, S8, NG;
-    unsigned off_range, off_tag, off_angle, off_masks, off_misc, off_lut;
-    size_t total;
-};
-
-inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
 bool layout_for(const KParams& kp, int CL, int NW, Layout* L) {
     const int W = kp.W, H = kp.H;
     const int CW = (W + CL - 1) / CL;
     if (CW < 2 && W >= 2) return false;
     if (W - (CL - 1) * CW <= 0) return false;  // the last CTA must own at least one column
+    *L = layout_hcw(H, CW, NW);
     L->CL = CL;
-    L->CW = CW;
-    L->S16 = CW + 2 + ((CW & 1) ? 1 : 0);  // odd word stride: a column-major walk over rows hits distinct banks
-    if (((L->S16 / 2) & 1) == 0) L->S16 += 2;
-    L->S8 = static_cast<int>(align_up(CW + 4, 4));
-    if (((L->S8 / 4) & 1) == 0) L->S8 += 4;
-    L->NG = (CW + 31) / 32;
-    if (static_cast<size_t>(H) * L->S16 > 65535) return false;  // slab addresses are 16-bit
-    if (static_cast<size_t>(H) * CW > 32768) return false;      // run indices are 15-bit
-    const size_t range_bytes = align_up(static_cast<size_t>(H) * L->S16 * 2, 16);
-    const size_t masks_bytes = align_up(static_cast<size_t>(MK_COUNT) * NW * CW * 8 + static_cast<size_t>(2) * H * L->NG * 4, 16);
-    const size_t tag_bytes = align_up(std::max(range_bytes, static_cast<size_t>(H) * CW * 2), 16);
-    const size_t angle_bytes = align_up(std::max(static_cast<size_t>(H) * L->S8, static_cast<size_t>(MAX_BLOCKS) * 3), 16);
-    const size_t Hp = (static_cast<size_t>(H) + 7) & ~static_cast<size_t>(7);
-    const size_t misc_bytes = align_up(14 * 8 + static_cast<size_t>(MAX_CL) * Hp * 4 + Hp * 4 + Hp + 2 * MAX_CL * 4 + (8 + 20 + 64) * 4 + 64, 16);
-    L->off_range = 0;
-    L->off_tag = static_cast<unsigned>(range_bytes);
-    L->off_angle = static_cast<unsigned>(range_bytes + tag_bytes);
-    L->off_masks = static_cast<unsigned>(range_bytes + tag_bytes + angle_bytes);
-    L->off_misc = static_cast<unsigned>(range_bytes + tag_bytes + angle_bytes + masks_bytes);
-    // per-CTA copies of the lookup tables: cos/sin(azimuth) of my columns, cos/sin(altitude), sin/cos(angle_y) as double and float
-    const size_t lut_bytes = align_up(static_cast<size_t>(2) * CW * 8 + static_cast<size_t>(4) * H * 8 + static_cast<size_t>(2) * H * 4, 16);
-    L->off_lut = static_cast<unsigned>(range_bytes + tag_bytes + angle_bytes + masks_bytes + misc_bytes);
-    L->total = range_bytes + tag_bytes + angle_bytes + masks_bytes + misc_bytes + lut_bytes;
-    return true;
+    return L->ok;
 }
 
 struct FusedPlan {
@@ -1307,6 +1327,19 @@ struct FusedPlan {
     int max_clusters;
 };
 
+}  // namespace
+
+namespace {
+// the instantiation that serves (NW, threads, H, columns per CTA): specialised for the BASELINE sensor shapes, generic otherwise
+const void* select_kernel(int NW, int nt, int H, int CW) {
+    if (nt == 1024) {
+        if (NW == 1 && H == 64 && CW == 512) return reinterpret_cast<const void*>(k_frame<1, 1024, 64, 512>);   // C2 / C4: 64 x 2048 on 4 CTAs
+        if (NW == 1 && H == 16 && CW == 900) return reinterpret_cast<const void*>(k_frame<1, 1024, 16, 900>);   // C1: 16 x 1800 on 2 CTAs
+        if (NW == 2 && H == 128 && CW == 256) return reinterpret_cast<const void*>(k_frame<2, 1024, 128, 256>);  // C3 / C5: 128 x 2048 on 8 CTAs
+        return NW == 1 ? reinterpret_cast<const void*>(k_frame<1, 1024, 0, 0>) : reinterpret_cast<const void*>(k_frame<2, 1024, 0, 0>);
+    }
+    return NW == 1 ? reinterpret_cast<const void*>(k_frame<1, 512, 0, 0>) : reinterpret_cast<const void*>(k_frame<2, 512, 0, 0>);
+}
 }  // namespace
 
 int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const SgTaps& sg, bool smooth, bool repair, int device) {
@@ -1336,17 +1369,18 @@ int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const Sg
     const char* force_cl = getenv("GS_FUSED_CLUSTER");
     const int nt = (mode && atoi(mode) == 512) ? 512 : 1024;
     const size_t smem_cap = nt == 512 ? static_cast<size_t>(max_smem_sm) / 2 - 1024 : static_cast<size_t>(max_smem);
-    const void* kern = nt == 512 ? (NW == 1 ? reinterpret_cast<const void*>(k_frame<1, 512>) : reinterpret_cast<const void*>(k_frame<2, 512>))
-                                 : (NW == 1 ? reinterpret_cast<const void*>(k_frame<1, 1024>) : reinterpret_cast<const void*>(k_frame<2, 1024>));
-    // the attribute is per function, not per context: always ask for the device maximum
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    if (e != cudaSuccess) return static_cast<int>(e);
     Layout lay;
     int max_clusters = 0, best_sms = 0;
     for (int CL = 1; CL <= MAX_CL; ++CL) {
         if (force_cl && atoi(force_cl) != CL) continue;
         Layout l;
         if (!layout_for(kp, CL, NW, &l) || l.total > smem_cap) continue;
+        const void* kern = select_kernel(NW, nt, kp.H, l.CW);
+        // the attribute is per function, not per context: always ask for the device maximum
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(static_cast<unsigned>((nt == 512 ? 2 : 1) * n_sms / CL * CL));
         cfg.blockDim = dim3(nt);
@@ -1368,6 +1402,7 @@ int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const Sg
             best_sms = n * CL;
             max_clusters = n;
             lay = l;
+            fs.kernel = kern;
         }
     }
     if (max_clusters < 1) return 0;  // no cluster shape fits here: staged kernels
@@ -1495,9 +1530,8 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e;
-    if (fs.threads == 512) e = NW == 1 ? cudaLaunchKernelEx(&cfg, k_frame<1, 512>, a) : cudaLaunchKernelEx(&cfg, k_frame<2, 512>, a);
-    else e = NW == 1 ? cudaLaunchKernelEx(&cfg, k_frame<1, 1024>, a) : cudaLaunchKernelEx(&cfg, k_frame<2, 1024>, a);
+    void* kargs[] = {&a};
+    const cudaError_t e = cudaLaunchKernelExC(&cfg, fs.kernel, kargs);
     if (e != cudaSuccess) return static_cast<int>(e);
     ++*L.n_launches;
     return 0;

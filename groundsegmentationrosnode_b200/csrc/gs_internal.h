@@ -98,6 +98,7 @@ struct FusedState {
     bool configured = false; // the configuration fits the fused kernel
     int cluster = 0;         // CTAs per frame
     int threads = 1024;      // threads per CTA
+    const void* kernel = nullptr;  // the k_frame instantiation chosen for this configuration
     int cols_per_cta = 0;
     size_t smem_bytes = 0;
     int n_sms = 0;
