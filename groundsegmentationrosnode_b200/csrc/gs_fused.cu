@@ -491,22 +491,22 @@ struct Smem {
 // the kernel
 // ====================================================================================================================
 // NW: 64-bit words per column mask (H <= 64 * NW); NT: threads per CTA (1024 x 1 CTA/SM or 512 x 2 CTAs/SM);
-// HT, CWT: image rows and columns per CTA fixed at compile time (0 = read from the arguments): the BASELINE sensor shapes
-// get instantiations whose strides, offsets and trip counts are constants.
-template <int NW, int NT, int HT, int CWT>
+// HT, CWT, CLT: image rows, columns per CTA and CTAs per frame fixed at compile time (0 = read from the arguments; the image
+// is then exactly CLT * CWT wide): the BASELINE sensor shapes get instantiations whose strides, offsets and trip counts are constants.
+template <int NW, int NT, int HT, int CWT, int CLT>
 __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs A) {
     constexpr bool SPEC = HT > 0;
     constexpr Layout LC = layout_hcw(SPEC ? HT : 64, SPEC ? CWT : 512, NW);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
     const KParams& kp = A.kp;
-    const int CL = A.CL, CW = SPEC ? CWT : A.CW, H = SPEC ? HT : kp.H, W = kp.W;
+    const int CL = SPEC ? CLT : A.CL, CW = SPEC ? CWT : A.CW, H = SPEC ? HT : kp.H, W = SPEC ? CLT * CWT : kp.W;
     const int rank = static_cast<int>(cluster.block_rank());
     const int cluster_id = blockIdx.x / CL;
     const int n_clusters = gridDim.x / CL;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col0 = rank * CW;                 // first global column of my slab
-    const int myCW = min(CW, W - col0);         // columns I own (> 0 by construction)
+    const int myCW = SPEC ? CWT : min(CW, W - col0);  // columns I own (> 0 by construction)
     const int S16 = SPEC ? LC.S16 : A.S16, S8 = SPEC ? LC.S8 : A.S8, NG = SPEC ? LC.NG : A.NG;
     const unsigned off_range = SPEC ? LC.off_range : A.off_range, off_tag = SPEC ? LC.off_tag : A.off_tag, off_angle = SPEC ? LC.off_angle : A.off_angle;
     const unsigned off_masks = SPEC ? LC.off_masks : A.off_masks, off_misc = SPEC ? LC.off_misc : A.off_misc, off_lut = SPEC ? LC.off_lut : A.off_lut;
@@ -1331,14 +1331,14 @@ struct FusedPlan {
 
 namespace {
 // the instantiation that serves (NW, threads, H, columns per CTA): specialised for the BASELINE sensor shapes, generic otherwise
-const void* select_kernel(int NW, int nt, int H, int CW) {
-    if (nt == 1024) {
-        if (NW == 1 && H == 64 && CW == 512) return reinterpret_cast<const void*>(k_frame<1, 1024, 64, 512>);   // C2 / C4: 64 x 2048 on 4 CTAs
-        if (NW == 1 && H == 16 && CW == 900) return reinterpret_cast<const void*>(k_frame<1, 1024, 16, 900>);   // C1: 16 x 1800 on 2 CTAs
-        if (NW == 2 && H == 128 && CW == 256) return reinterpret_cast<const void*>(k_frame<2, 1024, 128, 256>);  // C3 / C5: 128 x 2048 on 8 CTAs
-        return NW == 1 ? reinterpret_cast<const void*>(k_frame<1, 1024, 0, 0>) : reinterpret_cast<const void*>(k_frame<2, 1024, 0, 0>);
+const void* select_kernel(int NW, int nt, int H, int CW, int CL, int W) {
+    if (nt == 1024 && W == CL * CW) {
+        if (NW == 1 && H == 64 && CW == 512 && CL == 4) return reinterpret_cast<const void*>(k_frame<1, 1024, 64, 512, 4>);   // C2 / C4: 64 x 2048 on 4 CTAs
+        if (NW == 1 && H == 16 && CW == 900 && CL == 2) return reinterpret_cast<const void*>(k_frame<1, 1024, 16, 900, 2>);   // C1: 16 x 1800 on 2 CTAs
+        if (NW == 2 && H == 128 && CW == 256 && CL == 8) return reinterpret_cast<const void*>(k_frame<2, 1024, 128, 256, 8>);  // C3 / C5: 128 x 2048 on 8 CTAs
     }
-    return NW == 1 ? reinterpret_cast<const void*>(k_frame<1, 512, 0, 0>) : reinterpret_cast<const void*>(k_frame<2, 512, 0, 0>);
+    if (nt == 1024) return NW == 1 ? reinterpret_cast<const void*>(k_frame<1, 1024, 0, 0, 0>) : reinterpret_cast<const void*>(k_frame<2, 1024, 0, 0, 0>);
+    return NW == 1 ? reinterpret_cast<const void*>(k_frame<1, 512, 0, 0, 0>) : reinterpret_cast<const void*>(k_frame<2, 512, 0, 0, 0>);
 }
 }  // namespace
 
@@ -1375,7 +1375,7 @@ int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const Sg
         if (force_cl && atoi(force_cl) != CL) continue;
         Layout l;
         if (!layout_for(kp, CL, NW, &l) || l.total > smem_cap) continue;
-        const void* kern = select_kernel(NW, nt, kp.H, l.CW);
+        const void* kern = select_kernel(NW, nt, kp.H, l.CW, CL, kp.W);
         // the attribute is per function, not per context: always ask for the device maximum
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess) {
             cudaGetLastError();
