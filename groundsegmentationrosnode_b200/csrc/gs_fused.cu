@@ -81,6 +81,9 @@ struct FusedArgs {
     const KParams* kp_dev;     // device-memory copy of kp for the out-of-line exact path
     int col_limit, col_wrap;   // largest column the fast path may return; GS_COL_WRAP
     double range_lo_in, range_hi_in, range_lo_out, range_hi_out;  // range gates -/+ 1e-9 m
+    // lean fast path (project_lean): encoded range in 2^-UB fixed point, altitude gates in cell fixed point
+    double u_scale, u_c0;      // ufix = trunc(range * u_scale + u_c0) = ((range - min_range) * 65534 / span + 1) * 2^UB
+    int alt_gate_lo, alt_gate_span;  // rn(altitude * alt_to_fix) - alt_gate_lo <= alt_gate_span (unsigned): certainly inside the altitude gates
     float sg_t[11];            // Savitzky-Golay taps (cloud2range_node.cpp:470), sg_ws = 0: no smoothing
     int sg_ws;
     int use_fast;
@@ -460,6 +463,82 @@ __device__ __forceinline__ int project_fast(const FusedArgs& A, float fx, float 
     return 0;
 }
 
+constexpr int UB = 14;  // fractional bits of the fixed-point encoded range
+
+__device__ __forceinline__ float rsqrt_ftz(float a) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
+__device__ __forceinline__ float rcp_ftz(float a) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
+
+// Lean version of project_fast (same certificates, ~40 % fewer instructions; returns 0 = pixel found, 1 = dropped,
+// 2 = undecided -> project_point_d):
+//  * range: fused double sum of squares, MUFU rsqrt seed (relative error e0 < 2.2e-7) and ONE Heron step
+//    r + (s2 - r*r) * (0.5 * seed), relative error 1.5 e0^2 < 7e-14, i.e. < 6e-9 of an encoded-range unit.  The encoded
+//    value is taken in 2^-14 fixed point from one DFMA + F2I; a fractional part of 0 or 16383 (within 6.1e-5 of an
+//    integer, 10^4 x the error) or a value outside (1, 65535) — the range gates of alfa_gs.cpp:261 map to exactly 1 and
+//    65535 — leaves the decision to the cold path below / the exact evaluation.
+//  * altitude / azimuth: float atan as in project_fast with the raw MUFU rcp / rsqrt (flush-to-zero forms: the operands
+//    are certified > 1e-15 first), gates and cell edges tested on the fixed-point cell coordinates with the same margins.
+__device__ __forceinline__ int project_lean(const FusedArgs& A, float fx, float fy, float fz, int* row_out, int* col_out, unsigned* enc_out) {
+    const KParams& kp = A.kp;
+    const double x = fx, y = fy, z = fz;
+    const double s2 = __fma_rn(x, x, __fma_rn(y, y, __dmul_rn(z, z)));
+    const float seed = rsqrt_ftz(__double2float_rn(s2));
+    const double r0 = __dmul_rn(s2, static_cast<double>(seed));
+    const double range = __fma_rn(__fma_rn(-r0, r0, s2), static_cast<double>(__fmul_rn(0.5f, seed)), r0);
+    const int ufix = __double2int_rz(__fma_rn(range, A.u_scale, A.u_c0));  // NaN -> 0, overflow saturates: both fail the test below
+    const unsigned ufrac = static_cast<unsigned>(ufix) & ((1u << UB) - 1u);
+    if (static_cast<unsigned>(ufix - ((1 << UB) + 1)) > static_cast<unsigned>((65534 << UB) - 2) || ufrac - 1u > (1u << UB) - 3u) {
+        // cold: outside the gates by more than 1e-9 m -> dropped (alfa_gs.cpp:261); anything else -> exact evaluation
+        if (range < A.range_lo_out || range > A.range_hi_out) return 1;
+        return 2;
+    }
+    const float h2 = __fmaf_rn(fx, fx, __fmul_rn(fy, fy));
+    if (fy == 0.0f || !(h2 > 1e-30f)) return 2;  // atan2(-0.0, x < 0) = -pi in the reference (Q3); flush-to-zero forms below need h2 > 0
+    // altitude = atan2(z, hypot(x, y))
+    const float az = fabsf(fz);
+    const float h = __fmul_rn(h2, rsqrt_ftz(h2));
+    float t = atan01(__fmul_rn(fminf(az, h), rcp_ftz(fmaxf(az, h))));
+    if (az > h) t = 1.57079632679489662f - t;
+    const float alt = __uint_as_float(__float_as_uint(t) | (__float_as_uint(fz) & 0x80000000u));
+    const int altfix = __float2int_rn(__fmul_rn(alt, A.alt_to_fix));
+    const int rowfix = A.row0_fix - altfix;
+    const unsigned rfrac = static_cast<unsigned>(rowfix) & ((1u << FB) - 1u);
+    // azimuth in [0, 2 pi): octant reduction, reflections in exact fixed point
+    const float ax = fabsf(fx), ay = fabsf(fy);
+    int c = __float2int_rn(__fmul_rn(atan01(__fmul_rn(fminf(ax, ay), rcp_ftz(fmaxf(ax, ay)))), A.az_to_fix));
+    if (ay > ax) c = A.quarter_fix - c;
+    if (fx < 0.0f) c = 2 * A.quarter_fix - c;
+    if (fy < 0.0f) c = 4 * A.quarter_fix - c;
+    const int colfix = c + A.col_half_fix;
+    const unsigned cfrac = static_cast<unsigned>(colfix) & ((1u << FB) - 1u);
+    const int row = rowfix >> FB;
+    int col = colfix >> FB;
+    const unsigned rm = static_cast<unsigned>(A.row_margin), cm = static_cast<unsigned>(A.col_margin);
+    const bool gate_ok = static_cast<unsigned>(altfix - A.alt_gate_lo) <= static_cast<unsigned>(A.alt_gate_span);
+    const bool edges_ok = rfrac - rm <= (1u << FB) - 2u * rm && cfrac - cm <= (1u << FB) - 2u * cm;
+    const bool box_ok = static_cast<unsigned>(row) < static_cast<unsigned>(kp.H) && static_cast<unsigned>(col) <= static_cast<unsigned>(A.col_limit);
+    if (!(gate_ok && edges_ok && box_ok)) {
+        // cold: certainly outside the altitude gates (alfa_gs.cpp:269) -> dropped; within a margin of a gate or an edge -> exact
+        if (alt < A.alt_lo - 1e-6f || alt > A.alt_hi + 1e-6f) return 1;
+        return 2;
+    }
+    if (col == kp.W) {  // only the alfa_gs variant gets here (col_limit = W)
+        if (A.col_wrap) col = 0;                  // GS_COL_WRAP
+        else if (row == kp.H - 1) return 1;       // Q2: flat index past the end of the image
+    }
+    *row_out = row;
+    *col_out = col;
+    *enc_out = static_cast<unsigned>(ufix) >> UB;
+    return 0;
+}
+
 // cheap column estimate used only to deal point blocks to CTAs (any answer is correct, a good one is fast)
 __device__ __forceinline__ int approx_col(const KParams& kp, float x, float y) {
     float a = atan2f(y, x);
@@ -528,7 +607,6 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
     uint16_t* s_excl = reinterpret_cast<uint16_t*>(s_todo + static_cast<size_t>(CW) * NWD);  // [(CW - 1) * NWD + 1]
     uint16_t* s_qcw = s_excl + static_cast<size_t>(CW) * NWD + 2;                            // [(CW - 1) * NWD] column << 2 | word
     unsigned* s_grp = s_rowmask + H * NG;                                                                  // [H][NG]
-    uint8_t* s_assign = s_angle;                                                                           // [MAX_BLOCKS]
     uint16_t* s_mylist = reinterpret_cast<uint16_t*>(s_angle + MAX_BLOCKS);                                // [MAX_BLOCKS]
     unsigned char* misc = smem_raw + off_misc;
     const int Hp = (H + 7) & ~7;
@@ -562,12 +640,17 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         s_sin_y[r] = A.lut.sin_y[r];
         s_cos_y[r] = A.lut.cos_y[r];
     }
+    if (tid == 0) s_misc[0] = 0;  // blocks dealt to me (reset at the end of every frame)
     __syncthreads();
 
     uint2* rlist = A.rlist + (static_cast<size_t>(cluster_id) * CL + rank) * A.rcap;
     unsigned* rcount = A.rcount + static_cast<size_t>(cluster_id) * CL;
 
-    unsigned long long st_dropped = 0, st_near = 0, st_near_angle = 0, st_remote = 0, st_fallback = 0, st_mismatch = 0;
+    // statistics runs (tests): counters live in shared memory, not in registers of the hot loops
+    enum { ST_DROPPED = 0, ST_NEAR, ST_NEAR_ANGLE, ST_REMOTE, ST_FALLBACK, ST_MISMATCH, ST_COUNT };
+    unsigned* s_stat = s_scan + 64;  // [ST_COUNT] in the slack of the misc area
+    if (tid < ST_COUNT) s_stat[tid] = 0;
+#define GS_STAT(which) atomicAdd(&s_stat[which], 1u)
     // phase timing (GS_OPT_COLLECT_STATS): thread 0 of every CTA accumulates clock64() deltas per phase
     long long t_mark = 0;
     int t_phase = 0;
@@ -614,21 +697,9 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
 #pragma unroll
             for (int j = 1; j < MAX_CL; ++j)
                 if (votes[j] > votes[best]) best = j;
-            s_assign[b] = static_cast<uint8_t>(best);
+            if (best == rank) s_mylist[atomicAdd(&s_misc[0], 1u)] = static_cast<uint16_t>(b);  // any order: the pixel keys carry the point order
         }
         if (tid == 0) rcount[rank] = 0;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned n = 0;
-            for (int b0 = 0; b0 < nb; b0 += 32) {
-                const int b = b0 + lane;
-                const bool mine = b < nb && s_assign[b] == rank;
-                const unsigned m = __ballot_sync(0xffffffffu, mine);
-                if (mine) s_mylist[n + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(b);
-                n += __popc(m);
-            }
-            if (lane == 0) s_misc[0] = n;
-        }
         __syncthreads();
         const int nmine = static_cast<int>(s_misc[0]);
 
@@ -640,38 +711,33 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         unsigned* s_key = reinterpret_cast<unsigned*>(s_range);  // [H][S16] u32 over the range + tag slabs, compacted to u16 below
         int tag_shift = 0;  // order tag = index >> tag_shift, the smallest shift that fits 16 bits (uniform per frame)
         while ((((N - 1) >> tag_shift) + 1) > 65535) ++tag_shift;
-        for (int qb = 0; qb < nmine * BLK; qb += NT * NPT) {
-            float4 cur_p[NPT];
-            int cur_i[NPT];
-#pragma unroll
-            for (int j = 0; j < NPT; ++j) {  // all loads of the batch are in flight before the first one is used
-                const int q = qb + j * NT + tid;
-                int i = -1;
-                if (q < nmine * BLK) {
-                    i = static_cast<int>(s_mylist[q >> 8]) * BLK + (q & (BLK - 1));
-                    if (i >= N) i = -1;
-                }
-                cur_i[j] = i;
-                cur_p[j] = i >= 0 ? __ldcs(pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int j = 0; j < NPT; ++j) {
-                const int i = cur_i[j];
+        {
+            // Work units of 64 consecutive points (a quarter of a dealt block) go round-robin to the warps; the two loads of the
+            // next unit are issued before the current unit is processed.
+            const bool stats1 = (A.stats & 1) != 0;
+            const int n_punits = nmine * (BLK / 64);
+            auto load_unit = [&](int u, float4& pa, float4& pb) -> int {
+                const int i0 = static_cast<int>(s_mylist[u >> 2]) * BLK + (u & 3) * 64 + lane;
+                pa = i0 < N ? __ldcs(pts + i0) : make_float4(0.f, 0.f, 0.f, 0.f);
+                pb = i0 + 32 < N ? __ldcs(pts + i0 + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+                return i0;
+            };
+            auto place = [&](const float4 p4, const int i) {
                 unsigned k = 0x80000000u | lane;  // owner << 16 | slab address; this value is unique per lane: never matches
                 unsigned val = 0;                 // g << 16 | encoded range
-                if (i >= 0) {
-                    const float4 p4 = cur_p[j];
-                    int row = -1, col = -1;
-                    unsigned enc = 0;
-                    int st = A.use_fast ? project_fast(A, p4.x, p4.y, p4.z, &row, &col, &enc) : 2;
-                    if (st == 2 || (A.stats & 1)) {
+                int row = -1, col = -1;
+                unsigned enc = 0;
+                int st = 1;
+                if (i < N) {
+                    st = A.use_fast ? project_lean(A, p4.x, p4.y, p4.z, &row, &col, &enc) : 2;
+                    if (st == 2 || stats1) {
                         // exact evaluation: the undecided points, and every point when statistics are collected
                         const Proj pr = project_point_d(A.kp_dev, p4.x, p4.y, p4.z);
-                        if ((A.stats & 1)) {
-                            if (st == 2) ++st_fallback;
-                            else if ((st == 1) != (pr.row < 0) || (st == 0 && (row != pr.row || col != pr.col || enc != pr.enc))) ++st_mismatch;
-                            if (pr.row < 0) ++st_dropped;
-                            else if (pr.near_edge) ++st_near;
+                        if (stats1) {
+                            if (st == 2) GS_STAT(ST_FALLBACK);
+                            else if ((st == 1) != (pr.row < 0) || (st == 0 && (row != pr.row || col != pr.col || enc != pr.enc))) GS_STAT(ST_MISMATCH);
+                            if (pr.row < 0) GS_STAT(ST_DROPPED);
+                            else if (pr.near_edge) GS_STAT(ST_NEAR);
                         }
                         if (st == 2) {
                             row = pr.row;
@@ -680,24 +746,29 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                             st = pr.row < 0 ? 1 : 0;
                         }
                     }
-                    if (st == 0) {
-                        if (col == W) {  // Q2: at<ushort>(row, W) is flat index (row + 1) * W
-                            row += 1;
-                            col = 0;
-                        }
-                        const int owner = min(static_cast<int>(__umulhi(static_cast<unsigned>(col), A.cw_magic)), CL - 1);
-                        const int lc = col - owner * CW;
-                        k = (static_cast<unsigned>(owner) << 16) | static_cast<unsigned>(row * S16 + lc);
-                        val = ((static_cast<unsigned>(i >> tag_shift) + 1u) << 16) | enc;
+                }
+                if (st == 0) {
+                    if (col == W) {  // Q2: at<ushort>(row, W) is flat index (row + 1) * W
+                        row += 1;
+                        col = 0;
                     }
+                    const int owner = SPEC ? col / CW : min(static_cast<int>(__umulhi(static_cast<unsigned>(col), A.cw_magic)), CL - 1);
+                    const int lc = col - owner * CW;
+                    k = (static_cast<unsigned>(owner) << 16) | static_cast<unsigned>(row * S16 + lc);
+                    val = ((static_cast<unsigned>(i >> tag_shift) + 1u) << 16) | enc;
                 }
                 // points that share an order tag are 2^tag_shift consecutive lanes: the highest lane among those that hit the
                 // same pixel holds the latest point (xor-shuffles over the group; __match_any_sync would do the same for a
                 // whole warp but costs ~100 cycles of the address-divergence unit per call when all keys differ)
-                bool winner = !(k & 0x80000000u);
-                for (int d = 1; d < (1 << tag_shift); ++d) {
-                    const unsigned other = __shfl_xor_sync(0xffffffffu, k, d);
-                    if (other == k && (lane ^ d) > lane) winner = false;
+                bool winner = st == 0;
+                if (tag_shift) {  // uniform; 1 for frames of 64 Ki .. 128 Ki points
+                    const unsigned o1 = __shfl_xor_sync(0xffffffffu, k, 1);
+                    if (o1 == k && !(lane & 1)) winner = false;
+#pragma unroll 1
+                    for (int d = 2; d < (1 << tag_shift); ++d) {
+                        const unsigned other = __shfl_xor_sync(0xffffffffu, k, d);
+                        if (other == k && (lane ^ d) > lane) winner = false;
+                    }
                 }
                 const bool local = winner && static_cast<int>(k >> 16) == rank;
                 if (local) atomicMax(s_key + (k & 0xffffu), val);
@@ -711,9 +782,19 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                     if (remote) {
                         const unsigned slot = base + __popc(rm & ((1u << lane) - 1u));
                         if (slot < A.rcap) rlist[slot] = make_uint2(k, val);
-                        if ((A.stats & 1)) ++st_remote;
+                        if (stats1) GS_STAT(ST_REMOTE);
                     }
                 }
+            };
+            float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb4 = na;
+            int ni = 0;
+            if (warp < n_punits) ni = load_unit(warp, na, nb4);
+            for (int u = warp; u < n_punits; u += NT / 32) {
+                const float4 pa = na, pb = nb4;
+                const int i0 = ni;
+                if (u + NT / 32 < n_punits) ni = load_unit(u + NT / 32, na, nb4);
+                place(pa, i0);
+                place(pb, i0 + 32);
             }
         }
         GS_PHASE(2);
@@ -821,9 +902,9 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                                 const unsigned exact = static_cast<unsigned>(__float2int_rz(scaled));
                                 if ((A.stats & 1)) {
                                     const float fe = scaled - floorf(scaled);
-                                    if (fminf(fe, 1.0f - fe) < 1e-3f) ++st_near_angle;
-                                    if (!sure) ++st_fallback;
-                                    else if (exact != a_out) ++st_mismatch;
+                                    if (fminf(fe, 1.0f - fe) < 1e-3f) GS_STAT(ST_NEAR_ANGLE);
+                                    if (!sure) GS_STAT(ST_FALLBACK);
+                                    else if (exact != a_out) GS_STAT(ST_MISMATCH);
                                 }
                                 if (!sure) a_out = exact;
                             }
@@ -1291,17 +1372,20 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             }
         }
         GS_PHASE(0);
+        if (tid == 0) s_misc[0] = 0;
         __syncthreads();  // the slabs are cleared at the top of the next frame
     }
 
     if ((A.stats & 1)) {
-        // block-level reduction is not worth it: stats runs are test runs
-        if (st_dropped) atomicAdd(&A.cnt->dropped, st_dropped);
-        if (st_near) atomicAdd(&A.cnt->near_edge_project, st_near);
-        if (st_near_angle) atomicAdd(&A.cnt->near_edge_angle, st_near_angle);
-        if (st_remote) atomicAdd(&A.cnt->remote, st_remote);
-        if (st_fallback) atomicAdd(&A.cnt->slow_path, st_fallback);
-        if (st_mismatch) atomicAdd(&A.cnt->fast_mismatch, st_mismatch);
+        __syncthreads();
+        if (tid == 0) {
+            atomicAdd(&A.cnt->dropped, static_cast<unsigned long long>(s_stat[ST_DROPPED]));
+            atomicAdd(&A.cnt->near_edge_project, static_cast<unsigned long long>(s_stat[ST_NEAR]));
+            atomicAdd(&A.cnt->near_edge_angle, static_cast<unsigned long long>(s_stat[ST_NEAR_ANGLE]));
+            atomicAdd(&A.cnt->remote, static_cast<unsigned long long>(s_stat[ST_REMOTE]));
+            atomicAdd(&A.cnt->slow_path, static_cast<unsigned long long>(s_stat[ST_FALLBACK]));
+            atomicAdd(&A.cnt->fast_mismatch, static_cast<unsigned long long>(s_stat[ST_MISMATCH]));
+        }
     }
     cluster.sync();  // no CTA exits while a neighbour may still address its shared memory
 }
@@ -1500,6 +1584,15 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
         a.col_half_fix = c2r ? 0 : (1 << (FB - 1));
         a.row_margin = static_cast<int>(std::ceil(1.0e-6 * alt_scale * two_fb)) + 8;   // 1e-6 rad >= 4x the altitude error budget
         a.col_margin = static_cast<int>(std::ceil(7.5e-7 * az_scale * two_fb)) + 8;    // 7.5e-7 rad >= 4x the azimuth error budget
+        a.u_scale = a.enc_scale * static_cast<double>(1 << UB);
+        a.u_c0 = (1.0 - kp.min_range * a.enc_scale) * static_cast<double>(1 << UB);
+        {
+            // altitude gates (alfa_gs.cpp:269) on rn(altitude * alt_to_fix): inside by more than 1e-6 rad (+ 2 units of rounding)
+            const double glo = std::ceil((kp.min_angle + 1.0e-6) * alt_scale * two_fb) + 2.0;
+            const double ghi = std::floor((kp.max_angle - 1.0e-6) * alt_scale * two_fb) - 2.0;
+            a.alt_gate_lo = static_cast<int>(glo);
+            a.alt_gate_span = ghi >= glo ? static_cast<int>(ghi - glo) : -1;
+        }
         a.cw_magic = static_cast<unsigned>((0x100000000ull + lay.CW - 1) / lay.CW);
         a.ng_magic = static_cast<unsigned>((0x100000000ull + lay.NG - 1) / lay.NG);
         a.kp_dev = static_cast<const KParams*>(fs.d_const);
