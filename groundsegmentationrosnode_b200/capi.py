@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(HERE, "libgs_b200.so")
 GS_OPT_COLLECT_STATS = 1
 GS_OPT_FORCE_STAGED = 2
 GS_OPT_PHASE_TIMING = 3
+GS_OPT_CAS_UNIONS = 4
 
 # every symbol include/gs_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [

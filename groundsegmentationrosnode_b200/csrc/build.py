@@ -28,7 +28,8 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    cmd = [NVCC, *FLAGS, *(["-Xptxas", "-v"] if verbose else []), *[os.path.join(HERE, s) for s in SOURCES], "-o", LIB]
+    extra = os.environ.get("GS_EXTRA_NVCC_FLAGS", "").split()  # experiments (e.g. -DGS_UF_DEBUG)
+    cmd = [NVCC, *FLAGS, *extra, *(["-Xptxas", "-v"] if verbose else []), *[os.path.join(HERE, s) for s in SOURCES], "-o", LIB]
     subprocess.check_call(cmd)
     return LIB
 

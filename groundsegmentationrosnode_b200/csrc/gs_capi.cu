@@ -145,6 +145,7 @@ struct gs_ctx {
     unsigned long long n_launches = 0;
     bool collect_stats = false;
     bool phase_timing = false;
+    bool cas_unions = false;
     // single-frame staging (stage API)
     void* d_points = nullptr;
     size_t d_points_cap = 0;
@@ -412,7 +413,7 @@ int run_wave(gs_ctx* ctx, const void* d_points, size_t stride, const long long* 
     if (stride == 16 && (reinterpret_cast<uintptr_t>(d_points) & 15) == 0 && fused_supported(ctx->fused) && max_points <= fused_max_points()) {
         const Launch L = launch_of(ctx);
         const int rc = fused_run(ctx->fused, L, static_cast<const float4*>(d_points), d_offsets, frames, max_points, range_out, angle_out, res_out,
-                                 reinterpret_cast<float4*>(xyz_out), counts_out, ctx->d_cnt, (ctx->collect_stats ? 1 : 0) | (ctx->phase_timing ? 2 : 0));
+                                 reinterpret_cast<float4*>(xyz_out), counts_out, ctx->d_cnt, (ctx->collect_stats ? 1 : 0) | (ctx->phase_timing ? 2 : 0) | (ctx->cas_unions ? 4 : 0));
         if (rc) return fail(ctx, GS_ECUDA, "fused kernel launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(rc)));
         return GS_OK;
     }
@@ -555,6 +556,7 @@ int gs_set_option(gs_ctx* ctx, int option, int value) {
         case GS_OPT_COLLECT_STATS: ctx->collect_stats = value != 0; return GS_OK;
         case GS_OPT_FORCE_STAGED: ctx->fused.disabled = value != 0; return GS_OK;
         case GS_OPT_PHASE_TIMING: ctx->phase_timing = value != 0; return GS_OK;
+        case GS_OPT_CAS_UNIONS: ctx->cas_unions = value != 0; return GS_OK;
         default: return fail(ctx, GS_EINVAL, "unknown option %d", option);
     }
 }

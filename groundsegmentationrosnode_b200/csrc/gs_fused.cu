@@ -212,6 +212,92 @@ __device__ __forceinline__ void uf16_unite(uint16_t* par, int a, int b) {
         if (atomicCAS(w, old, want) == old) return;
     }
 }
+// ---- explicit shared::cta accesses on 32-bit window addresses.  Plain C++ dereferences of pointers into the dynamic
+// shared array compile to LDS/STS on shared::cluster addresses (this kernel maps neighbour CTAs' shared memory), and in
+// divergent code the compiler re-derives the window base from SR_CgaCtaId (S2R) at every access.  The latency-bound
+// union-find loops use these instead, on a base address that is kept in a register.
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ unsigned lds_u16(unsigned a) {
+    unsigned short v;
+    asm volatile("ld.shared::cta.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u32(unsigned a) {
+    unsigned v;
+    asm volatile("ld.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u16(unsigned a, unsigned v) {
+    asm volatile("st.shared::cta.u16 [%0], %1;" ::"r"(a), "h"(static_cast<unsigned short>(v)) : "memory");
+}
+__device__ __forceinline__ unsigned cas_shared_u32(unsigned a, unsigned expect, unsigned want) {
+    unsigned old;
+    asm volatile("atom.shared::cta.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(a), "r"(expect), "r"(want) : "memory");
+    return old;
+}
+
+// uf16_* on a forest addressed by its shared-window byte address `par`
+__device__ __forceinline__ int uf16s_find(unsigned par, int x) {
+    for (;;) {
+        const int p = lds_u16(par + 2 * x) & 0x7fff;
+        if (p == x) return x;
+        const int gp = lds_u16(par + 2 * p) & 0x7fff;
+        if (gp == p) return p;
+        sts_u16(par + 2 * x, gp);
+        x = gp;
+    }
+}
+// roots of two nodes found in lock-step (independent walks: one shared-memory round trip per hop for both), no writes
+__device__ __forceinline__ void uf16s_roots2(unsigned par, int& a, int& b) {
+    int pa = lds_u16(par + 2 * a) & 0x7fff, pb = lds_u16(par + 2 * b) & 0x7fff;
+    while (pa != a || pb != b) {
+        a = pa;
+        b = pb;
+        pa = lds_u16(par + 2 * a) & 0x7fff;
+        pb = lds_u16(par + 2 * b) & 0x7fff;
+    }
+}
+// Concurrent union with a compare-and-swap (any thread of the CTA may work on any part of the forest).  The node whose
+// parent entry is rewritten is verified to be a root by the compare-and-swap itself and is always hung under a node of
+// higher priority, so the forest stays acyclic even when the other node has stopped being a root meanwhile.
+__device__ __forceinline__ void uf16s_unite_cas(unsigned par, int a, int b) {
+    uf16s_roots2(par, a, b);
+    for (;;) {
+        if (a == b) return;
+        if (uf16_prio(a) > uf16_prio(b)) { const int t = a; a = b; b = t; }  // a: lower priority, hangs under b
+        const unsigned w = par + 4 * (a >> 1);
+        const int sh = (a & 1) * 16;
+        const unsigned old = lds_u32(w);
+        if (static_cast<int>((old >> sh) & 0xffffu) == a) {
+            const unsigned want = (old & ~(0xffffu << sh)) | (static_cast<unsigned>(b) << sh);
+            if (cas_shared_u32(w, old, want) == old) return;
+            continue;  // the word changed (maybe only its other half): look again
+        }
+        a = uf16s_find(par, a);  // a stopped being a root
+        b = uf16s_find(par, b);
+    }
+}
+// Warp-synchronous union of one link per lane WITHOUT atomics, for links whose components no other warp touches (shared-
+// memory atomics cost ~4 cycles per LANE, SM-wide: a compare-and-swap per link was two thirds of the union stage).
+// Round: every active lane finds its two roots (reads only); lanes with different roots hang the root of lower priority
+// under the other with a plain 16-bit store; __syncwarp; repeat.  All finds of a round complete before its stores and
+// only roots are written, always towards higher priority: the forest stays acyclic, and when several lanes hang the same
+// root one store survives — the others see different roots again in the next round and retry.  Every round merges at
+// least one pair per contested root, so the loop ends.
+__device__ __forceinline__ void uf16s_unite_warp(unsigned par, bool act, int a, int b) {
+    for (;;) {
+        if (act) {
+            uf16s_roots2(par, a, b);
+            act = a != b;
+        }
+        if (!__any_sync(0xffffffffu, act)) return;
+        if (act) {
+            if (uf16_prio(a) > uf16_prio(b)) sts_u16(par + 2 * b, a);
+            else sts_u16(par + 2 * a, b);
+        }
+        __syncwarp();
+    }
+}
 __device__ __forceinline__ bool uf16_flag_root(uint16_t* par, int x) {  // returns true when the flag was newly set
     for (;;) {
         const int root = uf16_find(par, x);
@@ -594,6 +680,12 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
     // runs starting at the same row in neighbouring columns (the ground does) fall into different shared-memory banks.
     auto run_node = [=](int c, int rs) -> int { return c * H + ((rs + 2 * c) & (H - 1)); };  // H is a power of two (checked on the host)
 
+    // shared-window address of the dynamic shared array, laundered through an opaque move so that it stays in a register
+    unsigned smem_base32;
+    {
+        const unsigned t = smem_addr(smem_raw);
+        asm volatile("mov.u32 %0, %1;" : "=r"(smem_base32) : "r"(t));
+    }
     // ---- shared memory carve-up
     uint16_t* s_range = reinterpret_cast<uint16_t*>(smem_raw + off_range);
     uint16_t* s_tag = reinterpret_cast<uint16_t*>(smem_raw + off_tag);
@@ -606,6 +698,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
     unsigned* s_todo = reinterpret_cast<unsigned*>(s_angle);                 // [(CW - 1) * NWD]
     uint16_t* s_excl = reinterpret_cast<uint16_t*>(s_todo + static_cast<size_t>(CW) * NWD);  // [(CW - 1) * NWD + 1]
     uint16_t* s_qcw = s_excl + static_cast<size_t>(CW) * NWD + 2;                            // [(CW - 1) * NWD] column << 2 | word
+    uint16_t* s_task = s_qcw + static_cast<size_t>(CW) * NWD + 2 + 2 * ((H + 7) & ~7);       // after s_broot [2][Hp] (boundary stage): the link list of the union stage, up to the mask area
     unsigned* s_grp = s_rowmask + H * NG;                                                                  // [H][NG]
     uint16_t* s_mylist = reinterpret_cast<uint16_t*>(s_angle + MAX_BLOCKS);                                // [MAX_BLOCKS]
     unsigned char* misc = smem_raw + off_misc;
@@ -1031,15 +1124,32 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         // Unions go level by level (level k joins column groups of width 2^k across the boundaries b = 2^k - 1 mod 2^(k+1)),
         // which keeps the trees shallow; inside a level the links are dealt evenly to all threads through a prefix sum, so
         // every lane of a warp performs a union in every iteration.
+        // Unions are organised so that most of them need no atomics.  Columns are cut into groups of GW = 2^GWL columns (at
+        // least one group per warp).  Stage 1: a warp unites everything inside its group — no other warp touches those
+        // trees.  Stage 2: the boundaries between groups go level by level (level k joins blocks of 2^k columns across the
+        // boundaries c = 2^k - 1 mod 2^(k+1)); within a level every boundary joins its own two blocks, so again one warp
+        // per boundary works alone.  Links are listed boundary by boundary: first the boundaries inside groups (ascending),
+        // then the group boundaries in level order; q = (position of the boundary in that order) * NWD + word.
         int n_levels = 0;
         while ((1 << n_levels) < myCW) ++n_levels;
-        const int n_q = (myCW - 1) * NWD;  // (boundary in level order, word)
+        int GWL = 4;
+        while (GWL > 1 && ((myCW + (1 << GWL) - 1) >> GWL) < NT / 32) --GWL;
+        const int GW = 1 << GWL;
+        const int n_groups = (myCW + GW - 1) >> GWL;
+        const int n_ext = (myCW - 1) >> GWL;      // group boundaries: c = GW - 1 mod GW, c <= myCW - 2
+        const int n_int = (myCW - 1) - n_ext;     // boundaries inside groups
+        const int n_q = (myCW - 1) * NWD;
         auto level_count = [=](int k) -> int {
             const int first = (1 << k) - 1;
             return (myCW - 2 >= first) ? ((myCW - 2 - first) >> (k + 1)) + 1 : 0;
         };
-        auto boundary_of = [=](int p) -> int {  // p-th boundary in level order -> left column of the boundary
-            for (int k = 0;; ++k) {
+        auto boundary_of = [=](int p) -> int {  // p-th boundary in list order -> left column of the boundary
+            if (p < n_int) {
+                const int g = p / (GW - 1);
+                return (g << GWL) + (p - g * (GW - 1));
+            }
+            p -= n_int;
+            for (int k = GWL;; ++k) {
                 const int nk = level_count(k);
                 if (p < nk) return ((1 << k) - 1) + p * (2 << k);
                 p -= nk;
@@ -1094,57 +1204,86 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         }
         GS_PHASE(14);
         {
-            // Balanced passes over the links in level order: in a pass thread t takes the tasks [ta + t*per, ta + (t+1)*per).
-            // The low levels (94 % of the links, small trees) go first; the few links of the high levels, which join the
-            // big components and walk the deepest trees, are spread over all threads in passes of their own so that no
-            // thread gets a long serial chain of slow finds.
-            int q_cut[4];
-            {
-                int q = 0, k = 0;
-                for (; k < min(4, n_levels); ++k) q += level_count(k) * NWD;
-                q_cut[0] = 0;
-                q_cut[1] = q;
-                for (; k < min(6, n_levels); ++k) q += level_count(k) * NWD;
-                q_cut[2] = q;
-                q_cut[3] = n_q;
-            }
-            for (int pass = 0; pass < 3; ++pass) {
-                const int ta = s_excl[q_cut[pass]], tb = s_excl[q_cut[pass + 1]];
-                if (tb <= ta) continue;  // uniform
-                const int per = (tb - ta + NT - 1) / NT;
-                int task = ta + tid * per;
-                const int task_end = min(task + per, tb);
-                if (task < task_end) {
-                    int ql = q_cut[pass], qh = q_cut[pass + 1] - 1;  // largest q of the pass with s_excl[q] <= task
-                    while (ql < qh) {
-                        const int mid = (ql + qh + 1) >> 1;
-                        if (static_cast<int>(s_excl[mid]) <= task) ql = mid;
-                        else qh = mid - 1;
-                    }
-                    int q = ql;
+            auto at = [&](const void* ptr) -> unsigned { return smem_base32 + static_cast<unsigned>(reinterpret_cast<const unsigned char*>(ptr) - smem_raw); };
+            const unsigned a_task = at(s_task), a_qcw = at(s_qcw), a_par = at(s_par);
+            const unsigned a_runs = at(s_m32 + static_cast<size_t>(MK_S) * NWD * CW);  // MW(MK_S, w, c) = [w * CW + c]
+            // link t of the list -> the forest nodes of the two runs it joins
+            auto link_nodes = [&](int t_rel, int& na, int& nb) {
+                const unsigned tk = lds_u16(a_task + 2 * t_rel);
+                const int i = tk & 31;
+                const int cw = lds_u16(a_qcw + 2 * (tk >> 5)), w = cw & 3, c = cw >> 2;
+                const unsigned below = 0xffffffffu >> (31 - i);
+                // run starts of (32w + i, c) and (32w + i, c + 1): highest run-start bit at or below the row
+                int wa = w, wb = w;
+                unsigned ma = lds_u32(a_runs + 4 * (w * CW + c)) & below, mb = lds_u32(a_runs + 4 * (w * CW + c + 1)) & below;
+                while (ma == 0u) ma = lds_u32(a_runs + 4 * (--wa * CW + c));
+                while (mb == 0u) mb = lds_u32(a_runs + 4 * (--wb * CW + c + 1));
+                na = run_node(c, 32 * wa + 31 - __clz(ma));
+                nb = run_node(c + 1, 32 * wb + 31 - __clz(mb));
+            };
+            auto write_tasks = [&](int qb, int qe, int base) {
+                for (int q = qb + tid; q < qe; q += NT) {
                     unsigned word = s_todo[q];
-                    for (int k = task - static_cast<int>(s_excl[q]); k > 0; --k) word &= word - 1;
-                    int cw = s_qcw[q], w = cw & 3, c = cw >> 2;
-                    for (; task < task_end; ++task) {
-                        while (word == 0u) {
-                            ++q;
-                            word = s_todo[q];
-                            cw = s_qcw[q];
-                            w = cw & 3;
-                            c = cw >> 2;
-                        }
-                        const int i = __ffs(word) - 1;
+                    uint16_t* dst = s_task + (static_cast<int>(s_excl[q]) - base);
+                    while (word) {
+                        *dst++ = static_cast<uint16_t>((q << 5) | (__ffs(word) - 1));
                         word &= word - 1;
-                        const unsigned below = 0xffffffffu >> (31 - i);
-                        // run starts of (32w + i, c) and (32w + i, c + 1): highest run-start bit at or below the row
-                        int wa = w, wb = w;
-                        unsigned ma = MW(MK_S, w, c) & below, mb = MW(MK_S, w, c + 1) & below;
-                        while (ma == 0u) ma = MW(MK_S, --wa, c);
-                        while (mb == 0u) mb = MW(MK_S, --wb, c + 1);
-                        uf16_unite(s_par, run_node(c, 32 * wa + 31 - __clz(ma)), run_node(c + 1, 32 * wb + 31 - __clz(mb)));
                     }
                 }
+            };
+            const int task_cap = static_cast<int>((smem_raw + off_masks - reinterpret_cast<unsigned char*>(s_task)) / 2);
+            const int n_tasks = s_excl[n_q];
+            if (n_tasks <= task_cap && !(A.stats & 4)) {
+                // the whole list fits: warp-synchronous unions without atomics
+                write_tasks(0, n_q, 0);
                 __syncthreads();
+                auto warp_range = [&](int ta, int tb) {  // the whole warp unites the links [ta, tb), 32 at a time
+                    for (int t0 = ta; t0 < tb; t0 += 32) {
+                        const bool act = t0 + lane < tb;
+                        int na = 0, nb = 0;
+                        if (act) link_nodes(t0 + lane, na, nb);
+                        uf16s_unite_warp(a_par, act, na, nb);
+                    }
+                };
+                for (int g = warp; g < n_groups; g += NT / 32) {
+                    const int p0 = g * (GW - 1), p1 = min(p0 + GW - 1, n_int);
+                    warp_range(s_excl[p0 * NWD], s_excl[p1 * NWD]);
+                }
+                __syncthreads();
+                int p_base = n_int;
+                for (int k = GWL; k < n_levels; ++k) {  // uniform
+                    const int nk = level_count(k);
+                    for (int p = warp; p < nk; p += NT / 32) warp_range(s_excl[(p_base + p) * NWD], s_excl[(p_base + p + 1) * NWD]);
+                    p_base += nk;
+                    __syncthreads();
+                }
+            } else {
+                // more links than the list holds (or GS_OPT_DEBUG_CAS_UNIONS): chunks of q, thread t takes the links t, t + NT, ...
+                // of a chunk and unites with compare-and-swap
+                int qb = 0;
+                while (qb < n_q) {  // uniform
+                    const int base = s_excl[qb];
+                    int qe = n_q;
+                    if (n_tasks - base > task_cap) {
+                        int ql = qb + 1, qh = n_q;  // largest qe with excl[qe] - base <= cap (a word holds at most 32 <= cap links)
+                        while (ql < qh) {
+                            const int mid = (ql + qh + 1) >> 1;
+                            if (static_cast<int>(s_excl[mid]) - base <= task_cap) ql = mid;
+                            else qh = mid - 1;
+                        }
+                        qe = ql;
+                    }
+                    write_tasks(qb, qe, base);
+                    __syncthreads();
+                    const int n_t = static_cast<int>(s_excl[qe]) - base;
+                    for (int t = tid; t < n_t; t += NT) {
+                        int na, nb;
+                        link_nodes(t, na, nb);
+                        uf16s_unite_cas(a_par, na, nb);
+                    }
+                    __syncthreads();
+                    qb = qe;
+                }
             }
         }
         GS_PHASE(15);

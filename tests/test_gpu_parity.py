@@ -320,6 +320,35 @@ def test_batch_device_and_host_match_per_frame_oracle(ctxs, oracle, staged):
         assert np.array_equal(h_xyz[out_offs[f]:out_offs[f + 1]], w["xyz"])
 
 
+@pytest.mark.parametrize("preset", [P.GS_PRESET_VLP16, P.GS_PRESET_HDL64E_2048, P.GS_PRESET_OS1_128])
+def test_fused_union_paths_agree_with_oracle(oracle, preset):
+    """The fused kernel has two union paths: warp-synchronous without atomics (the link list fits in shared memory) and
+    compare-and-swap on chunks of the list (it does not).  Both must give the oracle's no-ground image on a batch."""
+    import torch
+
+    p = P.preset(preset)
+    H, W = p.shape
+    pool, offs = synth.make_pool(p, 6, seed0=synth.SEED0 + 900)
+    pts, offsets = synth.tile_pool(pool, offs, 40)
+    F = len(offsets) - 1
+    want = [oracle.process_frame(p, pool[offs[i]:offs[i + 1]]) for i in range(6)]
+    d_pts = torch.from_numpy(pts).cuda()
+    for cas in (0, 1):
+        with capi.Context(p) as ctx:
+            ctx.set_option(capi.GS_OPT_CAS_UNIONS, cas)
+            d_res = torch.zeros((F, H, W), dtype=torch.int16, device="cuda")
+            d_cnt = torch.zeros(F, dtype=torch.int32, device="cuda")
+            torch.cuda.synchronize()
+            l0 = ctx.stats().kernel_launches
+            ctx.process_batch_device(d_pts.data_ptr(), offsets, F, 0, 0, d_res.data_ptr(), 0, d_cnt.data_ptr())
+            ctx.synchronize()
+            assert ctx.stats().kernel_launches - l0 == 1, "the fused kernel should have taken this batch"
+            res = d_res.cpu().numpy().view(np.uint16)
+            for f in range(F):
+                assert np.array_equal(res[f], want[f % 6]["no_ground"]), "frame %d, cas=%d" % (f, cas)
+                assert int(d_cnt[f]) == want[f % 6]["xyz"].shape[0]
+
+
 def test_set_params_recomputes_derived(ctxs, oracle):
     """gs_set_params replaces Alfa_GS::UpdateSegmentationSettings (alfa_gs.cpp:1122-1136) and, unlike it, refreshes
     the derived values."""
