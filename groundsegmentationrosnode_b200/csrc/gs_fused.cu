@@ -279,23 +279,33 @@ __device__ __forceinline__ void uf16s_unite_cas(unsigned par, int a, int b) {
 }
 // Warp-synchronous union of one link per lane WITHOUT atomics, for links whose components no other warp touches (shared-
 // memory atomics cost ~4 cycles per LANE, SM-wide: a compare-and-swap per link was two thirds of the union stage).
-// Round: every active lane finds its two roots (reads only); lanes with different roots hang the root of lower priority
-// under the other with a plain 16-bit store; __syncwarp; repeat.  All finds of a round complete before its stores and
-// only roots are written, always towards higher priority: the forest stays acyclic, and when several lanes hang the same
-// root one store survives — the others see different roots again in the next round and retry.  Every round merges at
-// least one pair per contested root, so the loop ends.
+// Round: an active lane finds its two roots (reads only) and, if they differ, hangs the root of lower priority under the
+// other with a plain 16-bit store; __syncwarp; the lane then checks that its store survived (another lane may have hung
+// the same root elsewhere, or overwritten it meanwhile) and retries if not.  Parents always have a higher priority than
+// their children, so the forest stays acyclic whatever the interleaving; a hook can only be lost to another store of the
+// same round, which its owner detects after the barrier — links found united rest on hooks whose owners make them stick.
+// There is no path compression here: a shortcut taken through a hook that is lost later would bypass a subtree.
 __device__ __forceinline__ void uf16s_unite_warp(unsigned par, bool act, int a, int b) {
     for (;;) {
+        int lo = 0, hi = 0;
         if (act) {
             uf16s_roots2(par, a, b);
             act = a != b;
+            if (act) {
+                const bool a_high = uf16_prio(a) > uf16_prio(b);
+                lo = a_high ? b : a;
+                hi = a_high ? a : b;
+                sts_u16(par + 2 * lo, hi);
+            }
         }
         if (!__any_sync(0xffffffffu, act)) return;
-        if (act) {
-            if (uf16_prio(a) > uf16_prio(b)) sts_u16(par + 2 * b, a);
-            else sts_u16(par + 2 * a, b);
-        }
         __syncwarp();
+        if (act) {
+            act = (lds_u16(par + 2 * lo) & 0x7fff) != static_cast<unsigned>(hi);
+            a = lo;
+            b = hi;
+        }
+        if (!__any_sync(0xffffffffu, act)) return;
     }
 }
 __device__ __forceinline__ bool uf16_flag_root(uint16_t* par, int x) {  // returns true when the flag was newly set
@@ -1126,10 +1136,9 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         // every lane of a warp performs a union in every iteration.
         // Unions are organised so that most of them need no atomics.  Columns are cut into groups of GW = 2^GWL columns (at
         // least one group per warp).  Stage 1: a warp unites everything inside its group — no other warp touches those
-        // trees.  Stage 2: the boundaries between groups go level by level (level k joins blocks of 2^k columns across the
-        // boundaries c = 2^k - 1 mod 2^(k+1)); within a level every boundary joins its own two blocks, so again one warp
-        // per boundary works alone.  Links are listed boundary by boundary: first the boundaries inside groups (ascending),
-        // then the group boundaries in level order; q = (position of the boundary in that order) * NWD + word.
+        // trees.  Stage 2: the few links across group boundaries are united by all threads with compare-and-swap.  Links are
+        // listed boundary by boundary: first the boundaries inside groups (ascending), then the group boundaries in level
+        // order (low levels, small trees, first); q = (position of the boundary in that order) * NWD + word.
         int n_levels = 0;
         while ((1 << n_levels) < myCW) ++n_levels;
         int GWL = 4;
@@ -1250,13 +1259,13 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                     warp_range(s_excl[p0 * NWD], s_excl[p1 * NWD]);
                 }
                 __syncthreads();
-                int p_base = n_int;
-                for (int k = GWL; k < n_levels; ++k) {  // uniform
-                    const int nk = level_count(k);
-                    for (int p = warp; p < nk; p += NT / 32) warp_range(s_excl[(p_base + p) * NWD], s_excl[(p_base + p + 1) * NWD]);
-                    p_base += nk;
-                    __syncthreads();
+                // stage 2: the links of the group boundaries (a few per cent of all), one per thread, with compare-and-swap
+                for (int t = static_cast<int>(s_excl[n_int * NWD]) + tid; t < n_tasks; t += NT) {
+                    int na, nb;
+                    link_nodes(t, na, nb);
+                    uf16s_unite_cas(a_par, na, nb);
                 }
+                __syncthreads();
             } else {
                 // more links than the list holds (or GS_OPT_DEBUG_CAS_UNIONS): chunks of q, thread t takes the links t, t + NT, ...
                 // of a chunk and unites with compare-and-swap
