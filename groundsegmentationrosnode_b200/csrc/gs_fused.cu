@@ -257,6 +257,17 @@ __device__ __forceinline__ void uf16s_roots2(unsigned par, int& a, int& b) {
         pb = lds_u16(par + 2 * b) & 0x7fff;
     }
 }
+// same walk; returns the raw root entries (bit 15 = ground flag)
+__device__ __forceinline__ void uf16s_root_entries2(unsigned par, int a, int b, unsigned& ea, unsigned& eb) {
+    ea = lds_u16(par + 2 * a);
+    eb = lds_u16(par + 2 * b);
+    while (static_cast<int>(ea & 0x7fff) != a || static_cast<int>(eb & 0x7fff) != b) {
+        a = ea & 0x7fff;
+        b = eb & 0x7fff;
+        ea = lds_u16(par + 2 * a);
+        eb = lds_u16(par + 2 * b);
+    }
+}
 // Concurrent union with a compare-and-swap (any thread of the CTA may work on any part of the forest).  The node whose
 // parent entry is rewritten is verified to be a root by the compare-and-swap itself and is always hung under a node of
 // higher priority, so the forest stays acyclic even when the other node has stopped being a root meanwhile.
@@ -1377,29 +1388,52 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             }
         }
         GS_PHASE(10);
-        // read the ground mask of every unit out of the forest
-        for (int u = tid; u < n_units; u += NT) {
-            const int w = u / myCW, c = u - w * myCW;
-            const unsigned valid = MW(MK_VALID, w, c);
-            unsigned runs = MW(MK_S, w, c);
-            unsigned g = 0;
-            // pixels of a run that started in a lower word: the non-empty pixels below the first run start of this word
-            const unsigned head = valid & (runs ? ((runs & (0u - runs)) - 1u) : 0xffffffffu);
-            if (head) {
-                int wa = w;
-                unsigned ma = 0;
-                while (ma == 0u) ma = MW(MK_S, --wa, c);
-                const int root = uf16_find(s_par, run_node(c, 32 * wa + 31 - __clz(ma)));
-                if (s_par[root] & 0x8000u) g = head;
+        // read the ground mask of every unit out of the forest, two runs at a time (lock-step walks)
+        {
+            auto at = [&](const void* ptr) -> unsigned { return smem_base32 + static_cast<unsigned>(reinterpret_cast<const unsigned char*>(ptr) - smem_raw); };
+            const unsigned a_par = at(s_par);
+            const unsigned a_runs = at(s_m32 + static_cast<size_t>(MK_S) * NWD * CW), a_valid = at(s_m32 + static_cast<size_t>(MK_VALID) * NWD * CW);
+            for (int u = tid; u < n_units; u += NT) {
+                const int w = u / myCW, c = u - w * myCW;
+                const unsigned valid = lds_u32(a_valid + 4 * (w * CW + c));
+                unsigned runs = lds_u32(a_runs + 4 * (w * CW + c));
+                unsigned g = 0;
+                // pixels of a run that started in a lower word: the non-empty pixels below the first run start of this word
+                unsigned head = valid & (runs ? ((runs & (0u - runs)) - 1u) : 0xffffffffu);
+                auto next = [&](int& nd, unsigned& mk) -> bool {
+                    if (head) {
+                        int wa = w;
+                        unsigned ma = 0;
+                        while (ma == 0u) ma = lds_u32(a_runs + 4 * (--wa * CW + c));
+                        nd = run_node(c, 32 * wa + 31 - __clz(ma));
+                        mk = head;
+                        head = 0;
+                        return true;
+                    }
+                    if (runs) {
+                        const unsigned bit = runs & (0u - runs);
+                        runs ^= bit;
+                        const unsigned upto_next = runs ? ((runs & (0u - runs)) - 1u) : 0xffffffffu;
+                        nd = run_node(c, 32 * w + __ffs(bit) - 1);
+                        mk = valid & upto_next & ~(bit - 1u);
+                        return true;
+                    }
+                    return false;
+                };
+                int n0 = 0, n1 = 0;
+                unsigned m0 = 0, m1 = 0;
+                while (next(n0, m0)) {
+                    if (!next(n1, m1)) {
+                        n1 = n0;
+                        m1 = 0;
+                    }
+                    unsigned e0, e1;
+                    uf16s_root_entries2(a_par, n0, n1, e0, e1);
+                    if (e0 & 0x8000u) g |= m0;
+                    if (e1 & 0x8000u) g |= m1;
+                }
+                MW(MK_G, w, c) = g;
             }
-            while (runs) {
-                const unsigned bit = runs & (0u - runs);
-                runs ^= bit;
-                const unsigned upto_next = runs ? ((runs & (0u - runs)) - 1u) : 0xffffffffu;
-                const int root = uf16_find(s_par, run_node(c, 32 * w + __ffs(bit) - 1));
-                if (s_par[root] & 0x8000u) g |= valid & upto_next & ~(bit - 1u);
-            }
-            MW(MK_G, w, c) = g;
         }
         __syncthreads();
 
@@ -1489,6 +1523,17 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         __syncthreads();
 
         GS_PHASE(13);
+        // the next frame of this cluster: pull the sampled points of the block dealing (P0) into L2 while the output streams
+        // out, so that the top of the next frame does not wait a full HBM round trip twice (offsets, then samples)
+        {
+            const int fn = f + n_clusters;
+            if (fn < A.frames) {
+                const long long begn = A.offsets[fn];
+                const int Nn = static_cast<int>(A.offsets[fn + 1] - begn);
+                const float4* ptsn = A.points + begn;
+                for (int i = 32 + 64 * tid; i < Nn; i += 64 * NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptsn + i));
+            }
+        }
         // ================================================================================ B: no-ground image + cloud
         {
             uint16_t* res = A.res_out ? A.res_out + static_cast<size_t>(f) * kp.P : nullptr;

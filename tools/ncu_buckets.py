@@ -18,8 +18,8 @@ frames = int(sys.argv[2]) if len(sys.argv) > 2 else 296
 src = open(os.path.join(T.ROOT, "groundsegmentationrosnode_b200", "csrc", "gs_fused.cu")).read().splitlines()
 marks = [(i + 1, int(re.search(r"GS_PHASE\((\d+)\)", l).group(1))) for i, l in enumerate(src) if re.match(r"\s+GS_PHASE\(\d+\);", l)]
 kernel_start = [i + 1 for i, l in enumerate(src) if "__global__ void __launch_bounds__(NT" in l][0]
-names = {0: "clear+deal", 1: "project rounds", 2: "wait rounds", 3: "remote", 4: "angle walk", 5: "wait angles", 6: "edges+seeds", 7: "wait edges",
-         8: "unions", 9: "boundary rounds", 10: "readout", 11: "label/dilate/transpose", 12: "wait rowcounts", 13: "output", 14: "flatten", 15: "seed flags"}
+names = {0: "clear+deal", 1: "project rounds", 2: "wait rounds", 3: "remote+compact", 4: "angle walk", 5: "wait angles", 6: "edges+seeds", 7: "wait edges",
+         8: "link scan", 9: "boundary rounds", 10: "readout", 11: "label/dilate/transpose", 12: "wait rowcounts", 13: "output", 14: "unions", 15: "seed flags"}
 
 
 def bucket(l):
