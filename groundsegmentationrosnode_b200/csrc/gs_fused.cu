@@ -583,38 +583,45 @@ __device__ __forceinline__ float rcp_ftz(float a) {
     return r;
 }
 
-// Lean version of project_fast (same certificates, ~40 % fewer instructions; returns 0 = pixel found, 1 = dropped,
-// 2 = undecided -> project_point_d):
-//  * range: fused double sum of squares, MUFU rsqrt seed (relative error e0 < 2.2e-7) and ONE Heron step
-//    r + (s2 - r*r) * (0.5 * seed), relative error 1.5 e0^2 < 7e-14, i.e. < 6e-9 of an encoded-range unit.  The encoded
-//    value is taken in 2^-14 fixed point from one DFMA + F2I; a fractional part of 0 or 16383 (within 6.1e-5 of an
-//    integer, 10^4 x the error) or a value outside (1, 65535) — the range gates of alfa_gs.cpp:261 map to exactly 1 and
-//    65535 — leaves the decision to the cold path below / the exact evaluation.
-//  * altitude / azimuth: float atan as in project_fast with the raw MUFU rcp / rsqrt (flush-to-zero forms: the operands
-//    are certified > 1e-15 first), gates and cell edges tested on the fixed-point cell coordinates with the same margins.
-__device__ __forceinline__ int project_lean(const FusedArgs& A, float fx, float fy, float fz, int* row_out, int* col_out, unsigned* enc_out) {
+// Lean, BRANCH-FREE version of project_fast (same certificates, ~40 % fewer instructions).  Being straight-line code,
+// the evaluations of two points interleave in the instruction stream, which hides the latency of the FP64 chain.
+//  * range: double sum of squares, MUFU rsqrt seed of the float sum of squares (relative error e0 < 2.5e-7) and ONE Heron
+//    step r + (s2 - r*r) * (0.5 * seed): relative error 1.5 e0^2 < 1e-13, i.e. < 1e-8 of an encoded-range unit.  The
+//    encoded value is taken in 2^-14 fixed point from one DFMA + F2I; a fractional part of 0 or 16383 (within 6.1e-5 of
+//    an integer) or a value outside (1, 65535) — the range gates of alfa_gs.cpp:261 map to exactly 1 and 65535 — is not
+//    decided here.
+//  * altitude / azimuth: float atan as in project_fast with the raw MUFU rcp / rsqrt (flush-to-zero forms; operands
+//    below 1e-15 are not decided here), gates and cell edges tested on the fixed-point cell coordinates with the same
+//    margins (>= 4x the error budget).
+// ok = pixel (row, col, enc) certified.  Everything else — outside a gate, within a margin of a gate or an edge, the
+// flat-index alias column W, y == 0, non-finite — is classified by project_undecided / project_point_d.
+struct Lean {
+    int row, col;
+    unsigned enc;
+    bool ok;
+    float alt;     // for project_undecided
+    double range;  // for project_undecided
+};
+__device__ __forceinline__ Lean project_lean(const FusedArgs& A, float fx, float fy, float fz) {
     const KParams& kp = A.kp;
+    Lean o;
     const double x = fx, y = fy, z = fz;
     const double s2 = __fma_rn(x, x, __fma_rn(y, y, __dmul_rn(z, z)));
-    const float seed = rsqrt_ftz(__double2float_rn(s2));
-    const double r0 = __dmul_rn(s2, static_cast<double>(seed));
-    const double range = __fma_rn(__fma_rn(-r0, r0, s2), static_cast<double>(__fmul_rn(0.5f, seed)), r0);
-    const int ufix = __double2int_rz(__fma_rn(range, A.u_scale, A.u_c0));  // NaN -> 0, overflow saturates: both fail the test below
-    const unsigned ufrac = static_cast<unsigned>(ufix) & ((1u << UB) - 1u);
-    if (static_cast<unsigned>(ufix - ((1 << UB) + 1)) > static_cast<unsigned>((65534 << UB) - 2) || ufrac - 1u > (1u << UB) - 3u) {
-        // cold: outside the gates by more than 1e-9 m -> dropped (alfa_gs.cpp:261); anything else -> exact evaluation
-        if (range < A.range_lo_out || range > A.range_hi_out) return 1;
-        return 2;
-    }
     const float h2 = __fmaf_rn(fx, fx, __fmul_rn(fy, fy));
-    if (fy == 0.0f || !(h2 > 1e-30f)) return 2;  // atan2(-0.0, x < 0) = -pi in the reference (Q3); flush-to-zero forms below need h2 > 0
+    const double rd = static_cast<double>(rsqrt_ftz(__fmaf_rn(fz, fz, h2)));
+    const double r0 = __dmul_rn(s2, rd);
+    o.range = __fma_rn(__fma_rn(-r0, r0, s2), __dmul_rn(0.5, rd), r0);
+    const int ufix = __double2int_rz(__fma_rn(o.range, A.u_scale, A.u_c0));  // NaN -> 0, overflow saturates: both fail the test below
+    const unsigned ufrac = static_cast<unsigned>(ufix) & ((1u << UB) - 1u);
+    const bool range_ok = static_cast<unsigned>(ufix - ((1 << UB) + 1)) <= static_cast<unsigned>((65534 << UB) - 2) && ufrac - 1u <= (1u << UB) - 3u;
+    const bool xy_ok = fy != 0.0f && h2 > 1e-30f;  // atan2(-0.0, x < 0) = -pi in the reference (Q3); the flush-to-zero forms need h2 > 0
     // altitude = atan2(z, hypot(x, y))
     const float az = fabsf(fz);
     const float h = __fmul_rn(h2, rsqrt_ftz(h2));
     float t = atan01(__fmul_rn(fminf(az, h), rcp_ftz(fmaxf(az, h))));
     if (az > h) t = 1.57079632679489662f - t;
-    const float alt = __uint_as_float(__float_as_uint(t) | (__float_as_uint(fz) & 0x80000000u));
-    const int altfix = __float2int_rn(__fmul_rn(alt, A.alt_to_fix));
+    o.alt = __uint_as_float(__float_as_uint(t) | (__float_as_uint(fz) & 0x80000000u));
+    const int altfix = __float2int_rn(__fmul_rn(o.alt, A.alt_to_fix));
     const int rowfix = A.row0_fix - altfix;
     const unsigned rfrac = static_cast<unsigned>(rowfix) & ((1u << FB) - 1u);
     // azimuth in [0, 2 pi): octant reduction, reflections in exact fixed point
@@ -625,25 +632,24 @@ __device__ __forceinline__ int project_lean(const FusedArgs& A, float fx, float 
     if (fy < 0.0f) c = 4 * A.quarter_fix - c;
     const int colfix = c + A.col_half_fix;
     const unsigned cfrac = static_cast<unsigned>(colfix) & ((1u << FB) - 1u);
-    const int row = rowfix >> FB;
-    int col = colfix >> FB;
+    o.row = rowfix >> FB;
+    o.col = colfix >> FB;
+    o.enc = static_cast<unsigned>(ufix) >> UB;
     const unsigned rm = static_cast<unsigned>(A.row_margin), cm = static_cast<unsigned>(A.col_margin);
     const bool gate_ok = static_cast<unsigned>(altfix - A.alt_gate_lo) <= static_cast<unsigned>(A.alt_gate_span);
     const bool edges_ok = rfrac - rm <= (1u << FB) - 2u * rm && cfrac - cm <= (1u << FB) - 2u * cm;
-    const bool box_ok = static_cast<unsigned>(row) < static_cast<unsigned>(kp.H) && static_cast<unsigned>(col) <= static_cast<unsigned>(A.col_limit);
-    if (!(gate_ok && edges_ok && box_ok)) {
-        // cold: certainly outside the altitude gates (alfa_gs.cpp:269) -> dropped; within a margin of a gate or an edge -> exact
-        if (alt < A.alt_lo - 1e-6f || alt > A.alt_hi + 1e-6f) return 1;
-        return 2;
-    }
-    if (col == kp.W) {  // only the alfa_gs variant gets here (col_limit = W)
-        if (A.col_wrap) col = 0;                  // GS_COL_WRAP
-        else if (row == kp.H - 1) return 1;       // Q2: flat index past the end of the image
-    }
-    *row_out = row;
-    *col_out = col;
-    *enc_out = static_cast<unsigned>(ufix) >> UB;
-    return 0;
+    // col < W: the alias column W of the alfa_gs variant (Q2) is left to the exact path
+    const bool box_ok = static_cast<unsigned>(o.row) < static_cast<unsigned>(kp.H) && static_cast<unsigned>(o.col) < static_cast<unsigned>(kp.W);
+    o.ok = range_ok && xy_ok && gate_ok && edges_ok && box_ok;
+    return o;
+}
+// a point project_lean did not certify: 1 = certainly dropped by a gate (alfa_gs.cpp:261, :269), 2 = exact evaluation
+__device__ __forceinline__ int project_undecided(const FusedArgs& A, const Lean& o, float fy, float h2ok) {
+    if (o.range < A.range_lo_out || o.range > A.range_hi_out) return 1;  // outside the range gates by more than 1e-9 m
+    if (!(o.range > A.range_lo_in && o.range < A.range_hi_in)) return 2;  // within 1e-9 m of a gate, or not finite
+    if (fy == 0.0f || !(h2ok > 1e-30f)) return 2;                         // the float altitude is not meaningful
+    if (o.alt < A.alt_lo - 1e-6f || o.alt > A.alt_hi + 1e-6f) return 1;   // outside the altitude gates by more than 1e-6 rad
+    return 2;
 }
 
 // cheap column estimate used only to deal point blocks to CTAs (any answer is correct, a good one is fast)
@@ -836,28 +842,31 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                 pb = i0 + 32 < N ? __ldcs(pts + i0 + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
                 return i0;
             };
-            auto place = [&](const float4 p4, const int i) {
+            auto place = [&](const float4 p4, const int i, const Lean& L) {
                 unsigned k = 0x80000000u | lane;  // owner << 16 | slab address; this value is unique per lane: never matches
                 unsigned val = 0;                 // g << 16 | encoded range
-                int row = -1, col = -1;
-                unsigned enc = 0;
+                int row = L.row, col = L.col;
+                unsigned enc = L.enc;
                 int st = 1;
                 if (i < N) {
-                    st = A.use_fast ? project_lean(A, p4.x, p4.y, p4.z, &row, &col, &enc) : 2;
-                    if (st == 2 || stats1) {
-                        // exact evaluation: the undecided points, and every point when statistics are collected
-                        const Proj pr = project_point_d(A.kp_dev, p4.x, p4.y, p4.z);
-                        if (stats1) {
-                            if (st == 2) GS_STAT(ST_FALLBACK);
-                            else if ((st == 1) != (pr.row < 0) || (st == 0 && (row != pr.row || col != pr.col || enc != pr.enc))) GS_STAT(ST_MISMATCH);
-                            if (pr.row < 0) GS_STAT(ST_DROPPED);
-                            else if (pr.near_edge) GS_STAT(ST_NEAR);
-                        }
-                        if (st == 2) {
-                            row = pr.row;
-                            col = pr.col;
-                            enc = pr.enc;
-                            st = pr.row < 0 ? 1 : 0;
+                    st = 0;
+                    if (!L.ok || !A.use_fast || stats1) {
+                        // not certified: a gate drop, or the exact evaluation (every point when statistics are collected)
+                        st = A.use_fast ? (L.ok ? 0 : project_undecided(A, L, p4.y, __fmaf_rn(p4.x, p4.x, __fmul_rn(p4.y, p4.y)))) : 2;
+                        if (st == 2 || stats1) {
+                            const Proj pr = project_point_d(A.kp_dev, p4.x, p4.y, p4.z);
+                            if (stats1) {
+                                if (st == 2) GS_STAT(ST_FALLBACK);
+                                else if ((st == 1) != (pr.row < 0) || (st == 0 && (row != pr.row || col != pr.col || enc != pr.enc))) GS_STAT(ST_MISMATCH);
+                                if (pr.row < 0) GS_STAT(ST_DROPPED);
+                                else if (pr.near_edge) GS_STAT(ST_NEAR);
+                            }
+                            if (st == 2) {
+                                row = pr.row;
+                                col = pr.col;
+                                enc = pr.enc;
+                                st = pr.row < 0 ? 1 : 0;
+                            }
                         }
                     }
                 }
@@ -907,8 +916,9 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                 const float4 pa = na, pb = nb4;
                 const int i0 = ni;
                 if (u + NT / 32 < n_punits) ni = load_unit(u + NT / 32, na, nb4);
-                place(pa, i0);
-                place(pb, i0 + 32);
+                const Lean La = project_lean(A, pa.x, pa.y, pa.z), Lb = project_lean(A, pb.x, pb.y, pb.z);  // straight-line: the two interleave
+                place(pa, i0, La);
+                place(pb, i0 + 32, Lb);
             }
         }
         GS_PHASE(2);
