@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-from .params import (GS_ECUDA, GS_EINVAL, GS_OK, GsDerived, GsParams, GsStats)
+from .params import (GS_ECUDA, GS_EINVAL, GS_OK, GsDerived, GsEval, GsParams, GsStats)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgs_b200.so")
@@ -26,7 +26,7 @@ EXPORTS = [
     "gs_last_error", "gs_project", "gs_angle_image", "gs_smooth", "gs_repair_gaps", "gs_erase_ground",
     "gs_label_one_component", "gs_label_components", "gs_backproject", "gs_process_frame", "gs_process_batch_device",
     "gs_process_batch_host", "gs_synchronize", "gs_unpack_points", "gs_process_cloud2", "gs_pack_cloud_xyzrgb",
-    "gs_get_camera_info",
+    "gs_get_camera_info", "gs_create_labeled_range_image", "gs_evaluate",
 ]
 
 
@@ -88,6 +88,8 @@ def load(build_if_missing=False):
                                     C.POINTER(C.c_uint32)]
     L.gs_pack_cloud_xyzrgb.argtypes = [C.c_void_p, f32p, C.c_uint32, vp]
     L.gs_get_camera_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+    L.gs_create_labeled_range_image.argtypes = [C.c_void_p, vp, C.c_size_t, u16p]
+    L.gs_evaluate.argtypes = [C.c_void_p, u16p, u16p, u16p, C.POINTER(GsEval)]
     _lib = L
     return L
 
@@ -294,6 +296,22 @@ class Context:
         K = (C.c_double * 9)()
         self._ck(self._L.gs_get_camera_info(self._h, C.byref(h), C.byref(w), K))
         return h.value, w.value, [float(x) for x in K]
+
+    # ---- evaluation
+    def create_labeled_range_image(self, points32):
+        """Alfa_GS::CreateLabeledRangeImage on 32-byte pcl::PointXYZRGB records (uint8 array [n, 32])."""
+        H, W = self.shape
+        a = np.ascontiguousarray(points32, dtype=np.uint8).reshape(-1, 32)
+        out = np.empty((H, W), np.uint16)
+        self._ck(self._L.gs_create_labeled_range_image(self._h, _ptr(a), a.shape[0], _ptr(out)))
+        return out
+
+    def evaluate(self, og_range, seg_range, labeled_range):
+        """Per-frame counters and IoU_g / Recall_g / Recall_mo of Alfa_GS::CheckNumberOfDetectedRIdGnd."""
+        out = GsEval()
+        imgs = [np.ascontiguousarray(x, dtype=np.uint16) for x in (og_range, seg_range, labeled_range)]
+        self._ck(self._L.gs_evaluate(self._h, _ptr(imgs[0]), _ptr(imgs[1]), _ptr(imgs[2]), C.byref(out)))
+        return out
 
     # ---- batch API
     def process_batch_device(self, d_points, h_offsets, n_frames, d_range=0, d_angle=0, d_no_ground=0, d_xyz4=0, d_counts=0):

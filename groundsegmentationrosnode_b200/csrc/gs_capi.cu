@@ -594,6 +594,59 @@ int gs_reset_stats(gs_ctx* ctx) {
 
 const char* gs_last_error(const gs_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
+int gs_create_labeled_range_image(gs_ctx* ctx, const void* points_xyzrgb32, size_t n_points, uint16_t* labeled_out) {
+    if (!ctx || !labeled_out || (!points_xyzrgb32 && n_points)) return fail(ctx, GS_EINVAL, "gs_create_labeled_range_image: bad arguments");
+    cudaSetDevice(ctx->device);
+    int rc;
+    const size_t raw = (n_points * 32 + 15) / 16 * 16;
+    if ((rc = ensure_stage(ctx)) || (rc = ensure_points(ctx, raw + label_image_scratch_bytes(n_points)))) return rc;
+    unsigned char* base = static_cast<unsigned char*>(ctx->d_points);
+    uint8_t* flags = base + raw;
+    const size_t chunks = (n_points + 255) / 256;
+    uint8_t* summary = flags + (n_points + 15) / 16 * 16;
+    int* flat = reinterpret_cast<int*>(summary + (chunks + 15) / 16 * 16);
+    if (n_points) CU(cudaMemcpyAsync(base, points_xyzrgb32, n_points * 32, cudaMemcpyHostToDevice, ctx->stream));
+    launch_label_image(launch_of(ctx), ctx->kp, base, n_points, flags, flat, summary, ctx->d_a);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(labeled_out, ctx->d_a, static_cast<size_t>(ctx->kp.P) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GS_OK;
+}
+
+int gs_evaluate(gs_ctx* ctx, const uint16_t* og_range, const uint16_t* seg_range, const uint16_t* labeled_range, gs_eval* out) {
+    if (!ctx || !og_range || !seg_range || !labeled_range || !out) return fail(ctx, GS_EINVAL, "gs_evaluate: bad arguments");
+    cudaSetDevice(ctx->device);
+    int rc;
+    if ((rc = ensure_stage(ctx))) return rc;
+    const size_t bytes = static_cast<size_t>(ctx->kp.P) * 2;
+    unsigned long long* d9 = reinterpret_cast<unsigned long long*>(ctx->d_lab32);  // P * 4 bytes >= 72
+    CU(cudaMemcpyAsync(ctx->d_a, og_range, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_b, seg_range, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_c, labeled_range, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(d9, 0, 9 * sizeof(unsigned long long), ctx->stream));
+    launch_evaluate(launch_of(ctx), ctx->kp, ctx->d_a, ctx->d_b, ctx->d_c, d9);
+    CU(cudaGetLastError());
+    unsigned long long h9[9];
+    CU(cudaMemcpyAsync(h9, d9, sizeof(h9), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    out->points = h9[0];
+    out->labeled_gnd = h9[1];
+    out->labeled_obst = h9[2];
+    out->seg_gnd = h9[3];
+    out->true_positive = h9[4];
+    out->false_positive = h9[5];
+    out->true_negative = h9[6];
+    out->false_negative = h9[7];
+    out->true_detected_obst = h9[8];
+    // the reference counts in float (alfa_gs.cpp:834): increments stop at 2^24
+    auto as_float_counter = [](unsigned long long v) { return static_cast<float>(std::min<unsigned long long>(v, 16777216ull)); };
+    const float tp = as_float_counter(h9[4]), fp = as_float_counter(h9[5]), tn = as_float_counter(h9[6]), fn = as_float_counter(h9[7]);
+    out->iou_g = (tp / (tp + fp + fn)) * 100;   // :885
+    out->recall_g = (tp / (tp + fn)) * 100;     // :886
+    out->recall_mo = (tn / (tn + fp)) * 100;    // :887
+    return GS_OK;
+}
+
 int gs_synchronize(gs_ctx* ctx) {
     if (!ctx) return GS_EINVAL;
     cudaSetDevice(ctx->device);

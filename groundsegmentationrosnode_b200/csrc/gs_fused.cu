@@ -39,7 +39,6 @@ namespace gs {
 
 namespace {
 
-constexpr int NPT = 4;          // points per thread per round
 constexpr int BLK = 256;        // points per dealt block
 constexpr int MAX_BLOCKS = 4096;  // per frame: up to 1 Mi points
 constexpr int MAX_CL = 8;
@@ -67,7 +66,7 @@ struct FusedArgs {
     uint2* rlist;        // [clusters][CL][rcap] remote records
     unsigned* rcount;    // [clusters][CL]
     unsigned rcap;
-    // ---- fast (float / fixed-point) projection, certified by margins (see project_fast)
+    // ---- fast (float / fixed-point) projection, certified by margins (see project_lean)
     double enc_scale;          // 65534 / (max_range - min_range)
     float alt_to_fix;          // altitude (rad) -> row cells * 2^FB
     float az_to_fix;           // angle (rad)    -> column cells * 2^FB
@@ -166,21 +165,6 @@ __device__ __forceinline__ float atan01(float a) {
     return __fmaf_rn(__fmul_rn(a, s), q, a);
 }
 
-__device__ __forceinline__ void cas_max_u16(uint16_t* p, unsigned v) {
-    // raises the 16-bit word *p to at least v (shared or distributed shared memory)
-    unsigned* w = reinterpret_cast<unsigned*>(reinterpret_cast<uintptr_t>(p) & ~static_cast<uintptr_t>(3));
-    const int sh = (reinterpret_cast<uintptr_t>(p) & 2) ? 16 : 0;
-    unsigned old = *w;
-    for (;;) {
-        const unsigned cur = (old >> sh) & 0xffffu;
-        if (cur >= v) return;
-        const unsigned want = (old & ~(0xffffu << sh)) | (v << sh);
-        const unsigned got = atomicCAS(w, old, want);
-        if (got == old) return;
-        old = got;
-    }
-}
-
 // Union-find over vertical runs, 16-bit parents in shared memory: bits 0..14 = parent index, bit 15 = "ground" flag
 // (meaningful on roots).  A root is always hung under a root of higher priority, priority = a multiplicative hash of the
 // index (ties impossible: the hash is a bijection on 16 bits), so the forest is acyclic and — unlike linking by index,
@@ -196,20 +180,6 @@ __device__ __forceinline__ int uf16_find(volatile uint16_t* par, int x) {
         if (gp == p) return p;
         par[x] = static_cast<uint16_t>(gp);
         x = gp;
-    }
-}
-__device__ __forceinline__ void uf16_unite(uint16_t* par, int a, int b) {
-    for (;;) {
-        a = uf16_find(par, a);
-        b = uf16_find(par, b);
-        if (a == b) return;
-        if (uf16_prio(a) > uf16_prio(b)) { const int t = a; a = b; b = t; }  // a: lower priority, hangs under b
-        unsigned* w = reinterpret_cast<unsigned*>(par) + (a >> 1);
-        const int sh = (a & 1) * 16;
-        const unsigned old = *reinterpret_cast<volatile unsigned*>(w);
-        if (static_cast<int>((old >> sh) & 0xffffu) != a) continue;  // a stopped being a root meanwhile
-        const unsigned want = (old & ~(0xffffu << sh)) | (static_cast<unsigned>(b) << sh);
-        if (atomicCAS(w, old, want) == old) return;
     }
 }
 // ---- explicit shared::cta accesses on 32-bit window addresses.  Plain C++ dereferences of pointers into the dynamic
@@ -505,71 +475,6 @@ __device__ __noinline__ Proj project_point_d(const KParams* __restrict__ kpp, fl
     return out;
 }
 
-// Fast projection.  The range (hence the gates and the encoded pixel value) is computed with the reference's own double
-// operations, except that the division by (max_range - min_range) becomes a multiplication checked against a 1e-9
-// margin (the two differ by < 1e-10).  Altitude and azimuth come from a float atan (error budget 2e-7 rad) and are
-// turned into fixed-point cell coordinates; when the fractional position lies within the margin (>= 7.5e-7 rad) of a
-// cell edge or an altitude gate, the caller falls back to project_point_d.  returns 0 = pixel found, 1 = dropped,
-// 2 = undecided (fall back).
-__device__ __forceinline__ int project_fast(const FusedArgs& A, float fx, float fy, float fz, int* row_out, int* col_out, unsigned* enc_out) {
-    const KParams& kp = A.kp;
-    const double x = fx, y = fy, z = fz;
-    // range = sqrt(x*x + y*y + z*z) to ~5e-16 relative (the reference's value, utils.h:41-43, differs from it by rounding
-    // only): fused sum of squares, float rsqrt seed, two Newton steps in double.  11 FP64 operations instead of the ~28 of
-    // three products, two sums and a correctly rounded square root; every decision taken on it keeps a 1e-9 m margin.
-    const double s2 = __fma_rn(x, x, __fma_rn(y, y, __dmul_rn(z, z)));
-    double rs = static_cast<double>(rsqrtf(static_cast<float>(s2)));
-    const double hs = __dmul_rn(0.5, s2);
-    rs = __dmul_rn(rs, __fma_rn(-__dmul_rn(hs, rs), rs, 1.5));
-    rs = __dmul_rn(rs, __fma_rn(-__dmul_rn(hs, rs), rs, 1.5));
-    const double range = __dmul_rn(s2, rs);
-    if (!(range > A.range_lo_in && range < A.range_hi_in)) {            // alfa_gs.cpp:261
-        if (range < A.range_lo_out || range > A.range_hi_out) return 1;  // certainly outside the gates
-        return 2;                                                        // within 1e-9 m of a gate, zero or not finite: exact path
-    }
-    const double u = __fma_rn(__dsub_rn(range, kp.min_range), A.enc_scale, 1.0);
-    const int e = __double2int_rz(u);
-    const double uf = u - static_cast<double>(e);
-    if (!(uf > 1e-9 && uf < 1.0 - 1e-9)) return 2;
-    // altitude
-    const float ax = fabsf(fx), ay = fabsf(fy), az = fabsf(fz);
-    if (fy == 0.0f) return 2;  // atan2(-0.0, x < 0) = -pi in the reference (Q3): exact path
-    const float h2 = __fmaf_rn(fx, fx, __fmul_rn(fy, fy));
-    const float h = __fmul_rn(h2, rsqrtf(h2));  // 2-3 ulp: 1e-7 rad of altitude at most
-    const float lo_a = fminf(az, h), hi_a = fmaxf(az, h);
-    float t = atan01(__fdividef(lo_a, hi_a));
-    if (az > h) t = 1.57079632679489662f - t;
-    const float alt = fz < 0.0f ? -t : t;
-    if (!(alt > A.alt_lo + 1e-6f && alt < A.alt_hi - 1e-6f)) {
-        if (alt < A.alt_lo - 1e-6f || alt > A.alt_hi + 1e-6f) return 1;  // alfa_gs.cpp:269, certainly outside
-        return 2;                                                        // within the margin of a gate (or NaN)
-    }
-    const int rowfix = A.row0_fix - __float2int_rn(__fmul_rn(alt, A.alt_to_fix));
-    const int rfrac = rowfix & ((1 << FB) - 1);
-    if (rfrac < A.row_margin || rfrac > (1 << FB) - A.row_margin) return 2;
-    const int row = rowfix >> FB;
-    // azimuth in [0, 2 pi): octant reduction, reflections in exact fixed point
-    const float lo_b = fminf(ax, ay), hi_b = fmaxf(ax, ay);
-    int c = __float2int_rn(__fmul_rn(atan01(__fdividef(lo_b, hi_b)), A.az_to_fix));
-    if (ay > ax) c = A.quarter_fix - c;
-    if (fx < 0.0f) c = 2 * A.quarter_fix - c;
-    if (fy < 0.0f) c = 4 * A.quarter_fix - c;
-    const int colfix = c + A.col_half_fix;
-    const int cfrac = colfix & ((1 << FB) - 1);
-    if (!(cfrac >= A.col_margin && cfrac <= (1 << FB) - A.col_margin)) return 2;
-    int col = colfix >> FB;
-    // inside the gates 0 <= row < H and 0 <= col <= W hold; anything else goes to the exact path
-    if (static_cast<unsigned>(row) >= static_cast<unsigned>(kp.H) || static_cast<unsigned>(col) > static_cast<unsigned>(A.col_limit)) return 2;
-    if (col == kp.W) {  // only the alfa_gs variant gets here (col_limit = W)
-        if (A.col_wrap) col = 0;                  // GS_COL_WRAP
-        else if (row == kp.H - 1) return 1;       // Q2: flat index past the end of the image
-    }
-    *row_out = row;
-    *col_out = col;
-    *enc_out = static_cast<unsigned>(e);
-    return 0;
-}
-
 constexpr int UB = 14;  // fractional bits of the fixed-point encoded range
 
 __device__ __forceinline__ float rsqrt_ftz(float a) {
@@ -583,16 +488,21 @@ __device__ __forceinline__ float rcp_ftz(float a) {
     return r;
 }
 
-// Lean, BRANCH-FREE version of project_fast (same certificates, ~40 % fewer instructions).  Being straight-line code,
-// the evaluations of two points interleave in the instruction stream, which hides the latency of the FP64 chain.
+// Certified fast projection: BRANCH-FREE float / fixed-point arithmetic whose every decision keeps a margin >= 4x its error
+// budget; a point that lands inside a margin is "not certified" and goes to the reference's exact double arithmetic
+// (project_point_d).  With GS_OPT_COLLECT_STATS the kernel evaluates both for every point and counts disagreements (0 in
+// all tests).  Being straight-line code, the evaluations of two points interleave in the instruction stream, which hides
+// the latency of the FP64 chain.
 //  * range: double sum of squares, MUFU rsqrt seed of the float sum of squares (relative error e0 < 2.5e-7) and ONE Heron
-//    step r + (s2 - r*r) * (0.5 * seed): relative error 1.5 e0^2 < 1e-13, i.e. < 1e-8 of an encoded-range unit.  The
-//    encoded value is taken in 2^-14 fixed point from one DFMA + F2I; a fractional part of 0 or 16383 (within 6.1e-5 of
-//    an integer) or a value outside (1, 65535) — the range gates of alfa_gs.cpp:261 map to exactly 1 and 65535 — is not
-//    decided here.
-//  * altitude / azimuth: float atan as in project_fast with the raw MUFU rcp / rsqrt (flush-to-zero forms; operands
-//    below 1e-15 are not decided here), gates and cell edges tested on the fixed-point cell coordinates with the same
-//    margins (>= 4x the error budget).
+//    step r + (s2 - r*r) * (0.5 * seed): relative error 1.5 e0^2 < 1e-13, i.e. < 1e-8 of an encoded-range unit (the
+//    reference's sqrt(x*x + y*y + z*z), utils.h:41-43, differs from the true value by rounding only).  The encoded value
+//    (alfa_gs.cpp:288-291) is taken in 2^-14 fixed point from one DFMA + F2I; a fractional part of 0 or 16383 (within
+//    6.1e-5 of an integer) or a value outside (1, 65535) — the range gates of alfa_gs.cpp:261 map to exactly 1 and 65535 —
+//    is not certified.
+//  * altitude / azimuth (utils.h:8-28): float atan on [0, 1] (atan01, error 6.6e-8 rad) after octant reduction with the
+//    raw MUFU rcp / rsqrt (flush-to-zero forms; operands below 1e-15 are not certified), reflections in exact 18-bit fixed
+//    point; the altitude gates (alfa_gs.cpp:269) and the cell edges (:275, :277) are tested on the fixed-point cell
+//    coordinates with margins of 1e-6 rad / 7.5e-7 rad.
 // ok = pixel (row, col, enc) certified.  Everything else — outside a gate, within a margin of a gate or an edge, the
 // flat-index alias column W, y == 0, non-finite — is classified by project_undecided / project_point_d.
 struct Lean {
@@ -702,7 +612,6 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
     const int S16 = SPEC ? LC.S16 : A.S16, S8 = SPEC ? LC.S8 : A.S8, NG = SPEC ? LC.NG : A.NG;
     const unsigned off_range = SPEC ? LC.off_range : A.off_range, off_tag = SPEC ? LC.off_tag : A.off_tag, off_angle = SPEC ? LC.off_angle : A.off_angle;
     const unsigned off_masks = SPEC ? LC.off_masks : A.off_masks, off_misc = SPEC ? LC.off_misc : A.off_misc, off_lut = SPEC ? LC.off_lut : A.off_lut;
-    const int CWp = CW;                         // mask arrays are CW wide
     // forest index of the run that starts at row rs of local column c.  The row is rotated by 2c inside the column so that
     // runs starting at the same row in neighbouring columns (the ground does) fall into different shared-memory banks.
     auto run_node = [=](int c, int rs) -> int { return c * H + ((rs + 2 * c) & (H - 1)); };  // H is a power of two (checked on the host)
@@ -1770,7 +1679,7 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
     a.cnt = cnt;
     a.stats = stats;  // bit 0: verification + counters, bit 1: phase timing
     a.rcap = rcap;
-    // fast-path constants (see project_fast)
+    // fast-path constants (see project_lean)
     {
         const double two_fb = static_cast<double>(1 << FB);
         const bool c2r = kp.variant == GS_VARIANT_CLOUD2RANGE;

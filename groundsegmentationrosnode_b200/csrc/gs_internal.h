@@ -89,6 +89,11 @@ void launch_erase(const Launch& L, const KParams& kp, int frames, const uint16_t
 void launch_backproject(const Launch& L, const KParams& kp, const Luts& lut, int frames, const uint16_t* image,
                         const unsigned* rowcount, float* xyz4, unsigned* counts, bool range_as_double);
 void launch_rowcount(const Launch& L, const KParams& kp, int frames, const uint16_t* image, unsigned* rowcount);
+// N3 evaluation: Alfa_GS::CreateLabeledRangeImage (32-byte PointXYZRGB records) and the counters of CheckNumberOfDetectedRIdGnd
+size_t label_image_scratch_bytes(size_t n);
+void launch_label_image(const Launch& L, const KParams& kp, const void* points32, size_t n, uint8_t* flags, int* flat, uint8_t* summary,
+                        uint16_t* labeled);
+void launch_evaluate(const Launch& L, const KParams& kp, const uint16_t* og, const uint16_t* seg, const uint16_t* lab, unsigned long long* out9);
 
 
 // ---- fused single-kernel pipeline (gs_fused.cu): one thread-block cluster per frame, images resident in (distributed)

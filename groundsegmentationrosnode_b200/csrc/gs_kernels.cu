@@ -17,6 +17,8 @@
 // round-to-nearest intrinsics so it does not depend on the flag.
 #include <math_constants.h>
 
+#include <algorithm>
+
 #include "gs_internal.h"
 #include "gs_math.cuh"
 
@@ -563,6 +565,108 @@ __global__ void __launch_bounds__(256) k_pack_xyzrgb(const float4* __restrict__ 
     out[2 * i + 1] = make_uint4(0xff000000u, 0u, 0u, 0u);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// N3 — evaluation (Alfa_GS::CreateLabeledRangeImage alfa_gs.cpp:945-995, CheckNumberOfDetectedRIdGnd :831-943)
+// ------------------------------------------------------------------------------------------------
+// Labelled range image: 1 everywhere, 0 where a kept point lands while the reference's `gnd_flag` is up.  The flag is
+// raised by every point with a ground colour (:961-965) BEFORE the range / altitude gates and lowered only at the end of
+// a kept point's iteration (:992), so it sticks across skipped points: a kept point is marked iff itself or any point
+// since the previous kept point has a ground colour.  Pixels are only ever set to 0, hence the result does not depend on
+// the order of the stores; the sticky flag is a segmented OR over the input order, done in three passes: per-point
+// (kept, ground) bits, per-chunk summaries, look-back.
+constexpr int EV_CHUNK = 256;
+__device__ __forceinline__ bool ground_colour(unsigned rgba) {
+    // PCL PointXYZRGB: bytes b, g, r, a at offset 16 (alfa_gs.cpp:961)
+    const unsigned b = rgba & 0xffu, g = (rgba >> 8) & 0xffu, r = (rgba >> 16) & 0xffu;
+    return (r == 75 && g == 0 && b == 75) || (r == 255 && g == 0 && b == 255) || (r == 255 && g == 150 && b == 255);
+}
+__global__ void __launch_bounds__(EV_CHUNK) k_label_flags(const unsigned char* __restrict__ points, size_t n, KParams kp, uint8_t* __restrict__ flags,
+                                                           int* __restrict__ flat_out) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * EV_CHUNK + threadIdx.x;
+    if (i >= n) return;
+    const float* q = reinterpret_cast<const float*>(points + i * 32);
+    const unsigned rgba = *reinterpret_cast<const unsigned*>(points + i * 32 + 16);
+    const Projected pr = project_point(kp, q[0], q[1], q[2]);
+    flags[i] = static_cast<uint8_t>((pr.flat >= 0 ? 1 : 0) | (ground_colour(rgba) ? 2 : 0));
+    flat_out[i] = pr.flat;
+}
+// one thread per chunk: (a kept point exists) | (ground colour after the last kept point) << 1 | (ground colour anywhere) << 2
+__global__ void __launch_bounds__(128) k_label_chunks(const uint8_t* __restrict__ flags, size_t n, uint8_t* __restrict__ summary, int n_chunks) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    const size_t beg = static_cast<size_t>(c) * EV_CHUNK, end = min(beg + EV_CHUNK, n);
+    unsigned kept = 0, tail = 0, all = 0;
+    for (size_t i = beg; i < end; ++i) {
+        const unsigned f = flags[i];
+        if (f & 2u) { tail = 1; all = 1; }
+        if (f & 1u) { kept = 1; tail = 0; }
+    }
+    summary[c] = static_cast<uint8_t>(kept | (tail << 1) | (all << 2));
+}
+__global__ void __launch_bounds__(EV_CHUNK) k_label_mark(const uint8_t* __restrict__ flags, const int* __restrict__ flat, const uint8_t* __restrict__ summary,
+                                                          size_t n, uint16_t* __restrict__ labeled) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * EV_CHUNK + threadIdx.x;
+    if (i >= n) return;
+    const unsigned f = flags[i];
+    if (!(f & 1u)) return;  // skipped points store nothing
+    bool up = (f & 2u) != 0;
+    // look back to the previous kept point: inside the chunk point by point, then over chunk summaries
+    const size_t chunk_beg = static_cast<size_t>(blockIdx.x) * EV_CHUNK;
+    bool found_kept = false;
+    for (size_t j = i; !up && j > chunk_beg;) {
+        --j;
+        const unsigned g = flags[j];
+        if (g & 1u) { found_kept = true; break; }
+        if (g & 2u) up = true;
+    }
+    if (!up && !found_kept) {
+        for (int c = static_cast<int>(blockIdx.x) - 1; c >= 0; --c) {
+            const unsigned sm = summary[c];
+            if (sm & 1u) { up = (sm & 2u) != 0; break; }
+            if (sm & 4u) { up = true; break; }
+        }
+    }
+    if (up) labeled[flat[i]] = 0;  // alfa_gs.cpp:988-991
+}
+__global__ void __launch_bounds__(256) k_fill_u16(uint16_t* __restrict__ p, size_t n, uint16_t v) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+// CheckNumberOfDetectedRIdGnd: the nine per-frame counters of alfa_gs.cpp:838-870 in one pass over the three images
+__global__ void __launch_bounds__(256) k_evaluate(const uint16_t* __restrict__ og, const uint16_t* __restrict__ seg, const uint16_t* __restrict__ lab, size_t P,
+                                                  unsigned long long* __restrict__ out9) {
+    unsigned c[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) c[k] = 0;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < P; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const unsigned o = og[i], s = seg[i], l = lab[i];
+        c[0] += 1;                                 // points_cntr
+        if (l == 0) c[1] += 1;                     // labeled_gnd_cntr          :840
+        else if (o != 0) c[2] += 1;                // labeled_obst_cntr         :843-845
+        if (s == 0 && o != 0) c[3] += 1;           // seg_gnd_cntr              :847
+        if (s == l && o != 0) c[4] += 1;           // true_positive             :850
+        if (s == 0 && l != 0 && o != 0) c[5] += 1; // false_positive            :855
+        if (s != 0 && l != 0) c[6] += 1;           // true_negative             :858
+        if (s != 0 && l == 0) c[7] += 1;           // false_negative            :861
+        if (s != 0 && l != 0) c[8] += 1;           // true_detected_obst_cntr   :864
+    }
+    __shared__ unsigned sm[9][8];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        unsigned v = c[k];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+        if ((threadIdx.x & 31) == 0) sm[k][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 9) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; ++w) t += sm[threadIdx.x][w];
+        if (t) atomicAdd(out9 + threadIdx.x, t);
+    }
+}
+
 inline dim3 pixel_grid(const KParams& kp, int frames) { return dim3((kp.P + 255) / 256, frames); }
 
 }  // namespace
@@ -665,6 +769,27 @@ void launch_backproject(const Launch& L, const KParams& kp, const Luts& lut, int
     else
         k_backproject<false><<<dim3(kp.H, frames), 256, 0, L.stream>>>(image, rowcount, reinterpret_cast<float4*>(xyz4), counts, kp, lut);
     GS_COUNT(L);
+}
+
+void launch_label_image(const Launch& L, const KParams& kp, const void* points32, size_t n, uint8_t* flags, int* flat, uint8_t* summary,
+                        uint16_t* labeled) {
+    k_fill_u16<<<static_cast<unsigned>((kp.P + 255) / 256), 256, 0, L.stream>>>(labeled, static_cast<size_t>(kp.P), 1);  // Mat(n_beams_, n_cols_, CV_16UC1, 1)  :947
+    ++*L.n_launches;
+    if (n == 0) return;
+    const int n_chunks = static_cast<int>((n + EV_CHUNK - 1) / EV_CHUNK);
+    k_label_flags<<<n_chunks, EV_CHUNK, 0, L.stream>>>(static_cast<const unsigned char*>(points32), n, kp, flags, flat);
+    k_label_chunks<<<(n_chunks + 127) / 128, 128, 0, L.stream>>>(flags, n, summary, n_chunks);
+    k_label_mark<<<n_chunks, EV_CHUNK, 0, L.stream>>>(flags, flat, summary, n, labeled);
+    *L.n_launches += 3;
+}
+size_t label_image_scratch_bytes(size_t n) {  // flags [n] u8 | summary [chunks] u8 (padded) | flat [n] i32
+    const size_t chunks = (n + EV_CHUNK - 1) / EV_CHUNK;
+    return ((n + 15) / 16 * 16) + ((chunks + 15) / 16 * 16) + n * 4;
+}
+void launch_evaluate(const Launch& L, const KParams& kp, const uint16_t* og, const uint16_t* seg, const uint16_t* lab, unsigned long long* out9) {
+    const unsigned blocks = static_cast<unsigned>(std::min<size_t>((kp.P + 255) / 256, 148 * 8));
+    k_evaluate<<<blocks, 256, 0, L.stream>>>(og, seg, lab, static_cast<size_t>(kp.P), out9);
+    ++*L.n_launches;
 }
 
 }  // namespace gs

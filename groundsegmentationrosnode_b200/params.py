@@ -56,6 +56,13 @@ class GsParams(C.Structure):
         return (self.n_beams, self.n_cols)
 
 
+class GsEval(C.Structure):
+    """gs_eval of include/gs_b200.h (CheckNumberOfDetectedRIdGnd, alfa_gs.cpp:831-889)."""
+    _fields_ = [(n, C.c_uint64) for n in ("points", "labeled_gnd", "labeled_obst", "seg_gnd", "true_positive", "false_positive",
+                                          "true_negative", "false_negative", "true_detected_obst")] + \
+               [(n, C.c_float) for n in ("iou_g", "recall_g", "recall_mo")]
+
+
 class GsDerived(C.Structure):
     _fields_ = [
         ("n_rows", C.c_int32),

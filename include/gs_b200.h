@@ -210,6 +210,24 @@ int gs_pack_cloud_xyzrgb(gs_ctx* ctx, const float* xyz4, uint32_t n_points, void
  * the u16 row-major buffers of this API are the mono16 payload (step = 2 * width). */
 int gs_get_camera_info(const gs_ctx* ctx, int32_t* height, int32_t* width, double* K9);
 
+/* ---- evaluation against labelled data ----
+ * gs_create_labeled_range_image = Alfa_GS::CreateLabeledRangeImage (src/alfa_gs.cpp:945-995): points are 32-byte
+ * pcl::PointXYZRGB records (x y z pad | b g r a | pad); the image is 1 everywhere and 0 where a kept point lands while the
+ * reference's gnd_flag is up — the flag is raised by every point coloured (75,0,75), (255,0,255) or (255,150,255) and
+ * lowered only at the end of a kept point's iteration, so it sticks across points skipped by the gates (kept literally).
+ * gs_evaluate = the per-frame part of Alfa_GS::CheckNumberOfDetectedRIdGnd (src/alfa_gs.cpp:831-889): the counters of
+ * :838-870 over (original range image, no-ground image, labelled image) and IoU_g / Recall_g / Recall_mo in the
+ * reference's float arithmetic (:885-887; NaN when a denominator is 0, as there).  The reference's integer percentages
+ * (:873-877) divide by counters that may be 0 (and true_detected_gnd_cntr is never incremented) and its running means
+ * over frames are logging state: neither is reproduced. */
+typedef struct gs_eval {
+    uint64_t points, labeled_gnd, labeled_obst, seg_gnd;
+    uint64_t true_positive, false_positive, true_negative, false_negative, true_detected_obst;
+    float iou_g, recall_g, recall_mo;
+} gs_eval;
+int gs_create_labeled_range_image(gs_ctx* ctx, const void* points_xyzrgb32, size_t n_points, uint16_t* labeled_out);
+int gs_evaluate(gs_ctx* ctx, const uint16_t* og_range, const uint16_t* seg_range, const uint16_t* labeled_range, gs_eval* out);
+
 /* ---- batch API: frames are independent (alfa_gs.cpp:196-239 holds no cross-frame state) ---- */
 /* DEVICE buffers.  points: packed 16-byte XYZI records of all frames; offsets (HOST, n_frames+1
  * entries, in points) delimit frames.  no_ground_out: n_frames * P u16;  xyz4_out: n_frames * P

@@ -248,6 +248,31 @@ public:
         }
         return cloud;
     }
+    // alfa_gs.cpp:945-995: 1 everywhere, 0 where a kept point lands with the (sticky) ground-colour flag up
+    Image<uint16_t> CreateLabeledRangeImage(const std::vector<PointXYZRGB>& input_cloud) {
+        Image<uint16_t> out(n_rows(), n_cols());
+        ctx_->check(gs_create_labeled_range_image(ctx_->get(), input_cloud.data(), input_cloud.size(), out.ptr()));
+        return out;
+    }
+    // alfa_gs.cpp:831-943: the per-frame counters and IoU_g / Recall_g / Recall_mo; the running means the reference keeps in
+    // function-local statics for its log line (:890-927) are accumulated here per object
+    gs_eval CheckNumberOfDetectedRIdGnd(const Image<uint16_t>& og_range_image, const Image<uint16_t>& seg_range_image,
+                                        const Image<uint16_t>& labeled_range_image) {
+        gs_eval e;
+        ctx_->check(gs_evaluate(ctx_->get(), og_range_image.ptr(), seg_range_image.ptr(), labeled_range_image.ptr(), &e));
+        eval_sum_[0] += e.iou_g;
+        eval_sum_[1] += e.recall_g;
+        eval_sum_[2] += e.recall_mo;
+        ++eval_cnt_;
+        return e;
+    }
+    // mean IoU_g, Recall_g, Recall_mo over the frames evaluated so far (alfa_gs.cpp:921-927)
+    void EvaluationMeans(float* iou_g, float* recall_g, float* recall_mo) const {
+        const float n = static_cast<float>(eval_cnt_ ? eval_cnt_ : 1);
+        *iou_g = eval_sum_[0] / n;
+        *recall_g = eval_sum_[1] / n;
+        *recall_mo = eval_sum_[2] / n;
+    }
     // alfa_gs.cpp:175-244, the hw == 0 branch: range image -> angle image -> (discarded moving average) -> EraseBFS
     // -> CameraCb, fused on the GPU; the caller publishes the two results (alfa_node.cpp:27-57)
     struct Frame {
@@ -298,6 +323,8 @@ public:
     }
 
 private:
+    float eval_sum_[3] = {0.f, 0.f, 0.f};
+    int eval_cnt_ = 0;
     void refresh_cinfo() {  // alfa_gs.cpp:55-63
         const gs_params& p = ctx_->params();
         const gs_derived& d = ctx_->derived();

@@ -608,4 +608,94 @@ float gso_atan2f(float y, float x) { return atan2f(y, x); }
 float gso_sinf(float x) { return sinf(x); }
 float gso_cosf(float x) { return cosf(x); }
 
+// ---- N3 : Alfa_GS::CreateLabeledRangeImage (alfa_gs.cpp:945-995) ------------------------------
+// points: 32-byte pcl::PointXYZRGB records (x y z pad | b g r a | pad).  gnd_flag is raised before the gates (:961-965)
+// and lowered only at the end of a kept point's iteration (:992): it sticks across skipped points (kept literally).
+// Projection = CreateRangeImage's (the same lines, :968-985); the flat-index alias of column W and non-finite points
+// follow the same contract (Q2, Q3).
+int gso_create_labeled_range_image(const gs_params* p, const void* points, size_t n, uint16_t* img) {
+    const Dims d = dims_of(*p);
+    const int H = d.H, W = d.W;
+    const size_t P = static_cast<size_t>(H) * W;
+    for (size_t i = 0; i < P; ++i) img[i] = 1;  // Mat(n_beams_, n_cols_, CV_16UC1, 1)  :947
+    const double half_d_alt = d.d_alt / 2, half_d_az = d.d_az / 2;  // :953-954
+    int gnd_flag = 0;
+    const unsigned char* base = static_cast<const unsigned char*>(points);
+    for (size_t i = 0; i < n; ++i) {
+        float fx, fy, fz;
+        std::memcpy(&fx, base + i * 32 + 0, 4);
+        std::memcpy(&fy, base + i * 32 + 4, 4);
+        std::memcpy(&fz, base + i * 32 + 8, 4);
+        const unsigned b = base[i * 32 + 16], g = base[i * 32 + 17], r = base[i * 32 + 18];
+        if ((r == 75 && g == 0 && b == 75) || (r == 255 && g == 0 && b == 255) || (r == 255 && g == 150 && b == 255)) gnd_flag = 1;  // :961-965
+        if (!finite3(fx, fy, fz)) continue;  // contract Q3
+        const double x = fx, y = fy, z = fz;
+        const double range = point_range(x, y, z);
+        if (range < p->min_range || range > p->max_range) continue;  // :967-971
+        const double azimuth = point_azimuth(x, y);
+        const double altitude = point_altitude(x, y, z);
+        if (altitude < p->min_angle || altitude > p->max_angle) continue;  // :975-979
+        double rowf, colf;
+        if (p->variant == GS_VARIANT_CLOUD2RANGE) {
+            rowf = ((p->max_angle - altitude) / (p->max_angle - p->min_angle)) * H;
+            colf = azimuth / d.d_az;
+        } else {
+            rowf = (H - 1) - ((altitude - half_d_alt - p->min_angle) / d.d_alt);  // :981
+            colf = (azimuth + half_d_az) / d.d_az;                                // :982
+        }
+        if (!(colf >= 0.0)) continue;
+        const int row = static_cast<int>(rowf);
+        int col = static_cast<int>(colf);
+        if (row < 0 || row >= H) continue;
+        size_t flat;
+        if (p->variant == GS_VARIANT_CLOUD2RANGE) {
+            if (col >= W) continue;
+            flat = static_cast<size_t>(row) * W + col;
+        } else if (p->col_policy == GS_COL_WRAP) {
+            col %= W;
+            flat = static_cast<size_t>(row) * W + col;
+        } else {
+            flat = static_cast<size_t>(row) * W + col;
+            if (flat >= P) continue;
+        }
+        if (gnd_flag == 1) img[flat] = 0;  // :988-991
+        gnd_flag = 0;                      // :992
+    }
+    return GS_OK;
+}
+
+// ---- N3 : Alfa_GS::CheckNumberOfDetectedRIdGnd (alfa_gs.cpp:831-889), per-frame part ------------
+int gso_evaluate(const gs_params* p, const uint16_t* og, const uint16_t* seg, const uint16_t* lab, gs_eval* out) {
+    const Dims d = dims_of(*p);
+    int points_cntr = 0, seg_gnd_cntr = 0, labeled_gnd_cntr = 0, labeled_obst_cntr = 0, true_detected_obst_cntr = 0;  // :833
+    float true_positive = 0, false_positive = 0, true_negative = 0, false_negative = 0;                              // :834
+    for (int col = 0; col < d.W; ++col) {      // :838
+        for (int row = 0; row < d.H; ++row) {  // :840
+            const size_t i = static_cast<size_t>(row) * d.W + col;
+            points_cntr++;
+            if (lab[i] == 0) labeled_gnd_cntr++;
+            else if (og[i] != 0) labeled_obst_cntr++;
+            if (seg[i] == 0 && og[i] != 0) seg_gnd_cntr++;
+            if (seg[i] == lab[i] && og[i] != 0) true_positive++;
+            if (seg[i] == 0 && lab[i] != 0 && og[i] != 0) false_positive++;
+            if (seg[i] != 0 && lab[i] != 0) true_negative++;
+            if (seg[i] != 0 && lab[i] == 0) false_negative++;
+            if (seg[i] != 0 && lab[i] != 0) true_detected_obst_cntr++;
+        }
+    }
+    out->points = points_cntr;
+    out->labeled_gnd = labeled_gnd_cntr;
+    out->labeled_obst = labeled_obst_cntr;
+    out->seg_gnd = seg_gnd_cntr;
+    out->true_positive = static_cast<uint64_t>(true_positive);
+    out->false_positive = static_cast<uint64_t>(false_positive);
+    out->true_negative = static_cast<uint64_t>(true_negative);
+    out->false_negative = static_cast<uint64_t>(false_negative);
+    out->true_detected_obst = true_detected_obst_cntr;
+    out->iou_g = ((true_positive) / (true_positive + false_positive + false_negative)) * 100;  // :885
+    out->recall_g = (true_positive / (true_positive + false_negative)) * 100;                   // :886
+    out->recall_mo = (true_negative / (true_negative + false_positive)) * 100;                  // :887
+    return GS_OK;
+}
+
 }  // extern "C"

@@ -11,7 +11,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
-from groundsegmentationrosnode_b200.params import GsDerived, GsParams  # noqa: E402  (POD layouts only)
+from groundsegmentationrosnode_b200.params import GsDerived, GsEval, GsParams  # noqa: E402  (POD layouts only)
 
 from . import build as _build  # noqa: E402
 
@@ -51,6 +51,8 @@ def lib():
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p]
         L.gso_process_batch.argtypes = [C.POINTER(GsParams), _f32p, _i64p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.POINTER(C.c_double), C.c_void_p]
+        L.gso_create_labeled_range_image.argtypes = [C.POINTER(GsParams), C.c_void_p, C.c_size_t, _u16p]
+        L.gso_evaluate.argtypes = [C.POINTER(GsParams), _u16p, _u16p, _u16p, C.POINTER(GsEval)]
         for name, n in (("gso_point_range", 3), ("gso_point_azimuth", 2), ("gso_point_altitude", 3), ("gso_rad_deg", 1)):
             fn = getattr(L, name)
             fn.restype = C.c_double
@@ -231,3 +233,20 @@ def process_batch(p, points_xyzi, offsets, n_threads=1, want_outputs=True):
                                    cnt.ctypes.data_as(C.c_void_p), C.byref(sec), ms.ctypes.data_as(C.c_void_p)),
            "process batch")
     return dict(no_ground=res, xyz=xyz, counts=cnt, seconds=sec.value, stage_ms=ms)
+
+
+def create_labeled_range_image(p, points32):
+    """Alfa_GS::CreateLabeledRangeImage on 32-byte PointXYZRGB records (uint8 array [n, 32])."""
+    H, W = p.shape
+    pts = np.ascontiguousarray(points32, np.uint8).reshape(-1, 32)
+    img = np.zeros((H, W), np.uint16)
+    _check(lib().gso_create_labeled_range_image(C.byref(p), pts.ctypes.data_as(C.c_void_p), pts.shape[0], img), "create_labeled_range_image")
+    return img
+
+
+def evaluate(p, og, seg, labeled):
+    """Per-frame counters and metrics of Alfa_GS::CheckNumberOfDetectedRIdGnd."""
+    out = GsEval()
+    _check(lib().gso_evaluate(C.byref(p), np.ascontiguousarray(og, np.uint16), np.ascontiguousarray(seg, np.uint16),
+                              np.ascontiguousarray(labeled, np.uint16), C.byref(out)), "evaluate")
+    return out

@@ -12,6 +12,8 @@
 extern "C" {
 int gso_process_frame(const gs_params* p, const void* points, size_t n, size_t stride, uint16_t* range_out, uint16_t* angle_out,
                       uint16_t* no_ground_out, float* xyz4_out, uint32_t* n_out, double* stage_ms);
+int gso_create_labeled_range_image(const gs_params* p, const void* points, size_t n, uint16_t* img);
+int gso_evaluate(const gs_params* p, const uint16_t* og, const uint16_t* seg, const uint16_t* lab, gs_eval* out);
 int gso_label_one_component(const gs_params* p, int label, int row, int col, float thr, const uint16_t* range, const uint16_t* angle,
                             uint8_t* label_image);
 }
@@ -85,6 +87,23 @@ int main() {
     gs::Alfa_GS::Frame f = node.process_pointcloud(cloud);
     CHECK(f.range_image.data == o_range && f.angle_image.data == o_angle && f.no_ground_image.data == o_res && f.seg_cloud.size() == o_n,
           "process_pointcloud");
+
+    // evaluation helpers (alfa_gs.cpp:831-995): colour every third low point as ground, compare with the oracle
+    {
+        std::vector<gs::PointXYZRGB> labelled = cloud;
+        for (size_t i = 0; i < labelled.size(); ++i)
+            if (labelled[i].z < -1.5f && i % 3 == 0) { labelled[i].r = 255; labelled[i].g = 0; labelled[i].b = 255; }
+        gs::Image<uint16_t> lab = node.CreateLabeledRangeImage(labelled);
+        std::vector<uint16_t> o_lab(H * W);
+        gso_create_labeled_range_image(&p, labelled.data(), labelled.size(), o_lab.data());
+        CHECK(lab.data == o_lab, "CreateLabeledRangeImage");
+        gs_eval e = node.CheckNumberOfDetectedRIdGnd(range_image, no_ground, lab), o_e;
+        gso_evaluate(&p, o_range.data(), o_res.data(), o_lab.data(), &o_e);
+        CHECK(e.true_positive == o_e.true_positive && e.false_positive == o_e.false_positive && e.true_negative == o_e.true_negative &&
+                  e.false_negative == o_e.false_negative && e.labeled_gnd == o_e.labeled_gnd && e.seg_gnd == o_e.seg_gnd && e.iou_g == o_e.iou_g &&
+                  e.recall_g == o_e.recall_g && e.recall_mo == o_e.recall_mo,
+              "CheckNumberOfDetectedRIdGnd");
+    }
 
     // error behaviour of the reference: std::logic_error for even windows / unknown Savitzky-Golay sizes
     bool threw = false;
