@@ -745,10 +745,22 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             // next unit are issued before the current unit is processed.
             const bool stats1 = (A.stats & 1) != 0;
             const int n_punits = nmine * (BLK / 64);
+            // x, y, z are loaded as 8 + 4 bytes, not as one 16-byte record: the register of the unused intensity word would be
+            // handed out as a temporary while the prefetch is in flight, and the first write to it waits for the load (WAW)
+            auto load_point = [&](int i) -> float4 {
+                float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < N) {
+                    const float2 xy = __ldcs(reinterpret_cast<const float2*>(pts + i));
+                    q.x = xy.x;
+                    q.y = xy.y;
+                    q.z = __ldcs(reinterpret_cast<const float*>(pts + i) + 2);
+                }
+                return q;
+            };
             auto load_unit = [&](int u, float4& pa, float4& pb) -> int {
                 const int i0 = static_cast<int>(s_mylist[u >> 2]) * BLK + (u & 3) * 64 + lane;
-                pa = i0 < N ? __ldcs(pts + i0) : make_float4(0.f, 0.f, 0.f, 0.f);
-                pb = i0 + 32 < N ? __ldcs(pts + i0 + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+                pa = load_point(i0);
+                pb = load_point(i0 + 32);
                 return i0;
             };
             auto place = [&](const float4 p4, const int i, const Lean& L) {
