@@ -978,7 +978,11 @@ int gs_process_batch_host(gs_ctx* ctx, const float* h_points_xyzi, const int64_t
     const size_t P = ctx->kp.P;
     int rc;
     // slot size: enough frames per wave to fill the GPU, small enough to pipeline copies against compute
-    const int wave = std::min(n_frames, ctx->chunk_frames > 0 ? ctx->chunk_frames : 148);
+    // The copies dominate (PCIe moves a frame in ~35 us, the GPU computes it in ~3 us), so waves are kept small: the first
+    // H2D and the last D2H overlap nothing, and that fill / drain time is proportional to the wave.  Two frames per
+    // co-resident cluster of the fused kernel keep its persistent grid busy.
+    const int auto_wave = fused_supported(ctx->fused) ? std::max(2 * ctx->fused.max_clusters, 16) : 148;
+    const int wave = std::min(n_frames, ctx->chunk_frames > 0 ? ctx->chunk_frames : auto_wave);
     if (ctx->slot_frames < wave) {
         for (int k = 0; k < 2; ++k) {
             cudaFree(ctx->d_res[k]); cudaFree(ctx->d_cloud[k]); cudaFree(ctx->d_counts[k]);

@@ -138,7 +138,9 @@ __device__ __forceinline__ double decode_range_d(const KParams& kp, unsigned enc
     // The division by the constant 65534 is done as q0 = n * R, r = fma(-q0, 65534, n), q = fma(r, R, q0) with
     // R = RN(1 / 65534): correctly rounded for every n in [0, 65534] (checked exhaustively against n / 65534.0 by
     // tests/clone_check.cpp), 3 FP64 instructions instead of the ~25 of a generic double division.
-    const double n = static_cast<double>(static_cast<int>(enc) - 1);
+    // (double)(enc - 1) without the conversion unit (I2F.F64 runs on the quarter-rate XU pipe, which the angle walk and the
+    // output saturate): 2^52 + n is exact, so is the subtraction
+    const double n = __dsub_rn(__hiloint2double(0x43300000, static_cast<int>(enc) - 1), 4503599627370496.0);
     const double R = 1.0 / 65534.0;
     const double q0 = __dmul_rn(n, R);
     const double r = __fma_rn(-q0, 65534.0, n);
@@ -934,12 +936,15 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                             const float dx = __double2float_rn(fabs(__dsub_rn(static_cast<double>(p_x), __dmul_rn(rng, s_cos_y_d[r]))));  // :367
                             // fast: float atan with a 2e-7 rad error budget; results within 4e-6 rad of a centi-radian edge
                             // (and 0/0) are recomputed with the bit-exact clone of the host's atan2f
-                            float t = atan01(__fdividef(fminf(dz, dx), fmaxf(dz, dx)));
+                            float t = atan01(__fmul_rn(fminf(dz, dx), rcp_ftz(fmaxf(dz, dx))));
                             if (dz > dx) t = 1.57079632679489662f - t;
-                            const float sc = __fmul_rn(t, 100.0f);
-                            const int kk = __float2int_rd(sc);
-                            const float fr = sc - static_cast<float>(kk);
-                            const bool sure = A.use_fast && fr > 4e-4f && fr < 1.0f - 4e-4f;
+                            const float sc = __fmul_rn(t, 100.0f);  // 0 .. 157.1 (NaN for 0/0 and flushed operands: not sure)
+                            // floor and distance to the nearest integer with the 1.5 * 2^23 trick (FP32 adds instead of two
+                            // conversions on the XU pipe): bits(sc + M) - bits(M) = rn(sc)
+                            const float tm = __fadd_rn(sc, 12582912.0f);
+                            const float diff = __fsub_rn(sc, __fsub_rn(tm, 12582912.0f));  // sc - rn(sc), exact
+                            const int kk = (__float_as_int(tm) - 0x4B400000) - (diff < 0.0f ? 1 : 0);
+                            const bool sure = A.use_fast && fabsf(diff) > 4e-4f;  // false for NaN
                             a_out = static_cast<unsigned>(kk);
                             if (!sure || (A.stats & 1)) {
                                 const float alfa = atan2f_exact(dz, dx);       // :368
