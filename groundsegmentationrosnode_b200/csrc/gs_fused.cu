@@ -565,12 +565,14 @@ __device__ __forceinline__ int project_undecided(const FusedArgs& A, const Lean&
 }
 
 // cheap column estimate used only to deal point blocks to CTAs (any answer is correct, a good one is fast)
-__device__ __forceinline__ int approx_col(const KParams& kp, float x, float y) {
-    float a = atan2f(y, x);
-    if (a < 0.0f) a += 6.2831853f;
-    const float half = kp.variant == GS_VARIANT_CLOUD2RANGE ? 0.0f : 0.5f;
-    int c = static_cast<int>(a / static_cast<float>(kp.d_az) + half);
-    return min(max(c, 0), kp.W - 1);
+__device__ __forceinline__ int approx_col(const FusedArgs& A, float x, float y) {
+    // the azimuth of project_lean (octant reduction, polynomial atan, reflections in fixed point) without its certificates
+    const float ax = fabsf(x), ay = fabsf(y);
+    int c = __float2int_rn(__fmul_rn(atan01(__fmul_rn(fminf(ax, ay), rcp_ftz(fmaxf(fmaxf(ax, ay), 1e-30f)))), A.az_to_fix));
+    if (ay > ax) c = A.quarter_fix - c;
+    if (x < 0.0f) c = 2 * A.quarter_fix - c;
+    if (y < 0.0f) c = 4 * A.quarter_fix - c;
+    return min(max((c + A.col_half_fix) >> FB, 0), A.kp.W - 1);
 }
 
 struct Smem {
@@ -710,25 +712,24 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             uint4* t4 = reinterpret_cast<uint4*>(s_tag);
             for (int i = tid; i < n16; i += NT) t4[i] = make_uint4(0, 0, 0, 0);
         }
-        for (int b = tid; b < nb; b += NT) {
-            // owner vote over 4 sampled points of the block
-            int votes[MAX_CL];
-#pragma unroll
-            for (int k = 0; k < MAX_CL; ++k) votes[k] = 0;
-            const int base = b * BLK;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int i = min(base + 32 + 64 * k, N - 1);
-                const float4 q = __ldg(pts + i);
-                const int o = min(static_cast<int>(__umulhi(static_cast<unsigned>(approx_col(kp, q.x, q.y)), A.cw_magic)), CL - 1);
-#pragma unroll
-                for (int j = 0; j < MAX_CL; ++j) votes[j] += (j == o);
+        // owner vote over 4 sampled points of every block: the 4 lanes of a quad take one sample each
+        for (int b0 = 0; b0 < nb; b0 += NT / 4) {  // uniform trip count
+            const int b = b0 + (tid >> 2);
+            unsigned o = 0xffu;  // no block: no vote
+            if (b < nb) {
+                const int i = min(b * BLK + 32 + 64 * (tid & 3), N - 1);
+                const float2 xy = __ldg(reinterpret_cast<const float2*>(pts + i));
+                o = static_cast<unsigned>(min(static_cast<int>(__umulhi(static_cast<unsigned>(approx_col(A, xy.x, xy.y)), A.cw_magic)), CL - 1));
             }
-            int best = 0;
+            // votes of my owner among the quad; most votes wins, ties go to the lowest rank
+            unsigned cnt = 0;
 #pragma unroll
-            for (int j = 1; j < MAX_CL; ++j)
-                if (votes[j] > votes[best]) best = j;
-            if (best == rank) s_mylist[atomicAdd(&s_misc[0], 1u)] = static_cast<uint16_t>(b);  // any order: the pixel keys carry the point order
+            for (int k = 0; k < 4; ++k) cnt += __shfl_sync(0xffffffffu, o, (lane & ~3) + k) == o;
+            unsigned key = cnt * 16u + (15u - (o & 15u));
+            key = max(key, __shfl_xor_sync(0xffffffffu, key, 1));
+            key = max(key, __shfl_xor_sync(0xffffffffu, key, 2));
+            if (b < nb && (tid & 3) == 0 && static_cast<int>(15u - (key & 15u)) == rank)
+                s_mylist[atomicAdd(&s_misc[0], 1u)] = static_cast<uint16_t>(b);  // any order: the pixel keys carry the point order
         }
         if (tid == 0) rcount[rank] = 0;
         __syncthreads();
