@@ -698,29 +698,24 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
     } while (0)
     if ((A.stats & 2) && tid == 0) t_mark = clock64();
 
-    for (int f = cluster_id; f < A.frames; f += n_clusters) {
-        const long long beg = A.offsets[f], end = A.offsets[f + 1];
-        const int N = static_cast<int>(end - beg);
-        const int nb = (N + BLK - 1) / BLK;
-        const float4* pts = A.points + beg;
-
-        // ================================================================================ P0: clear + deal blocks
-        {
-            uint4* r4 = reinterpret_cast<uint4*>(s_range);
-            const int n16 = (H * S16 * 2 + 15) / 16;
-            for (int i = tid; i < n16; i += NT) r4[i] = make_uint4(0, 0, 0, 0);
-            uint4* t4 = reinterpret_cast<uint4*>(s_tag);
-            for (int i = tid; i < n16; i += NT) t4[i] = make_uint4(0, 0, 0, 0);
+    // P0 — dealing: blocks of 256 consecutive points go to the CTA that most of 4 sampled points fall into (the 4 lanes of a
+    // quad take one sample each).  The list of a frame is built while the previous frame's output streams out.
+    auto deal_load = [&](const float4* ptsN, int Nn, int b0, float2 (&xy)[2]) {
+        const int nbn = (Nn + BLK - 1) / BLK;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int b = b0 + h * (NT / 4) + (tid >> 2);
+            xy[h] = make_float2(1.0f, 1.0f);
+            if (b < nbn) xy[h] = __ldg(reinterpret_cast<const float2*>(ptsN + min(b * BLK + 32 + 64 * (tid & 3), Nn - 1)));
         }
-        // owner vote over 4 sampled points of every block: the 4 lanes of a quad take one sample each
-        for (int b0 = 0; b0 < nb; b0 += NT / 4) {  // uniform trip count
-            const int b = b0 + (tid >> 2);
+    };
+    auto deal_vote = [&](int Nn, int b0, const float2 (&xy)[2]) {
+        const int nbn = (Nn + BLK - 1) / BLK;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int b = b0 + h * (NT / 4) + (tid >> 2);
             unsigned o = 0xffu;  // no block: no vote
-            if (b < nb) {
-                const int i = min(b * BLK + 32 + 64 * (tid & 3), N - 1);
-                const float2 xy = __ldg(reinterpret_cast<const float2*>(pts + i));
-                o = static_cast<unsigned>(min(static_cast<int>(__umulhi(static_cast<unsigned>(approx_col(A, xy.x, xy.y)), A.cw_magic)), CL - 1));
-            }
+            if (b < nbn) o = static_cast<unsigned>(min(static_cast<int>(__umulhi(static_cast<unsigned>(approx_col(A, xy[h].x, xy[h].y)), A.cw_magic)), CL - 1));
             // votes of my owner among the quad; most votes wins, ties go to the lowest rank
             unsigned cnt = 0;
 #pragma unroll
@@ -728,8 +723,47 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             unsigned key = cnt * 16u + (15u - (o & 15u));
             key = max(key, __shfl_xor_sync(0xffffffffu, key, 1));
             key = max(key, __shfl_xor_sync(0xffffffffu, key, 2));
-            if (b < nb && (tid & 3) == 0 && static_cast<int>(15u - (key & 15u)) == rank)
-                s_mylist[atomicAdd(&s_misc[0], 1u)] = static_cast<uint16_t>(b);  // any order: the pixel keys carry the point order
+            // append my blocks (any order: the pixel keys carry the point order); one shared-memory atomic per warp
+            const bool mine = b < nbn && (tid & 3) == 0 && static_cast<int>(15u - (key & 15u)) == rank;
+            const unsigned mm = __ballot_sync(0xffffffffu, mine);
+            if (mm) {
+                unsigned base = 0;
+                if (lane == __ffs(mm) - 1) base = atomicAdd(&s_misc[0], static_cast<unsigned>(__popc(mm)));
+                base = __shfl_sync(0xffffffffu, base, __ffs(mm) - 1);
+                if (mine) s_mylist[base + __popc(mm & ((1u << lane) - 1u))] = static_cast<uint16_t>(b);
+            }
+        }
+    };
+    // the rest of the blocks when a frame has more than NT / 2 of them (> 131 k points with 1024 threads)
+    auto deal_rest = [&](const float4* ptsN, int Nn) {
+        const int nbn = (Nn + BLK - 1) / BLK;
+        for (int b0 = NT / 2; b0 < nbn; b0 += NT / 2) {  // uniform trip count
+            float2 xy[2];
+            deal_load(ptsN, Nn, b0, xy);
+            deal_vote(Nn, b0, xy);
+        }
+    };
+    if (cluster_id < A.frames) {
+        const long long beg0 = A.offsets[cluster_id];
+        const int N0 = static_cast<int>(A.offsets[cluster_id + 1] - beg0);
+        float2 xy[2];
+        deal_load(A.points + beg0, N0, 0, xy);
+        deal_vote(N0, 0, xy);
+        deal_rest(A.points + beg0, N0);
+    }
+
+    for (int f = cluster_id; f < A.frames; f += n_clusters) {
+        const long long beg = A.offsets[f], end = A.offsets[f + 1];
+        const int N = static_cast<int>(end - beg);
+        const float4* pts = A.points + beg;
+
+        // ================================================================================ P0: clear (the block list was built during the previous frame's output)
+        {
+            uint4* r4 = reinterpret_cast<uint4*>(s_range);
+            const int n16 = (H * S16 * 2 + 15) / 16;
+            for (int i = tid; i < n16; i += NT) r4[i] = make_uint4(0, 0, 0, 0);
+            uint4* t4 = reinterpret_cast<uint4*>(s_tag);
+            for (int i = tid; i < n16; i += NT) t4[i] = make_uint4(0, 0, 0, 0);
         }
         if (tid == 0) rcount[rank] = 0;
         __syncthreads();
@@ -848,6 +882,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         GS_PHASE(2);
         __threadfence();  // remote records and counts visible before the cluster-wide phase
         cluster.sync();   // #1: all local pixels committed everywhere
+        if (tid == 0) s_misc[0] = 0;  // every thread has read the block count; the next frame's list is built during the output
 
         GS_PHASE(3);
         // ================================================================================ P2: remote records
@@ -1460,16 +1495,14 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         __syncthreads();
 
         GS_PHASE(13);
-        // the next frame of this cluster: pull the sampled points of the block dealing (P0) into L2 while the output streams
-        // out, so that the top of the next frame does not wait a full HBM round trip twice (offsets, then samples)
-        {
-            const int fn = f + n_clusters;
-            if (fn < A.frames) {
-                const long long begn = A.offsets[fn];
-                const int Nn = static_cast<int>(A.offsets[fn + 1] - begn);
-                const float4* ptsn = A.points + begn;
-                for (int i = 32 + 64 * tid; i < Nn; i += 64 * NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptsn + i));
-            }
+        // the next frame of this cluster: pull the sampled points of its block dealing (P0) into L2 while the output streams out
+        const int fn = f + n_clusters;
+        long long begn = 0;
+        int Nn = 0;
+        if (fn < A.frames) {  // uniform
+            begn = A.offsets[fn];
+            Nn = static_cast<int>(A.offsets[fn + 1] - begn);
+            for (int i = 32 + 64 * tid; i < Nn; i += 64 * NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.points + begn + i));
         }
         // ================================================================================ B: no-ground image + cloud
         {
@@ -1501,8 +1534,15 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                 }
             }
         }
+        // ... and build its block list once the output is on its way (measured: issuing the sample loads before the output
+        // loop delays every warp's start and costs more than it hides)
+        if (fn < A.frames) {  // uniform
+            float2 deal_xy[2];
+            deal_load(A.points + begn, Nn, 0, deal_xy);
+            deal_vote(Nn, 0, deal_xy);
+            deal_rest(A.points + begn, Nn);
+        }
         GS_PHASE(0);
-        if (tid == 0) s_misc[0] = 0;
         __syncthreads();  // the slabs are cleared at the top of the next frame
     }
 
