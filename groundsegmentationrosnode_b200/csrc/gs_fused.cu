@@ -743,18 +743,20 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             deal_vote(Nn, b0, xy);
         }
     };
+    long long beg_cur = 0;
+    int N_cur = 0;
     if (cluster_id < A.frames) {
-        const long long beg0 = A.offsets[cluster_id];
-        const int N0 = static_cast<int>(A.offsets[cluster_id + 1] - beg0);
+        beg_cur = A.offsets[cluster_id];
+        N_cur = static_cast<int>(A.offsets[cluster_id + 1] - beg_cur);
         float2 xy[2];
-        deal_load(A.points + beg0, N0, 0, xy);
-        deal_vote(N0, 0, xy);
-        deal_rest(A.points + beg0, N0);
+        deal_load(A.points + beg_cur, N_cur, 0, xy);
+        deal_vote(N_cur, 0, xy);
+        deal_rest(A.points + beg_cur, N_cur);
     }
 
     for (int f = cluster_id; f < A.frames; f += n_clusters) {
-        const long long beg = A.offsets[f], end = A.offsets[f + 1];
-        const int N = static_cast<int>(end - beg);
+        const long long beg = beg_cur;  // A.offsets[f]: loaded for the dealing during the previous frame (or the prologue)
+        const int N = N_cur;
         const float4* pts = A.points + beg;
 
         // ================================================================================ P0: clear (the block list was built during the previous frame's output)
@@ -904,12 +906,21 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             const int n_quads = (H * S16) >> 2;  // H is a power of two >= 16 and S16 is even: the slab is a whole number of quads
             const uint4* k4 = reinterpret_cast<const uint4*>(s_key);
             uint2* r2 = reinterpret_cast<uint2*>(s_range);
-            for (int base = 0; base < n_quads; base += NT) {
-                const int i = base + tid;
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (i < n_quads) v = k4[i];
-                __syncthreads();  // every key of this chunk is read before its bytes are overwritten
-                if (i < n_quads) r2[i] = make_uint2((v.x & 0xffffu) | (v.y << 16), (v.z & 0xffffu) | (v.w << 16));
+            constexpr int CQ = 3;  // quads per thread between two barriers (12 registers)
+            for (int base = 0; base < n_quads; base += CQ * NT) {
+                uint4 v[CQ];
+#pragma unroll
+                for (int j = 0; j < CQ; ++j) {
+                    const int i = base + j * NT + tid;
+                    v[j] = make_uint4(0u, 0u, 0u, 0u);
+                    if (i < n_quads) v[j] = k4[i];
+                }
+                __syncthreads();  // every key of this chunk is read before its bytes are overwritten (writes land in the first half of what was read so far)
+#pragma unroll
+                for (int j = 0; j < CQ; ++j) {
+                    const int i = base + j * NT + tid;
+                    if (i < n_quads) r2[i] = make_uint2((v[j].x & 0xffffu) | (v[j].y << 16), (v[j].z & 0xffffu) | (v[j].w << 16));
+                }
             }
             __syncthreads();
         }
@@ -1542,6 +1553,8 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             deal_vote(Nn, 0, deal_xy);
             deal_rest(A.points + begn, Nn);
         }
+        beg_cur = begn;
+        N_cur = Nn;
         GS_PHASE(0);
         __syncthreads();  // the slabs are cleared at the top of the next frame
     }
