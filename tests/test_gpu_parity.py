@@ -349,6 +349,38 @@ def test_fused_union_paths_agree_with_oracle(oracle, preset):
                 assert int(d_cnt[f]) == want[f % 6]["xyz"].shape[0]
 
 
+@pytest.mark.parametrize("noise_sigma,dropout", [(0.0, 0.0), (0.0, 0.3), (0.002, 0.0), (0.08, 0.05), (0.25, 0.0)])
+def test_union_stage_stress_frames(oracle, noise_sigma, dropout):
+    """Frames that stress the labelling stage of the fused kernel: without range noise the angle image is smooth, the
+    ground is a handful of giant components and almost every link of a warp's batch hangs the same root (maximal contention
+    in the warp-synchronous unions); with heavy noise nearly every pixel is a run of its own (maximal link and run counts,
+    the list spills into the compare-and-swap path for some frames).  Both union paths, bit-exact against the oracle."""
+    import torch
+
+    p = P.preset(P.GS_PRESET_HDL64E_2048)
+    H, W = p.shape
+    frames = [synth.make_frame(p, synth.SEED0 + 1200 + k, dropout=dropout, noise_sigma=noise_sigma) for k in range(3)]
+    offs = np.concatenate([[0], np.cumsum([f.shape[0] for f in frames])]).astype(np.int64)
+    pool = np.concatenate(frames)
+    pts, offsets = synth.tile_pool(pool, offs, 36)  # more frames than co-resident clusters
+    F = len(offsets) - 1
+    want = [oracle.process_frame(p, f) for f in frames]
+    d_pts = torch.from_numpy(pts).cuda()
+    for cas in (0, 1):
+        with capi.Context(p) as ctx:
+            ctx.set_option(capi.GS_OPT_CAS_UNIONS, cas)
+            d_res = torch.zeros((F, H, W), dtype=torch.int16, device="cuda")
+            d_cnt = torch.zeros(F, dtype=torch.int32, device="cuda")
+            torch.cuda.synchronize()
+            for rep in range(2):  # races are timing dependent: run the batch twice
+                ctx.process_batch_device(d_pts.data_ptr(), offsets, F, 0, 0, d_res.data_ptr(), 0, d_cnt.data_ptr())
+                ctx.synchronize()
+                res = d_res.cpu().numpy().view(np.uint16)
+                for f in range(F):
+                    assert np.array_equal(res[f], want[f % 3]["no_ground"]), "frame %d, cas=%d, rep=%d" % (f, cas, rep)
+                    assert int(d_cnt[f]) == want[f % 3]["xyz"].shape[0]
+
+
 def test_set_params_recomputes_derived(ctxs, oracle):
     """gs_set_params replaces Alfa_GS::UpdateSegmentationSettings (alfa_gs.cpp:1122-1136) and, unlike it, refreshes
     the derived values."""
