@@ -1066,22 +1066,67 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         }
         __syncthreads();
         const int n_units = myCW * NWD;  // one unit = 32 rows of one column
+        // Angle-difference links (label.cpp:90-99 with the float threshold folded to an integer): bit i of
+        // VA / HA says |a(r) - a(r+1)| <= K  /  |a(r, c) - a(r, c+1)| <= K for r = 32w + i.  Byte-parallel when the slab is a
+        // whole number of 4-column words: a thread takes 4 columns x 8 rows, one 32-bit load per row gives the 4 angles,
+        // VABSDIFF4 the four differences, and "d <= K" is bit 7 of ((K | 0x80) - (d & 0x7f)) & ~d per byte (K < 128);
+        // eight rows of those bits shifted together are the bytes of the four columns' mask words.
+        const bool simd_links = (myCW & 3) == 0 && (H & 7) == 0 && kp.k_ground < 128;  // uniform
+        if (simd_links) {
+            const int n_c4 = myCW >> 2;
+            const unsigned k4 = (static_cast<unsigned>(kp.k_ground) * 0x01010101u) | 0x80808080u;
+            uint8_t* m8 = reinterpret_cast<uint8_t*>(s_m32);
+            for (int t = tid; t < n_c4 * (H >> 3); t += NT) {
+                const int rb = t / n_c4, c4 = (t - rb * n_c4) << 2;
+                const int r0 = rb << 3;
+                const bool last_group = c4 + 4 == myCW;
+                unsigned acc_v = 0, acc_h = 0;
+                unsigned cur = *reinterpret_cast<const unsigned*>(s_angle + r0 * S8 + c4);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = r0 + i;
+                    const unsigned right = last_group ? static_cast<unsigned>(s_halo_angle[r]) : *reinterpret_cast<const unsigned*>(s_angle + r * S8 + c4 + 4);
+                    const unsigned dh = __vabsdiffu4(cur, __funnelshift_r(cur, right, 8));
+                    acc_h = (acc_h >> 1) | ((k4 - (dh & 0x7f7f7f7fu)) & ~dh & 0x80808080u);
+                    unsigned le_v = 0;
+                    if (r + 1 < H) {
+                        const unsigned down = *reinterpret_cast<const unsigned*>(s_angle + (r + 1) * S8 + c4);
+                        const unsigned dv = __vabsdiffu4(cur, down);
+                        le_v = (k4 - (dv & 0x7f7f7f7fu)) & ~dv & 0x80808080u;
+                        cur = down;
+                    }
+                    acc_v = (acc_v >> 1) | le_v;
+                }
+                const int w = r0 >> 5, byte = (r0 >> 3) & 3;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    m8[4 * ((MK_VA * NWD + w) * CW + c4 + j) + byte] = static_cast<uint8_t>(acc_v >> (8 * j));
+                    m8[4 * ((MK_HA * NWD + w) * CW + c4 + j) + byte] = static_cast<uint8_t>(acc_h >> (8 * j));
+                }
+            }
+            __syncthreads();
+        }
         for (int u = tid; u < n_units; u += NT) {
             const int w = u / myCW, c = u - w * myCW;
             const int lo = w * 32, nrow = min(32, H - lo);
             const unsigned valid = MW(MK_VALID, w, c);
             const bool last = (c == myCW - 1);
-            // angle-difference links (label.cpp:90-99 with the float threshold folded to an integer)
-            unsigned va = 0, ha = 0;  // bit i: |a(r) - a(r+1)| <= K  /  |a(r, c) - a(r, c+1)| <= K,  r = lo + i
-            int a_here = s_angle[lo * S8 + c];
-            const int a_first = a_here;
-            for (int i = 0; i < nrow; ++i) {
-                const int r = lo + i;
-                const int a_down = (r + 1 < H) ? s_angle[(r + 1) * S8 + c] : 0;
-                const int a_right = last ? s_halo_angle[r] : s_angle[r * S8 + c + 1];
-                if (r + 1 < H && abs(a_here - a_down) <= kp.k_ground) va |= 1u << i;
-                if (abs(a_here - a_right) <= kp.k_ground) ha |= 1u << i;
-                a_here = a_down;
+            unsigned va = 0, ha = 0;
+            const int a_first = s_angle[lo * S8 + c];
+            if (simd_links) {
+                const unsigned rows_mask = nrow < 32 ? (1u << nrow) - 1u : 0xffffffffu;  // bytes above H were not written
+                va = MW(MK_VA, w, c) & rows_mask;
+                ha = MW(MK_HA, w, c) & rows_mask;
+            } else {
+                int a_here = a_first;
+                for (int i = 0; i < nrow; ++i) {
+                    const int r = lo + i;
+                    const int a_down = (r + 1 < H) ? s_angle[(r + 1) * S8 + c] : 0;
+                    const int a_right = last ? s_halo_angle[r] : s_angle[r * S8 + c + 1];
+                    if (r + 1 < H && abs(a_here - a_down) <= kp.k_ground) va |= 1u << i;
+                    if (abs(a_here - a_right) <= kp.k_ground) ha |= 1u << i;
+                    a_here = a_down;
+                }
             }
             const unsigned valid_up = (w + 1 < NWD) ? MW(MK_VALID, w + 1, c) : 0u;
             const unsigned v = va & valid & ((valid >> 1) | (valid_up << 31));  // bit i: rows r and r+1 linked (both non-empty)
