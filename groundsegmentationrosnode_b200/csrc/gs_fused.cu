@@ -1646,6 +1646,8 @@ namespace {
 const void* select_kernel(int NW, int nt, int H, int CW, int CL, int W) {
     if (nt == 1024 && W == CL * CW) {
         if (NW == 1 && H == 64 && CW == 512 && CL == 4) return reinterpret_cast<const void*>(k_frame<1, 1024, 64, 512, 4>);   // C2 / C4: 64 x 2048 on 4 CTAs
+        if (NW == 1 && H == 64 && CW == 450 && CL == 4) return reinterpret_cast<const void*>(k_frame<1, 1024, 64, 450, 4>);   // the reference's Alfa_GS default: 64 x 1800 (alfa_gs.cpp:16-38)
+        if (NW == 1 && H == 64 && CW == 500 && CL == 4) return reinterpret_cast<const void*>(k_frame<1, 1024, 64, 500, 4>);   // the reference's cloud2range default: 64 x 2000 (cloud2range_node.cpp:274-329)
         if (NW == 1 && H == 16 && CW == 900 && CL == 2) return reinterpret_cast<const void*>(k_frame<1, 1024, 16, 900, 2>);   // C1: 16 x 1800 on 2 CTAs
         if (NW == 2 && H == 128 && CW == 256 && CL == 8) return reinterpret_cast<const void*>(k_frame<2, 1024, 128, 256, 8>);  // C3 / C5: 128 x 2048 on 8 CTAs
     }
