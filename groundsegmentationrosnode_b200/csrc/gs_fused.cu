@@ -28,6 +28,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include <math_constants.h>
 
 #include "gs_internal.h"
@@ -802,20 +803,24 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                 pb = load_point(i0 + 32);
                 return i0;
             };
-            auto place = [&](const float4 p4, const int i, const Lean& L) {
+            // `checked`: statistics runs and configurations without the certified fast path evaluate the exact projection for
+            // every point; the production instantiation keeps the hot path to the certified pixel, the key and one atomic,
+            // with everything else (padding lanes, uncertified points, the alias column) in one cold branch
+            const unsigned a_key = smem_base32 + off_range;  // shared-window address of the key slab
+            auto place = [&](auto checked_tag, const float4 p4, const int i, const Lean& L) {
+                constexpr bool CHECKED = decltype(checked_tag)::value;
                 unsigned k = 0x80000000u | lane;  // owner << 16 | slab address; this value is unique per lane: never matches
                 unsigned val = 0;                 // g << 16 | encoded range
                 int row = L.row, col = L.col;
                 unsigned enc = L.enc;
-                int st = 1;
-                if (i < N) {
-                    st = 0;
-                    if (!L.ok || !A.use_fast || stats1) {
+                bool have = L.ok && i < N;
+                if (CHECKED || !have) {
+                    if (i < N) {
                         // not certified: a gate drop, or the exact evaluation (every point when statistics are collected)
-                        st = A.use_fast ? (L.ok ? 0 : project_undecided(A, L, p4.y, __fmaf_rn(p4.x, p4.x, __fmul_rn(p4.y, p4.y)))) : 2;
-                        if (st == 2 || stats1) {
+                        int st = A.use_fast ? (L.ok ? 0 : project_undecided(A, L, p4.y, __fmaf_rn(p4.x, p4.x, __fmul_rn(p4.y, p4.y)))) : 2;
+                        if (st == 2 || (CHECKED && stats1)) {
                             const Proj pr = project_point_d(A.kp_dev, p4.x, p4.y, p4.z);
-                            if (stats1) {
+                            if (CHECKED && stats1) {
                                 if (st == 2) GS_STAT(ST_FALLBACK);
                                 else if ((st == 1) != (pr.row < 0) || (st == 0 && (row != pr.row || col != pr.col || enc != pr.enc))) GS_STAT(ST_MISMATCH);
                                 if (pr.row < 0) GS_STAT(ST_DROPPED);
@@ -828,13 +833,14 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                                 st = pr.row < 0 ? 1 : 0;
                             }
                         }
+                        have = st == 0;
+                        if (have && col == W) {  // Q2: at<ushort>(row, W) is flat index (row + 1) * W (only the exact path returns it)
+                            row += 1;
+                            col = 0;
+                        }
                     }
                 }
-                if (st == 0) {
-                    if (col == W) {  // Q2: at<ushort>(row, W) is flat index (row + 1) * W
-                        row += 1;
-                        col = 0;
-                    }
+                if (have) {
                     const int owner = SPEC ? col / CW : min(static_cast<int>(__umulhi(static_cast<unsigned>(col), A.cw_magic)), CL - 1);
                     const int lc = col - owner * CW;
                     k = (static_cast<unsigned>(owner) << 16) | static_cast<unsigned>(row * S16 + lc);
@@ -843,7 +849,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                 // points that share an order tag are 2^tag_shift consecutive lanes: the highest lane among those that hit the
                 // same pixel holds the latest point (xor-shuffles over the group; __match_any_sync would do the same for a
                 // whole warp but costs ~100 cycles of the address-divergence unit per call when all keys differ)
-                bool winner = st == 0;
+                bool winner = have;
                 if (tag_shift) {  // uniform; 1 for frames of 64 Ki .. 128 Ki points
                     const unsigned o1 = __shfl_xor_sync(0xffffffffu, k, 1);
                     if (o1 == k && !(lane & 1)) winner = false;
@@ -854,7 +860,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                     }
                 }
                 const bool local = winner && static_cast<int>(k >> 16) == rank;
-                if (local) atomicMax(s_key + (k & 0xffffu), val);
+                if (local) asm volatile("red.shared::cta.max.u32 [%0], %1;" ::"r"(a_key + 4u * (k & 0xffffu)), "r"(val) : "memory");
                 // remote pixels: queue the record (warp-aggregated slot claim)
                 const bool remote = winner && !local;
                 const unsigned rm = __ballot_sync(0xffffffffu, remote);
@@ -865,21 +871,25 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                     if (remote) {
                         const unsigned slot = base + __popc(rm & ((1u << lane) - 1u));
                         if (slot < A.rcap) rlist[slot] = make_uint2(k, val);
-                        if (stats1) GS_STAT(ST_REMOTE);
+                        if (CHECKED && stats1) GS_STAT(ST_REMOTE);
                     }
                 }
             };
-            float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb4 = na;
-            int ni = 0;
-            if (warp < n_punits) ni = load_unit(warp, na, nb4);
-            for (int u = warp; u < n_punits; u += NT / 32) {
-                const float4 pa = na, pb = nb4;
-                const int i0 = ni;
-                if (u + NT / 32 < n_punits) ni = load_unit(u + NT / 32, na, nb4);
-                const Lean La = project_lean(A, pa.x, pa.y, pa.z), Lb = project_lean(A, pb.x, pb.y, pb.z);  // straight-line: the two interleave
-                place(pa, i0, La);
-                place(pb, i0 + 32, Lb);
-            }
+            auto rounds = [&](auto checked_tag) {
+                float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb4 = na;
+                int ni = 0;
+                if (warp < n_punits) ni = load_unit(warp, na, nb4);
+                for (int u = warp; u < n_punits; u += NT / 32) {
+                    const float4 pa = na, pb = nb4;
+                    const int i0 = ni;
+                    if (u + NT / 32 < n_punits) ni = load_unit(u + NT / 32, na, nb4);
+                    const Lean La = project_lean(A, pa.x, pa.y, pa.z), Lb = project_lean(A, pb.x, pb.y, pb.z);  // straight-line: the two interleave
+                    place(checked_tag, pa, i0, La);
+                    place(checked_tag, pb, i0 + 32, Lb);
+                }
+            };
+            if (stats1 || !A.use_fast) rounds(std::true_type{});
+            else rounds(std::false_type{});
         }
         GS_PHASE(2);
         __threadfence();  // remote records and counts visible before the cluster-wide phase
