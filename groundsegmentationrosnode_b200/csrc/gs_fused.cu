@@ -118,7 +118,7 @@ __host__ __device__ constexpr Layout layout_hcw(int H, int CW, int NW) {
     const size_t tag_bytes = align_up(max_sz(range_bytes, static_cast<size_t>(H) * CW * 2), 16);
     const size_t angle_bytes = align_up(max_sz(static_cast<size_t>(H) * L.S8, static_cast<size_t>(4096) * 3), 16);  // 4096 = MAX_BLOCKS
     const size_t Hp = (static_cast<size_t>(H) + 7) & ~static_cast<size_t>(7);
-    const size_t misc_bytes = align_up(14 * 8 + static_cast<size_t>(8) * Hp * 4 + Hp * 4 + Hp + 2 * 8 * 4 + (8 + 20 + 64) * 4 + 64, 16);  // 8 = MAX_CL
+    const size_t misc_bytes = align_up(14 * 8 + static_cast<size_t>(8) * Hp * 4 + Hp * 4 + Hp + 2 * 8 * 4 + (8 + 20 + 64) * 4 + 64 + Hp + 16, 16);  // 8 = MAX_CL
     L.off_range = 0;
     L.off_tag = static_cast<unsigned>(range_bytes);
     L.off_angle = static_cast<unsigned>(range_bytes + tag_bytes);
@@ -652,6 +652,8 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
     unsigned* s_misc = s_flags + 2 * MAX_CL;                                            // [0] nmine, [1] scratch   (s_flags: [2 parities][MAX_CL], written by the other CTAs)
     unsigned* s_halo32 = s_misc + 8;                                                    // [5][4] halo mask words
     unsigned* s_scan = s_halo32 + 20;                                                   // [64] block scan scratch
+    uint8_t* s_haloL_angle = reinterpret_cast<uint8_t*>(s_scan + 64 + 16);              // [Hp] last angle column of the left neighbour (after the 16 statistics words)
+    unsigned* s_haloL_valid = reinterpret_cast<unsigned*>(s_haloL_angle + Hp);          // [4] its VALID words
 
     // lookup tables: shared-memory copies made once per CTA (the persistent kernel reuses them for every frame)
     double* s_cos_az = reinterpret_cast<double*>(smem_raw + off_lut);  // [CW]
@@ -892,7 +894,8 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             else rounds(std::false_type{});
         }
         GS_PHASE(2);
-        __threadfence();  // remote records and counts visible before the cluster-wide phase
+        // remote records and counts: barrier.cluster arrives with release and waits with acquire semantics at cluster scope,
+        // which orders the global stores / atomics above before the reads below in the other CTAs of the cluster — no __threadfence
         cluster.sync();   // #1: all local pixels committed everywhere
         if (tid == 0) s_misc[0] = 0;  // every thread has read the block count; the next frame's list is built during the output
 
@@ -1059,22 +1062,30 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                 out[r * W + col0 + c] = s_angle[r * S8 + c];
             }
         }
+        const int right_rank = (rank + 1 == CL) ? 0 : rank + 1;
+        const int left_rank = (rank == 0) ? CL - 1 : rank - 1;
+#define MW(kind, w, c) s_m32[((kind) * NWD + (w)) * CW + (c)]
+        // Halos are PUSHED into the neighbours' shared memory before the cluster barrier: my column 0 (angles, VALID words) is
+        // the left neighbour's right halo, my last column its right neighbour's left halo (column W-1's right neighbour is
+        // column 0: Label::WrapCols).  After the barrier nobody reads another CTA's angle slab or link words any more, which
+        // saves the cluster barrier that used to follow the link stage.
+        {
+            uint8_t* to_left = cluster.map_shared_rank(s_halo_angle, left_rank);
+            uint8_t* to_right = cluster.map_shared_rank(s_haloL_angle, right_rank);
+            for (int r = tid; r < H; r += NT) {
+                to_left[r] = s_angle[r * S8];
+                to_right[r] = s_angle[r * S8 + myCW - 1];
+            }
+            if (tid < NWD) {
+                cluster.map_shared_rank(s_halo32, left_rank)[0 * 4 + tid] = MW(MK_VALID, tid, 0);
+                cluster.map_shared_rank(s_haloL_valid, right_rank)[tid] = MW(MK_VALID, tid, myCW - 1);
+            }
+        }
         GS_PHASE(5);
-        cluster.sync();  // #4: angle slabs and VALID masks complete in the whole cluster
+        cluster.sync();  // #4: angle slabs, VALID masks and halos complete in the whole cluster
 
         GS_PHASE(6);
         // ================================================================================ G: links, runs, seeds, ground label
-        const int right_rank = (rank + 1 == CL) ? 0 : rank + 1;
-        const int left_rank = (rank == 0) ? CL - 1 : rank - 1;
-        const int left_last = min(CW, W - left_rank * CW) - 1;  // last local column of the left neighbour
-#define MW(kind, w, c) s_m32[((kind) * NWD + (w)) * CW + (c)]
-        // halo: angle column 0 and VALID of the right neighbour (column W-1's right neighbour is column 0: Label::WrapCols)
-        {
-            const uint8_t* r_angle = cluster.map_shared_rank(s_angle, right_rank);
-            for (int r = tid; r < H; r += NT) s_halo_angle[r] = r_angle[r * S8];
-            if (tid < NWD) s_halo32[0 * 4 + tid] = cluster.map_shared_rank(s_m32, right_rank)[(MK_VALID * NWD + tid) * CW + 0];
-        }
-        __syncthreads();
         const int n_units = myCW * NWD;  // one unit = 32 rows of one column
         // Angle-difference links (label.cpp:90-99 with the float threshold folded to an integer): bit i of
         // VA / HA says |a(r) - a(r+1)| <= K  /  |a(r, c) - a(r, c+1)| <= K for r = 32w + i.  Byte-parallel when the slab is a
@@ -1169,14 +1180,18 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             MW(MK_G, w, c) = gseed;
             MW(MK_KEEP, w, c) = eseed;
         }
-        GS_PHASE(7);
-        cluster.sync();  // #5: link words of every slab readable by the neighbours; the angle slab is free from here on
-        // static halos from the left neighbour: HM and HA of its last column (the edge between that column and my column 0)
-        if (tid < NWD) {
-            const unsigned* lm = cluster.map_shared_rank(s_m32, left_rank);
-            s_halo32[3 * 4 + tid] = lm[(MK_HM * NWD + tid) * CW + left_last];
-            s_halo32[4 * 4 + tid] = lm[(MK_HA * NWD + tid) * CW + left_last];
+        // the edge between the left neighbour's last column and my column 0: HA and HM words from the left halo
+        for (int r = tid; r < 32 * NWD; r += NT) {  // whole warps: one per 32 rows
+            const int w = r >> 5;
+            const bool le = r < H && abs(static_cast<int>(s_haloL_angle[min(r, H - 1)]) - static_cast<int>(s_angle[min(r, H - 1) * S8])) <= kp.k_ground;
+            const unsigned ha = __ballot_sync(0xffffffffu, le);
+            if (lane == 0) {
+                s_halo32[4 * 4 + w] = ha;
+                s_halo32[3 * 4 + w] = ha & s_haloL_valid[w] & MW(MK_VALID, w, 0);
+            }
         }
+        GS_PHASE(7);
+        __syncthreads();  // the angle slab is free from here on (the link scan reuses it)
         GS_PHASE(8);
         // Ground label = reachability from the accepted seeds (the Labeler's BFS, label.cpp:48-104).  Nodes are the
         // vertical runs of every column; horizontal links unite runs of adjacent columns in a 16-bit union-find forest.

@@ -48,7 +48,7 @@ rows = list(csv.reader(raw))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 hdr = rows[hi]
 body = [dict(zip(hdr, r)) for r in rows[hi + 1:] if len(r) == len(hdr)]
-lines = T.sass_lines(sys.argv[3] if len(sys.argv) > 3 else "k_frameILi1ELi1024ELi64")
+lines = T.sass_lines(sys.argv[3] if len(sys.argv) > 3 else "k_frameILi1ELi1024ELi64ELi512")
 STALLS = ["stall_barrier", "stall_short_sb", "stall_wait", "stall_long_sb", "stall_not_selected", "stall_branch_resolving", "stall_math", "stall_mio"]
 agg = collections.defaultdict(lambda: [0, 0] + [0] * len(STALLS))
 for d, l in zip(body, lines):
