@@ -1,5 +1,5 @@
 set -x
-D=gpurun_out/s41; mkdir -p $D
+D=gpurun_out/s43; mkdir -p $D
 python bench.py > $D/bench_default.json 2> $D/bench_default.err || exit 1
 python bench.py --impl reference --steps 3 --warmup 1 > $D/bench_reference.json 2> $D/bench_reference.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $D/launches.csv python bench.py --steps 2 --warmup 3 --frames 592 --e2e-frames 64 --no-cpu-baseline > $D/launches.log 2>&1
