@@ -949,8 +949,10 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
 
         GS_PHASE(4);
         // ================================================================================ A: angle image (column walks)
-        // one thread per (column, 32-row segment); bottom -> top like the reference (alfa_gs.cpp:347-382)
-        {
+        // one thread per (column, 32-row segment); bottom -> top like the reference (alfa_gs.cpp:347-382).  `checked`: statistics
+        // runs and configurations without the certified fast path; the production instantiation carries neither test.
+        auto angle_walk = [&](auto checked_tag) {
+            constexpr bool CHECKED = decltype(checked_tag)::value;
             const int nword = (H + 31) / 32;
             const int nseg = myCW * nword;
             for (int s = tid; s < nseg; s += NT) {
@@ -1004,13 +1006,13 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                             const float tm = __fadd_rn(sc, 12582912.0f);
                             const float diff = __fsub_rn(sc, __fsub_rn(tm, 12582912.0f));  // sc - rn(sc), exact
                             const int kk = (__float_as_int(tm) - 0x4B400000) - (diff < 0.0f ? 1 : 0);
-                            const bool sure = A.use_fast && fabsf(diff) > 4e-4f;  // false for NaN
+                            const bool sure = (!CHECKED || A.use_fast) && fabsf(diff) > 4e-4f;  // false for NaN
                             a_out = static_cast<unsigned>(kk);
-                            if (!sure || (A.stats & 1)) {
+                            if (!sure || (CHECKED && (A.stats & 1))) {
                                 const float alfa = atan2f_exact(dz, dx);       // :368
                                 const float scaled = __fmul_rn(alfa, 100.0f);  // :370
                                 const unsigned exact = static_cast<unsigned>(__float2int_rz(scaled));
-                                if ((A.stats & 1)) {
+                                if ((CHECKED && (A.stats & 1))) {
                                     const float fe = scaled - floorf(scaled);
                                     if (fminf(fe, 1.0f - fe) < 1e-3f) GS_STAT(ST_NEAR_ANGLE);
                                     if (!sure) GS_STAT(ST_FALLBACK);
@@ -1029,7 +1031,9 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                 // valid bits of this segment -> the column's VALID mask word
                 s_m32[(MK_VALID * NWD + wseg) * CW + c] = vbits;
             }
-        }
+        };
+        if ((A.stats & 1) || !A.use_fast) angle_walk(std::true_type{});
+        else angle_walk(std::false_type{});
         __syncthreads();
         if (A.sg_ws > 0) {
             // Alfa_GS::SavitskyGolaySmoothing (alfa_gs.cpp:705-713) = cv::filter2D with a ws x 1 kernel and BORDER_REFLECT101:
