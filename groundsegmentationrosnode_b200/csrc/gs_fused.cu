@@ -45,6 +45,12 @@ constexpr int MAX_BLOCKS = 4096;  // per frame: up to 1 Mi points
 constexpr int MAX_CL = 8;
 constexpr int MAX_H = 128;
 
+// constants of the cold classification path (project_undecided), in device memory behind the KParams copy
+struct GateConsts {
+    double range_lo_in, range_hi_in, range_lo_out, range_hi_out;  // range gates -/+ 1e-9 m
+    float alt_lo, alt_hi;                                         // altitude gates as floats
+};
+
 struct FusedArgs {
     KParams kp;
     Luts lut;
@@ -79,6 +85,7 @@ struct FusedArgs {
     unsigned cw_magic;         // ceil(2^32 / CW): owner = (col * cw_magic) >> 32 for col < 2^16
     unsigned ng_magic;         // ceil(2^32 / NG)
     const KParams* kp_dev;     // device-memory copy of kp for the out-of-line exact path
+    const GateConsts* gates_dev;  // device-memory constants of project_undecided
     int col_limit, col_wrap;   // largest column the fast path may return; GS_COL_WRAP
     double range_lo_in, range_hi_in, range_lo_out, range_hi_out;  // range gates -/+ 1e-9 m
     // lean fast path (project_lean): encoded range in 2^-UB fixed point, altitude gates in cell fixed point
@@ -512,8 +519,6 @@ struct Lean {
     int row, col;
     unsigned enc;
     bool ok;
-    float alt;     // for project_undecided
-    double range;  // for project_undecided
 };
 __device__ __forceinline__ Lean project_lean(const FusedArgs& A, float fx, float fy, float fz) {
     const KParams& kp = A.kp;
@@ -523,8 +528,8 @@ __device__ __forceinline__ Lean project_lean(const FusedArgs& A, float fx, float
     const float h2 = __fmaf_rn(fx, fx, __fmul_rn(fy, fy));
     const double rd = static_cast<double>(rsqrt_ftz(__fmaf_rn(fz, fz, h2)));
     const double r0 = __dmul_rn(s2, rd);
-    o.range = __fma_rn(__fma_rn(-r0, r0, s2), __dmul_rn(0.5, rd), r0);
-    const int ufix = __double2int_rz(__fma_rn(o.range, A.u_scale, A.u_c0));  // NaN -> 0, overflow saturates: both fail the test below
+    const double range = __fma_rn(__fma_rn(-r0, r0, s2), __dmul_rn(0.5, rd), r0);
+    const int ufix = __double2int_rz(__fma_rn(range, A.u_scale, A.u_c0));  // NaN -> 0, overflow saturates: both fail the test below
     const unsigned ufrac = static_cast<unsigned>(ufix) & ((1u << UB) - 1u);
     const bool range_ok = static_cast<unsigned>(ufix - ((1 << UB) + 1)) <= static_cast<unsigned>((65534 << UB) - 2) && ufrac - 1u <= (1u << UB) - 3u;
     const bool xy_ok = fy != 0.0f && h2 > 1e-30f;  // atan2(-0.0, x < 0) = -pi in the reference (Q3); the flush-to-zero forms need h2 > 0
@@ -533,8 +538,8 @@ __device__ __forceinline__ Lean project_lean(const FusedArgs& A, float fx, float
     const float h = __fmul_rn(h2, rsqrt_ftz(h2));
     float t = atan01(__fmul_rn(fminf(az, h), rcp_ftz(fmaxf(az, h))));
     if (az > h) t = 1.57079632679489662f - t;
-    o.alt = __uint_as_float(__float_as_uint(t) | (__float_as_uint(fz) & 0x80000000u));
-    const int altfix = __float2int_rn(__fmul_rn(o.alt, A.alt_to_fix));
+    const float alt = __uint_as_float(__float_as_uint(t) | (__float_as_uint(fz) & 0x80000000u));
+    const int altfix = __float2int_rn(__fmul_rn(alt, A.alt_to_fix));
     const int rowfix = A.row0_fix - altfix;
     const unsigned rfrac = static_cast<unsigned>(rowfix) & ((1u << FB) - 1u);
     // azimuth in [0, 2 pi): octant reduction, reflections in exact fixed point
@@ -556,12 +561,26 @@ __device__ __forceinline__ Lean project_lean(const FusedArgs& A, float fx, float
     o.ok = range_ok && xy_ok && gate_ok && edges_ok && box_ok;
     return o;
 }
-// a point project_lean did not certify: 1 = certainly dropped by a gate (alfa_gs.cpp:261, :269), 2 = exact evaluation
-__device__ __forceinline__ int project_undecided(const FusedArgs& A, const Lean& o, float fy, float h2ok) {
-    if (o.range < A.range_lo_out || o.range > A.range_hi_out) return 1;  // outside the range gates by more than 1e-9 m
-    if (!(o.range > A.range_lo_in && o.range < A.range_hi_in)) return 2;  // within 1e-9 m of a gate, or not finite
-    if (fy == 0.0f || !(h2ok > 1e-30f)) return 2;                         // the float altitude is not meaningful
-    if (o.alt < A.alt_lo - 1e-6f || o.alt > A.alt_hi + 1e-6f) return 1;   // outside the altitude gates by more than 1e-6 rad
+// a point project_lean did not certify: 1 = certainly dropped by a gate (alfa_gs.cpp:261, :269), 2 = exact evaluation.
+// Cold path: the range and the altitude are recomputed here (the same arithmetic as in project_lean) rather than kept
+// alive across the hot loop.
+__device__ __noinline__ int project_undecided(const GateConsts* __restrict__ Ap, float fx, float fy, float fz) {
+    const GateConsts& A = *Ap;
+    const double x = fx, y = fy, z = fz;
+    const double s2 = __fma_rn(x, x, __fma_rn(y, y, __dmul_rn(z, z)));
+    const float h2 = __fmaf_rn(fx, fx, __fmul_rn(fy, fy));
+    const double rd = static_cast<double>(rsqrt_ftz(__fmaf_rn(fz, fz, h2)));
+    const double r0 = __dmul_rn(s2, rd);
+    const double range = __fma_rn(__fma_rn(-r0, r0, s2), __dmul_rn(0.5, rd), r0);
+    if (range < A.range_lo_out || range > A.range_hi_out) return 1;  // outside the range gates by more than 1e-9 m
+    if (!(range > A.range_lo_in && range < A.range_hi_in)) return 2;  // within 1e-9 m of a gate, or not finite
+    if (fy == 0.0f || !(h2 > 1e-30f)) return 2;                       // the float altitude is not meaningful
+    const float az = fabsf(fz);
+    const float h = __fmul_rn(h2, rsqrt_ftz(h2));
+    float t = atan01(__fmul_rn(fminf(az, h), rcp_ftz(fmaxf(az, h))));
+    if (az > h) t = 1.57079632679489662f - t;
+    const float alt = __uint_as_float(__float_as_uint(t) | (__float_as_uint(fz) & 0x80000000u));
+    if (alt < A.alt_lo - 1e-6f || alt > A.alt_hi + 1e-6f) return 1;   // outside the altitude gates by more than 1e-6 rad
     return 2;
 }
 
@@ -819,7 +838,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                 if (CHECKED || !have) {
                     if (i < N) {
                         // not certified: a gate drop, or the exact evaluation (every point when statistics are collected)
-                        int st = A.use_fast ? (L.ok ? 0 : project_undecided(A, L, p4.y, __fmaf_rn(p4.x, p4.x, __fmul_rn(p4.y, p4.y)))) : 2;
+                        int st = A.use_fast ? (L.ok ? 0 : project_undecided(A.gates_dev, p4.x, p4.y, p4.z)) : 2;
                         if (st == 2 || (CHECKED && stats1)) {
                             const Proj pr = project_point_d(A.kp_dev, p4.x, p4.y, p4.z);
                             if (CHECKED && stats1) {
@@ -1758,10 +1777,22 @@ int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const Sg
     fs.n_sms = n_sms;
     fs.max_clusters = max_clusters;
     if (!fs.d_const) {
-        e = cudaMalloc(&fs.d_const, sizeof(KParams));
+        e = cudaMalloc(&fs.d_const, sizeof(KParams) + sizeof(GateConsts));
         if (e != cudaSuccess) return static_cast<int>(e);
     }
     e = cudaMemcpy(fs.d_const, &kp, sizeof(KParams), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    {
+        static_assert(sizeof(KParams) % 8 == 0, "GateConsts follows KParams in one allocation");
+        GateConsts g;
+        g.range_lo_in = kp.min_range + 1e-9;
+        g.range_hi_in = kp.max_range - 1e-9;
+        g.range_lo_out = kp.min_range - 1e-9;
+        g.range_hi_out = kp.max_range + 1e-9;
+        g.alt_lo = static_cast<float>(kp.min_angle);
+        g.alt_hi = static_cast<float>(kp.max_angle);
+        e = cudaMemcpy(static_cast<unsigned char*>(fs.d_const) + sizeof(KParams), &g, sizeof(g), cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) return static_cast<int>(e);
     fs.configured = true;
     return 0;
@@ -1855,6 +1886,7 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
         a.cw_magic = static_cast<unsigned>((0x100000000ull + lay.CW - 1) / lay.CW);
         a.ng_magic = static_cast<unsigned>((0x100000000ull + lay.NG - 1) / lay.NG);
         a.kp_dev = static_cast<const KParams*>(fs.d_const);
+        a.gates_dev = reinterpret_cast<const GateConsts*>(static_cast<const unsigned char*>(fs.d_const) + sizeof(KParams));
         a.col_limit = c2r ? kp.W - 1 : kp.W;
         a.sg_ws = fs.smooth ? fs.sg.ws : 0;
         for (int k = 0; k < 11; ++k) a.sg_t[k] = fs.sg.t[k];
