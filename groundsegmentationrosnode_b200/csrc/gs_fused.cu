@@ -11,17 +11,16 @@
 //                            Cloud2RangeNode::CloudCb src/cloud2range_node.cpp:396-455)
 //   A  angle image           Alfa_GS::CreateAngleImg    src/alfa_gs.cpp:335-386
 //   G  ground labelling      Alfa_GS::EraseBFS seeds :720-739 + Label::LabelOneComponent Labeler/label.cpp:48-104,
-//                            restated as bit-parallel flood fill over per-column row masks
+//                            restated as reachability in a union-find forest over vertical runs
 //   D  dilate + erase        GetUniformKernel + cv::dilate + erase  src/alfa_gs.cpp:747-764
 //   B  back-projection       Alfa_GS::CameraCb  src/alfa_gs.cpp:997-1074 (variant: range2cloud_node.cpp:64-91)
 //
-// Pixel ownership ("the last point in input order wins", alfa_gs.cpp:291) without atomics on the common path: every
-// group of 32 consecutive points carries the order tag g = index/32 + 1; lanes that hit the same pixel inside a warp
-// are resolved with __match_any_sync (highest lane wins); across warps a pixel's 16-bit tag in shared memory is raised
-// by plain stores, verified after a barrier (compare-and-swap only for the rare lost race), and the winner then stores
-// its range.  Blocks of 256 points are dealt to the CTA predicted (from 4 sampled points) to own their columns, so for
-// ordered clouds (sensor firing order or row-major organised) almost every store is CTA-local; the rest go through a
-// small remote list that is applied over distributed shared memory after the local rounds.
+// Pixel ownership ("the last point in input order wins", alfa_gs.cpp:291): one 32-bit shared-memory max per point on the
+// key (order tag << 16 | encoded range), order tag = (index >> s) + 1 with the smallest s that fits 16 bits; points that
+// share a tag are adjacent lanes and are resolved with shuffles first.  Blocks of 256 points are dealt to the CTA predicted
+// (from 4 sampled points) to own their columns, so for ordered clouds (sensor firing order or row-major organised) almost
+// every pixel is CTA-local; the rest go through a small remote list that is applied over distributed shared memory after
+// the local rounds.  DESIGN.md 4.1 describes every stage and what was measured on the way.
 #include <cooperative_groups.h>
 
 #include <algorithm>
