@@ -1058,22 +1058,55 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             // float32 accumulation in tap order, round half to even, saturate (pinned against OpenCV in tests/golden).
             // Smoothed angles stay below 256 (157 x the positive tap sum 1.19).  Filter into the (idle) tag slab, copy back.
             uint8_t* tmp = reinterpret_cast<uint8_t*>(s_tag);
-            const int half = A.sg_ws >> 1;
-            for (int i = tid; i < H * myCW; i += NT) {
-                const int r = i / myCW, c = i - r * myCW;
-                float acc = 0.0f;
-                for (int k = 0; k < A.sg_ws; ++k) {
-                    int rr = r + k - half;
-                    while (rr < 0 || rr >= H) rr = rr < 0 ? -rr : 2 * H - 2 - rr;
-                    acc = __fadd_rn(acc, __fmul_rn(A.sg_t[k], static_cast<float>(s_angle[rr * S8 + c])));
+            // a thread filters 8 rows of one column from a window held in registers (8 + ws - 1 loads for 8 outputs)
+            auto sg_pass = [&](auto ws_tag) {
+                constexpr int WS = decltype(ws_tag)::value, HALF = WS / 2, RB = 8;
+                const int n_rb = (H + RB - 1) / RB;
+                for (int t = tid; t < myCW * n_rb; t += NT) {
+                    const int rb = t / myCW, c = t - rb * myCW;
+                    const int r0 = rb * RB;
+                    float v[RB + 2 * HALF];
+#pragma unroll
+                    for (int j = 0; j < RB + 2 * HALF; ++j) {
+                        int rr = r0 + j - HALF;
+                        while (rr < 0 || rr >= H) rr = rr < 0 ? -rr : 2 * H - 2 - rr;  // BORDER_REFLECT101
+                        v[j] = static_cast<float>(s_angle[rr * S8 + c]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < RB; ++i) {
+                        if (r0 + i < H) {
+                            float acc = 0.0f;
+#pragma unroll
+                            for (int k = 0; k < WS; ++k) acc = __fadd_rn(acc, __fmul_rn(A.sg_t[k], v[i + k]));
+                            tmp[(r0 + i) * S8 + c] = static_cast<uint8_t>(max(0, min(255, __float2int_rn(acc))));
+                        }
+                    }
                 }
-                const int v = __float2int_rn(acc);
-                tmp[r * S8 + c] = static_cast<uint8_t>(max(0, min(255, v)));
+            };
+            if (H >= 8 && A.sg_ws == 5) sg_pass(std::integral_constant<int, 5>{});
+            else if (H >= 8 && A.sg_ws == 7) sg_pass(std::integral_constant<int, 7>{});
+            else if (H >= 8 && A.sg_ws == 9) sg_pass(std::integral_constant<int, 9>{});
+            else if (H >= 8 && A.sg_ws == 11) sg_pass(std::integral_constant<int, 11>{});
+            else {
+                const int half = A.sg_ws >> 1;
+                for (int i = tid; i < H * myCW; i += NT) {
+                    const int r = i / myCW, c = i - r * myCW;
+                    float acc = 0.0f;
+                    for (int k = 0; k < A.sg_ws; ++k) {
+                        int rr = r + k - half;
+                        while (rr < 0 || rr >= H) rr = rr < 0 ? -rr : 2 * H - 2 - rr;
+                        acc = __fadd_rn(acc, __fmul_rn(A.sg_t[k], static_cast<float>(s_angle[rr * S8 + c])));
+                    }
+                    const int v = __float2int_rn(acc);
+                    tmp[r * S8 + c] = static_cast<uint8_t>(max(0, min(255, v)));
+                }
             }
             __syncthreads();
-            for (int i = tid; i < H * myCW; i += NT) {
-                const int r = i / myCW, c = i - r * myCW;
-                s_angle[r * S8 + c] = tmp[r * S8 + c];
+            {
+                // copy back whole rows as 32-bit words (S8 is a multiple of 4; the padding columns are never read)
+                unsigned* dst = reinterpret_cast<unsigned*>(s_angle);
+                const unsigned* src = reinterpret_cast<const unsigned*>(tmp);
+                for (int i = tid; i < (H * S8) >> 2; i += NT) dst[i] = src[i];
             }
             __syncthreads();
         }
