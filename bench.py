@@ -36,7 +36,7 @@ METRIC = "frames/s, 64x2048 cloud->range->ground->cloud (points/s alongside)"
 WORKLOAD = "C4: synthetic HDL-64E 64x2048 frames (~120k pts), pool of 64 distinct frames tiled to the batch"
 N_DISTINCT = 64
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_frame launch / frames in it (ncu --set full, profiles/r1_fused_ncu.md)
-TRAFFIC_BYTES_PER_FRAME = 905146112 / 296  # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch over 296 frames (profiles/r1_final_ncu_raw_selected.txt)
+TRAFFIC_BYTES_PER_FRAME = 901476608 / 296  # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch over 296 frames (profiles/r1_final_ncu_raw_selected.txt)
 
 
 def rank_info():
