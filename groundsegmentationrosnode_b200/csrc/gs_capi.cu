@@ -158,6 +158,8 @@ struct gs_ctx {
     size_t d_in_cap[2] = {0, 0};
     uint16_t* d_res[2] = {nullptr, nullptr};
     float* d_cloud[2] = {nullptr, nullptr};
+    float* d_packed[2] = {nullptr, nullptr};              // the clouds of a wave packed back to back
+    unsigned long long* d_prefix[2] = {nullptr, nullptr};  // [slot_frames + 1]
     unsigned* d_counts[2] = {nullptr, nullptr};
     unsigned* h_counts[2] = {nullptr, nullptr};  // pinned
     int slot_frames = 0;
@@ -228,6 +230,8 @@ void free_stage(gs_ctx* c) {
     c->d_a = c->d_b = c->d_c = nullptr; c->d_lab = nullptr; c->d_lab32 = nullptr; c->d_xyz = nullptr;
     for (int k = 0; k < 2; ++k) {
         cudaFree(c->d_in[k]); cudaFree(c->d_res[k]); cudaFree(c->d_cloud[k]); cudaFree(c->d_counts[k]);
+        cudaFree(c->d_packed[k]); cudaFree(c->d_prefix[k]);
+        c->d_packed[k] = nullptr; c->d_prefix[k] = nullptr;
         if (c->h_counts[k]) cudaFreeHost(c->h_counts[k]);
         c->d_in[k] = nullptr; c->d_in_cap[k] = 0; c->d_res[k] = nullptr; c->d_cloud[k] = nullptr; c->d_counts[k] = nullptr;
         c->h_counts[k] = nullptr;
@@ -986,6 +990,8 @@ int gs_process_batch_host(gs_ctx* ctx, const float* h_points_xyzi, const int64_t
     if (ctx->slot_frames < wave) {
         for (int k = 0; k < 2; ++k) {
             cudaFree(ctx->d_res[k]); cudaFree(ctx->d_cloud[k]); cudaFree(ctx->d_counts[k]);
+            cudaFree(ctx->d_packed[k]); cudaFree(ctx->d_prefix[k]);
+            ctx->d_packed[k] = nullptr; ctx->d_prefix[k] = nullptr;
             if (ctx->h_counts[k]) cudaFreeHost(ctx->h_counts[k]);
             ctx->d_res[k] = nullptr; ctx->d_cloud[k] = nullptr; ctx->d_counts[k] = nullptr; ctx->h_counts[k] = nullptr;
         }
@@ -993,6 +999,8 @@ int gs_process_batch_host(gs_ctx* ctx, const float* h_points_xyzi, const int64_t
         for (int k = 0; k < 2; ++k) {
             CU(cudaMalloc(&ctx->d_res[k], static_cast<size_t>(wave) * P * 2));
             CU(cudaMalloc(&ctx->d_cloud[k], static_cast<size_t>(wave) * P * 16));
+            CU(cudaMalloc(&ctx->d_packed[k], static_cast<size_t>(wave) * P * 16));
+            CU(cudaMalloc(&ctx->d_prefix[k], (static_cast<size_t>(wave) + 1) * sizeof(unsigned long long)));
             CU(cudaMalloc(&ctx->d_counts[k], static_cast<size_t>(wave) * 4));
             CU(cudaMallocHost(&ctx->h_counts[k], static_cast<size_t>(wave) * 4));
         }
@@ -1039,6 +1047,9 @@ int gs_process_batch_host(gs_ctx* ctx, const float* h_points_xyzi, const int64_t
         const int rc2 = run_wave(ctx, base, 16, ctx->d_offsets + f0, nf, max_points, nullptr, nullptr, ctx->d_res[k], ctx->d_cloud[k],
                                  ctx->d_counts[k]);
         if (rc2) return rc2;
+        if (h_xyz4_out)
+            launch_pack_clouds(launch_of(ctx), reinterpret_cast<const float4*>(ctx->d_cloud[k]), ctx->d_counts[k], nf, P, ctx->d_prefix[k],
+                               reinterpret_cast<float4*>(ctx->d_packed[k]));
         CU(cudaMemcpyAsync(ctx->h_counts[k], ctx->d_counts[k], static_cast<size_t>(nf) * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaEventRecord(ctx->ev_done[k], ctx->stream));
         return GS_OK;
@@ -1051,17 +1062,16 @@ int gs_process_batch_host(gs_ctx* ctx, const float* h_points_xyzi, const int64_t
         if (h_no_ground_out)
             CU(cudaMemcpyAsync(h_no_ground_out + static_cast<size_t>(f0) * P, ctx->d_res[k], static_cast<size_t>(nf) * P * 2,
                                cudaMemcpyDeviceToHost, ctx->copy_out));
+        const int64_t wave_first = out_cursor;
         for (int f = 0; f < nf; ++f) {
             const unsigned n = ctx->h_counts[k][f];
-            if (h_xyz4_out) {
-                if (static_cast<uint64_t>(out_cursor) + n > xyz4_capacity) return fail(ctx, GS_EINVAL, "xyz4 output capacity exceeded at frame %d", f0 + f);
-                if (n)
-                    CU(cudaMemcpyAsync(h_xyz4_out + 4 * out_cursor, ctx->d_cloud[k] + 4 * static_cast<size_t>(f) * P, static_cast<size_t>(n) * 16,
-                                       cudaMemcpyDeviceToHost, ctx->copy_out));
-            }
+            if (h_xyz4_out && static_cast<uint64_t>(out_cursor) + n > xyz4_capacity) return fail(ctx, GS_EINVAL, "xyz4 output capacity exceeded at frame %d", f0 + f);
             out_cursor += n;
             if (h_out_offsets) h_out_offsets[f0 + f + 1] = out_cursor;
         }
+        if (h_xyz4_out && out_cursor > wave_first)  // the wave's clouds, packed on the device, in one copy
+            CU(cudaMemcpyAsync(h_xyz4_out + 4 * wave_first, ctx->d_packed[k], static_cast<size_t>(out_cursor - wave_first) * 16, cudaMemcpyDeviceToHost,
+                               ctx->copy_out));
         CU(cudaEventRecord(ctx->ev_out[k], ctx->copy_out));
         return GS_OK;
     };

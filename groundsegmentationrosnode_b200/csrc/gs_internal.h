@@ -89,6 +89,9 @@ void launch_erase(const Launch& L, const KParams& kp, int frames, const uint16_t
 void launch_backproject(const Launch& L, const KParams& kp, const Luts& lut, int frames, const uint16_t* image,
                         const unsigned* rowcount, float* xyz4, unsigned* counts, bool range_as_double);
 void launch_rowcount(const Launch& L, const KParams& kp, int frames, const uint16_t* image, unsigned* rowcount);
+// host batch path: packs the per-frame cloud slabs [frames][P] back to back (prefix: frames + 1 entries of device scratch)
+void launch_pack_clouds(const Launch& L, const float4* slabs, const unsigned* counts, int frames, size_t P, unsigned long long* prefix,
+                        float4* packed);
 // N3 evaluation: Alfa_GS::CreateLabeledRangeImage (32-byte PointXYZRGB records) and the counters of CheckNumberOfDetectedRIdGnd
 size_t label_image_scratch_bytes(size_t n);
 void launch_label_image(const Launch& L, const KParams& kp, const void* points32, size_t n, uint8_t* flags, int* flat, uint8_t* summary,

@@ -667,6 +667,44 @@ __global__ void __launch_bounds__(256) k_evaluate(const uint16_t* __restrict__ o
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// host batch path: the clouds of a wave, one slab of P records per frame, are packed back to back on the device so that
+// they leave with ONE device-to-host copy (a copy per frame costs ~10 us of DMA set-up each and stalls the pipeline)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_count_prefix(const unsigned* __restrict__ counts, int n, unsigned long long* __restrict__ prefix) {
+    // exclusive prefix sum of up to a few thousand frame counts by one block
+    __shared__ unsigned long long warp_sum[32];
+    __shared__ unsigned long long carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const unsigned long long v = i < n ? counts[i] : 0ull;
+        unsigned long long incl = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((threadIdx.x & 31) >= d) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        unsigned long long before = carry_s;
+        for (int w = 0; w < (threadIdx.x >> 5); ++w) before += warp_sum[w];
+        if (i < n) prefix[i] = before + incl - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry_s = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) prefix[n] = carry_s;
+}
+__global__ void __launch_bounds__(256) k_pack_clouds(const float4* __restrict__ slabs, const unsigned* __restrict__ counts,
+                                                     const unsigned long long* __restrict__ prefix, size_t P, float4* __restrict__ packed) {
+    const int f = blockIdx.y;
+    const unsigned n = counts[f];
+    const float4* src = slabs + static_cast<size_t>(f) * P;
+    float4* dst = packed + prefix[f];
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 inline dim3 pixel_grid(const KParams& kp, int frames) { return dim3((kp.P + 255) / 256, frames); }
 
 }  // namespace
@@ -792,4 +830,11 @@ void launch_evaluate(const Launch& L, const KParams& kp, const uint16_t* og, con
     ++*L.n_launches;
 }
 
+void launch_pack_clouds(const Launch& L, const float4* slabs, const unsigned* counts, int frames, size_t P, unsigned long long* prefix,
+                        float4* packed) {
+    if (frames <= 0) return;
+    k_count_prefix<<<1, 1024, 0, L.stream>>>(counts, frames, prefix);
+    k_pack_clouds<<<dim3(8, static_cast<unsigned>(frames)), 256, 0, L.stream>>>(slabs, counts, prefix, P, packed);
+    *L.n_launches += 2;
+}
 }  // namespace gs
