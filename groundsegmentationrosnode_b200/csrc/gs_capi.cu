@@ -403,7 +403,7 @@ int run_wave_staged(gs_ctx* ctx, const void* d_points, size_t stride, const long
     launch_ccl(L, kp, frames, range, angle, nullptr, kp.k_ground, s.parent);
     launch_ground(L, kp, frames, range, angle, s.parent, s.seed_row, s.eseed, s.label);
     launch_erase(L, kp, frames, range, s.label, res, s.rowcount);
-    if (xyz_out)
+    if (xyz_out || counts_out)  // the counts come out of the back-projection's slot computation (fused kernel: always written)
         launch_backproject(L, kp, ctx->lut, frames, res, s.rowcount, xyz_out, counts_out ? counts_out : s.counts,
                            ctx->params.variant == GS_VARIANT_CLOUD2RANGE);
     const cudaError_t e = cudaGetLastError();

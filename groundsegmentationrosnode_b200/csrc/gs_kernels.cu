@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(256) k_backproject(const uint16_t* __restrict_
             before += (w < static_cast<int>(warp)) ? t : 0u;
             total += t;
         }
-        if (enc != 0) {
+        if (enc != 0 && xyz) {  // xyz == nullptr: the caller wants the counts only
             const unsigned slot = running + before + __popc(ballot & ((1u << lane) - 1u));
             const double rng_d = decode_range(kp, enc);
             const double rng = RANGE_AS_DOUBLE ? rng_d : static_cast<double>(__double2float_rn(rng_d));  // alfa_gs.cpp:1027,1045 vs range2cloud_node.cpp:76

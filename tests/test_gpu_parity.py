@@ -381,6 +381,35 @@ def test_union_stage_stress_frames(oracle, noise_sigma, dropout):
                     assert int(d_cnt[f]) == want[f % 3]["xyz"].shape[0]
 
 
+@pytest.mark.parametrize("preset", [P.GS_PRESET_CLOUD2RANGE_DEFAULT, P.GS_PRESET_HDL64E_2048])
+def test_repair_gaps_in_the_pipeline(oracle, preset):
+    """N2: with repair_gaps on, RepairGaps(range, 5, 1.0f) feeds the angle image only (cloud2range_node.cpp:468-471, typed
+    version); such a configuration runs on the per-stage kernels.  Frame and batch entry points against the oracle."""
+    import torch
+
+    p = P.preset(preset).copy(repair_gaps=1)
+    H, W = p.shape
+    frames = [synth.make_frame(p, synth.SEED0 + 700 + k, dropout=0.15) for k in range(3)]
+    want = [oracle.process_frame(p, f) for f in frames]
+    assert not np.array_equal(want[0]["angle"], oracle.process_frame(p.copy(repair_gaps=0), frames[0])["angle"]), "RepairGaps had no effect"
+    with capi.Context(p) as ctx:
+        for f, w in zip(frames, want):
+            got = ctx.process_frame(f)
+            for k in ("range", "angle", "no_ground"):
+                assert np.array_equal(got[k], w[k]), k
+            assert np.array_equal(got["xyz"], w["xyz"])
+        offs = np.concatenate([[0], np.cumsum([f.shape[0] for f in frames])]).astype(np.int64)
+        d_pts = torch.from_numpy(np.concatenate(frames)).cuda()
+        d_res = torch.zeros((3, H, W), dtype=torch.int16, device="cuda")
+        d_cnt = torch.zeros(3, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        ctx.process_batch_device(d_pts.data_ptr(), offs, 3, 0, 0, d_res.data_ptr(), 0, d_cnt.data_ptr())
+        ctx.synchronize()
+        for k in range(3):
+            assert np.array_equal(d_res[k].cpu().numpy().view(np.uint16), want[k]["no_ground"])
+            assert int(d_cnt[k]) == want[k]["xyz"].shape[0]
+
+
 def test_set_params_recomputes_derived(ctxs, oracle):
     """gs_set_params replaces Alfa_GS::UpdateSegmentationSettings (alfa_gs.cpp:1122-1136) and, unlike it, refreshes
     the derived values."""
