@@ -410,6 +410,39 @@ def test_repair_gaps_in_the_pipeline(oracle, preset):
             assert int(d_cnt[k]) == want[k]["xyz"].shape[0]
 
 
+def test_frames_beyond_the_fused_kernels_point_limit(oracle):
+    """A frame with more than 2^20 points (many returns per pixel: the last one wins) cannot take the fused kernel; the wave
+    it is in runs on the per-stage kernels.  Same results, frame and batch entry points."""
+    import torch
+
+    p = P.preset(P.GS_PRESET_HDL64E_2048)
+    H, W = p.shape
+    small = synth.make_frame(p, synth.SEED0 + 800)
+    big = np.concatenate([synth.make_frame(p, synth.SEED0 + 801 + k) for k in range(9)])
+    assert big.shape[0] > (1 << 20)
+    want_big, want_small = oracle.process_frame(p, big), oracle.process_frame(p, small)
+    with capi.Context(p) as ctx:
+        l0 = ctx.stats().kernel_launches
+        got = ctx.process_frame(big)
+        assert ctx.stats().kernel_launches - l0 > 1, "expected the per-stage kernels"
+        for k in ("range", "angle", "no_ground"):
+            assert np.array_equal(got[k], want_big[k]), k
+        assert np.array_equal(got["xyz"], want_big["xyz"])
+        offs = np.array([0, small.shape[0], small.shape[0] + big.shape[0]], np.int64)
+        d_pts = torch.from_numpy(np.concatenate([small, big])).cuda()
+        d_res = torch.zeros((2, H, W), dtype=torch.int16, device="cuda")
+        d_xyz = torch.zeros((2, H * W, 4), dtype=torch.float32, device="cuda")
+        d_cnt = torch.zeros(2, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        ctx.process_batch_device(d_pts.data_ptr(), offs, 2, 0, 0, d_res.data_ptr(), d_xyz.data_ptr(), d_cnt.data_ptr())
+        ctx.synchronize()
+        for k, w in enumerate((want_small, want_big)):
+            assert np.array_equal(d_res[k].cpu().numpy().view(np.uint16), w["no_ground"])
+            n = int(d_cnt[k])
+            assert n == w["xyz"].shape[0]
+            assert np.array_equal(d_xyz[k, :n].cpu().numpy(), w["xyz"])
+
+
 def test_set_params_recomputes_derived(ctxs, oracle):
     """gs_set_params replaces Alfa_GS::UpdateSegmentationSettings (alfa_gs.cpp:1122-1136) and, unlike it, refreshes
     the derived values."""
