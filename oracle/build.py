@@ -1,9 +1,11 @@
 """Build recipe for the CPU oracle — TEST INFRASTRUCTURE ONLY.
 
   oracle/libgs_oracle.so      the restated oracle (oracle/gs_oracle.cpp)
-  oracle/_ref/libgs_ref.so    the reference's own Labeler/label.cpp + lib/utils.h, compiled verbatim from
-                              /root/reference against oracle/shim (only where /root/reference exists;
-                              the GPU box uses the prebuilt file that travels with the snapshot)
+  oracle/_ref/libgs_ref.so    the reference's OWN sources — Labeler/label.cpp, lib/utils.h, src/alfa_gs.cpp,
+                              src/alfa_node.cpp, src/cloud2range_node.cpp, src/range2cloud_node.cpp — compiled
+                              verbatim from /root/reference against the stand-in ROS / PCL / OpenCV headers of
+                              oracle/shim (only where /root/reference exists; the GPU box uses the prebuilt
+                              file that travels with the snapshot)
 
 Both are git-ignored build products.  Usage: python oracle/build.py [--force]
 """
@@ -38,12 +40,18 @@ def build_ref(force=False):
     and no prebuilt library travelled."""
     if not os.path.isdir(REFERENCE):
         return REF_SO if os.path.exists(REF_SO) else None
-    src = [os.path.join(HERE, "ref_wrap.cpp"), os.path.join(REFERENCE, "Labeler", "label.cpp"),
-           os.path.join(HERE, "shim", "cv_bridge", "cv_bridge.h")]
-    if force or _stale(REF_SO, src):
+    # the reference's own translation units, compiled where they lie (src/cloud2range_node.cpp and src/range2cloud_node.cpp
+    # carry a `main` each and are pulled in by their wrappers)
+    ref_units = [os.path.join(REFERENCE, "Labeler", "label.cpp"), os.path.join(REFERENCE, "src", "alfa_gs.cpp"),
+                 os.path.join(REFERENCE, "src", "alfa_node.cpp")]
+    wrappers = [os.path.join(HERE, w) for w in ("ref_wrap.cpp", "ref_alfa_wrap.cpp", "ref_c2r_wrap.cpp", "ref_r2c_wrap.cpp")]
+    deps = [os.path.join(HERE, "shim", "gsref_cv.h"), os.path.join(HERE, "shim", "gsref_ros.h"),
+            os.path.join(REFERENCE, "src", "cloud2range_node.cpp"), os.path.join(REFERENCE, "src", "range2cloud_node.cpp")]
+    if force or _stale(REF_SO, ref_units + wrappers + deps + [os.path.abspath(__file__)]):
         os.makedirs(os.path.dirname(REF_SO), exist_ok=True)
-        subprocess.check_call(["g++", *CXXFLAGS, "-I", os.path.join(HERE, "shim"), "-I", REFERENCE,
-                               "-I", os.path.join(REFERENCE, "lib"), src[0], src[1], "-o", REF_SO])
+        # -w: the reference does not compile warning-free (e.g. AlfaNode::process_config returns nothing)
+        subprocess.check_call(["g++", *CXXFLAGS, "-w", "-I", os.path.join(HERE, "shim"), "-I", REFERENCE,
+                               "-I", os.path.join(REFERENCE, "lib"), *wrappers, *ref_units, "-o", REF_SO])
     return REF_SO
 
 

@@ -9,14 +9,14 @@
 // the reference means logical element (r,c); the deterministic byte-pattern quirk of
 // GetUniformKernel (alfa_gs.cpp:630-639) is kept literally.
 //
-// Pinning status (see DESIGN.md "Oracle"):
-//   * Label::LabelOneComponent / WrapCols and utils.h are cross-checked against the reference's own
-//     sources compiled verbatim into oracle/_ref (oracle/build.py; tests/test_oracle_vs_ref.py).
-//   * the two OpenCV calls (cv::dilate with the GetUniformKernel bytes, cv::filter2D with the
-//     Savitzky-Golay kernel) are pinned against OpenCV 4.13 golden vectors in tests/golden/.
-//   * the reference ships no tests / golden vectors of its own, and alfa_gs.cpp itself
-//     cannot be built here (ROS, PCL, OpenCV C++ absent): CreateRangeImage, CreateAngleImg, EraseBFS
-//     seeds/erase and CameraCb are restated line by line below — "parity unpinned" for those stages.
+// Pinning status (see DESIGN.md "Oracle"): PINNED.  The reference's own translation units — src/alfa_gs.cpp,
+//   src/alfa_node.cpp, Labeler/label.cpp, src/cloud2range_node.cpp, src/range2cloud_node.cpp, lib/utils.h — are
+//   compiled verbatim from /root/reference into oracle/_ref/libgs_ref.so against stand-in ROS / PCL / OpenCV
+//   headers (oracle/shim, recipe oracle/build.py) and every function below is compared with the reference member
+//   it restates, bit for bit, stage by stage and as whole frames driven the way ROS drives the nodes
+//   (tests/test_reference_verbatim.py, tests/test_oracle_vs_ref.py).  The two OpenCV calls (cv::dilate with the
+//   GetUniformKernel bytes, cv::filter2D with the Savitzky-Golay kernel) — here and in the stand-in headers — are
+//   pinned against OpenCV 4.13 golden vectors in tests/golden/.
 //
 // Build: g++ -O2 -std=c++14 -ffp-contract=off -fPIC -shared (oracle/build.py).  No FMA contraction:
 // the x86-64 reference build has none either.

@@ -250,3 +250,303 @@ def evaluate(p, og, seg, labeled):
     _check(lib().gso_evaluate(C.byref(p), np.ascontiguousarray(og, np.uint16), np.ascontiguousarray(seg, np.uint16),
                               np.ascontiguousarray(labeled, np.uint16), C.byref(out)), "evaluate")
     return out
+
+
+# ---- the reference's own nodes, compiled verbatim into oracle/_ref (oracle/ref_alfa_wrap.cpp, ref_c2r_wrap.cpp,
+# ref_r2c_wrap.cpp) — used to pin the restatement above and as the CPU arm of bench.py ("kind": "reference") ----------
+_node_bound = False
+
+
+def _bind_nodes(R):
+    global _node_bound
+    if _node_bound:
+        return
+    vp, sz = C.c_void_p, C.c_size_t
+    R.gsref_alfa_ctor_values.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                         C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    R.gsref_alfa_create.argtypes = [C.POINTER(GsParams)]
+    R.gsref_alfa_create.restype = vp
+    R.gsref_alfa_destroy.argtypes = [vp]
+    R.gsref_alfa_shape.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    R.gsref_assert_failures.restype = C.c_long
+    R.gsref_log.argtypes = [C.c_char_p, C.c_int]
+    R.gsref_alfa_create_range_image.argtypes = [vp, vp, sz, sz, _u16p]
+    R.gsref_alfa_create_angle_img.argtypes = [vp, _u16p, _u16p]
+    R.gsref_alfa_repair_gaps.argtypes = [vp, _u16p, C.c_int, C.c_float, _u16p]
+    R.gsref_alfa_sg_smooth.argtypes = [vp, _u16p, C.c_int, C.c_int, C.c_int, _u16p]
+    R.gsref_alfa_sg_kernel.argtypes = [vp, C.c_int, _f32p]
+    R.gsref_alfa_uniform_kernel.argtypes = [vp, C.c_int, _u8p]
+    R.gsref_alfa_dilate.argtypes = [vp, _u8p, C.c_int, C.c_int, C.c_int, _u8p]
+    R.gsref_alfa_erase_bfs.argtypes = [vp, _u16p, _u16p, C.c_double, C.c_double, C.c_int, _u16p]
+    R.gsref_alfa_camera_cb.argtypes = [vp, _u16p, vp, sz]
+    R.gsref_alfa_camera_cb.restype = sz
+    R.gsref_alfa_labeled_range_image.argtypes = [vp, vp, sz, sz, vp, _u16p]
+    R.gsref_alfa_check_detected.argtypes = [vp, _u16p, _u16p, _u16p]
+    R.gsref_alfa_colored_angle_image.argtypes = [vp, _u16p, C.c_int, C.c_int, _u8p]
+    R.gsref_alfa_process_frame.argtypes = [vp, vp, sz, sz, vp, vp, sz]
+    R.gsref_alfa_process_frame.restype = C.c_long
+    R.gsref_node_store_pointcloud_hardware.argtypes = [vp, vp, sz, sz, vp]
+    R.gsref_node_read_hardware_pointcloud.argtypes = [vp, vp, C.c_uint, C.c_uint, _u16p]
+    R.gsref_node_read_hardware_filtered_angle_image.argtypes = [vp, vp, C.c_uint, C.c_uint, _u16p]
+    R.gsref_c2r_create.argtypes = [C.POINTER(GsParams)]
+    R.gsref_c2r_create.restype = vp
+    R.gsref_c2r_destroy.argtypes = [vp]
+    R.gsref_c2r_derived.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    R.gsref_c2r_cloud_cb.argtypes = [vp, vp, sz, sz, _u16p, C.POINTER(C.c_double)]
+    R.gsref_c2r_set_thresholds.argtypes = [vp, C.c_double, C.c_double]
+    R.gsref_c2r_repair_gaps.argtypes = [vp, _u16p, C.c_int, C.c_float, _u16p]
+    R.gsref_c2r_create_angle_img.argtypes = [vp, _u16p, _u16p]
+    R.gsref_c2r_sg_smooth.argtypes = [vp, _u16p, C.c_int, _u16p]
+    R.gsref_c2r_erase_ground_bfs.argtypes = [vp, _u16p, _u16p, C.c_double, C.c_double, C.c_int, _u16p]
+    R.gsref_r2c_create.restype = vp
+    R.gsref_r2c_destroy.argtypes = [vp]
+    R.gsref_r2c_camera_cb.argtypes = [vp, _u16p, C.c_int, C.c_int, C.POINTER(C.c_double), vp, sz]
+    R.gsref_r2c_camera_cb.restype = C.c_long
+    _node_bound = True
+
+
+def ref_log():
+    R = ref()
+    buf = C.create_string_buffer(1 << 16)
+    R.gsref_log(buf, len(buf))
+    return buf.value.decode("utf-8", "replace").splitlines()
+
+
+class RefAlfaGS:
+    """The reference's Alfa_GS node (src/alfa_gs.cpp + src/alfa_node.cpp + Labeler/label.cpp, verbatim).  One per thread."""
+
+    def __init__(self, p=None):
+        self.R = ref()
+        if self.R is None:
+            raise RuntimeError("oracle/_ref is not built and /root/reference is absent")
+        _bind_nodes(self.R)
+        self.h = self.R.gsref_alfa_create(C.byref(p) if p is not None else None)
+        if not self.h:
+            raise RuntimeError("the reference node came up on its FPGA path or its derivations disagree")
+        r, c = C.c_int(0), C.c_int(0)
+        self.R.gsref_alfa_shape(self.h, C.byref(r), C.byref(c))
+        self.shape = (r.value, c.value)
+
+    def close(self):
+        if self.h:
+            self.R.gsref_alfa_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _img(self):
+        return np.zeros(self.shape, np.uint16)
+
+    def create_range_image(self, points):
+        pts, ptr, n, stride = _points_arg(points)
+        out = self._img()
+        self.R.gsref_alfa_create_range_image(self.h, ptr, n, stride, out)
+        return out
+
+    def create_angle_img(self, range_image):
+        out = self._img()
+        self.R.gsref_alfa_create_angle_img(self.h, np.ascontiguousarray(range_image, np.uint16), out)
+        return out
+
+    def repair_gaps(self, range_image, step=5, depth_threshold=1.0):
+        out = self._img()
+        self.R.gsref_alfa_repair_gaps(self.h, np.ascontiguousarray(range_image, np.uint16), step, depth_threshold, out)
+        return out
+
+    def sg_smooth(self, image, ws):
+        img = np.ascontiguousarray(image, np.uint16)
+        out = np.zeros_like(img)
+        if self.R.gsref_alfa_sg_smooth(self.h, img, img.shape[0], img.shape[1], ws, out):
+            raise ValueError("std::logic_error")
+        return out
+
+    def sg_kernel(self, ws):
+        out = np.zeros(ws, np.float32)
+        if self.R.gsref_alfa_sg_kernel(self.h, ws, out):
+            raise ValueError("std::logic_error")
+        return out
+
+    def uniform_kernel(self, ks):
+        out = np.zeros(ks, np.uint8)
+        if self.R.gsref_alfa_uniform_kernel(self.h, ks, out):
+            raise ValueError("std::logic_error")
+        return out
+
+    def dilate(self, label_image, ks):
+        lab = np.ascontiguousarray(label_image, np.uint8)
+        out = np.zeros_like(lab)
+        if self.R.gsref_alfa_dilate(self.h, lab, lab.shape[0], lab.shape[1], ks, out):
+            raise ValueError("std::logic_error")
+        return out
+
+    def erase_bfs(self, range_image, angle_image, ground_thr, start_thr, kernel_size):
+        out = self._img()
+        if self.R.gsref_alfa_erase_bfs(self.h, np.ascontiguousarray(range_image, np.uint16),
+                                       np.ascontiguousarray(angle_image, np.uint16), ground_thr, start_thr, kernel_size, out):
+            raise ValueError("std::logic_error")
+        return out
+
+    def camera_cb(self, image):
+        """-> float32 [n, 4] {x, y, z, 1.0} (the first 16 bytes of the 32-byte pcl::PointXYZRGB records)"""
+        H, W = self.shape
+        buf = np.zeros((H * W, 8), np.float32)
+        n = self.R.gsref_alfa_camera_cb(self.h, np.ascontiguousarray(image, np.uint16), buf.ctypes.data_as(C.c_void_p), H * W)
+        return buf[:n, :4].copy()
+
+    def labeled_range_image(self, points, rgb):
+        pts, ptr, n, stride = _points_arg(points)
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        out = self._img()
+        self.R.gsref_alfa_labeled_range_image(self.h, ptr, n, stride, rgb.ctypes.data_as(C.c_void_p), out)
+        return out
+
+    def check_detected(self, og, seg, labeled):
+        """CheckNumberOfDetectedRIdGnd reports through ROS_INFO only: returns the logged lines."""
+        self.R.gsref_alfa_check_detected(self.h, np.ascontiguousarray(og, np.uint16), np.ascontiguousarray(seg, np.uint16),
+                                         np.ascontiguousarray(labeled, np.uint16))
+        return ref_log()
+
+    def colored_angle_image(self, angle_image):
+        img = np.ascontiguousarray(angle_image, np.uint16)
+        out = np.zeros(img.shape + (3,), np.uint8)
+        self.R.gsref_alfa_colored_angle_image(self.h, img, img.shape[0], img.shape[1], out)
+        return out
+
+    def process_frame(self, points, want_outputs=True):
+        """A PointCloud2 through AlfaNode::cloud_cb -> Alfa_GS::process_pointcloud; what the node published."""
+        pts, ptr, n, stride = _points_arg(points)
+        H, W = self.shape
+        if not want_outputs:
+            return self.R.gsref_alfa_process_frame(self.h, ptr, n, stride, None, None, 0)
+        img = self._img()
+        buf = np.zeros((H * W, 8), np.float32)
+        np_out = self.R.gsref_alfa_process_frame(self.h, ptr, n, stride, img.ctypes.data_as(C.c_void_p),
+                                                 buf.ctypes.data_as(C.c_void_p), H * W)
+        if np_out < 0:
+            raise RuntimeError("the reference node published nothing")
+        return dict(no_ground=img, xyz=buf[:np_out, :4].copy(), records=buf[:np_out].copy())
+
+    def store_pointcloud_hardware(self, points):
+        pts, ptr, n, stride = _points_arg(points)
+        out = np.zeros(n, np.uint64)
+        self.R.gsref_node_store_pointcloud_hardware(self.h, ptr, n, stride, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def read_hardware_pointcloud(self, words, rows, cols):
+        w = np.ascontiguousarray(words, np.uint64)
+        out = np.zeros((64, 1800), np.uint16)  # the reference hard-codes this shape (alfa_node.cpp:162)
+        self.R.gsref_node_read_hardware_pointcloud(self.h, w.ctypes.data_as(C.c_void_p), rows, cols, out)
+        return out
+
+    def read_hardware_filtered_angle_image(self, words, rows, cols):
+        w = np.ascontiguousarray(words, np.uint64).copy()  # the reference shifts the words it reads
+        out = np.zeros((rows, cols), np.uint16)
+        self.R.gsref_node_read_hardware_filtered_angle_image(self.h, w.ctypes.data_as(C.c_void_p), rows, cols, out)
+        return out
+
+
+def ref_ctor_values():
+    """What the UNTOUCHED Alfa_GS constructor computed: (n_cols, d_azimuth, d_altitude, K[0..5], hw)."""
+    R = ref()
+    _bind_nodes(R)
+    nc, hw = C.c_int(0), C.c_int(0)
+    da, dl = C.c_double(0), C.c_double(0)
+    K = (C.c_double * 6)()
+    R.gsref_alfa_ctor_values(C.byref(nc), C.byref(da), C.byref(dl), K, C.byref(hw))
+    return nc.value, da.value, dl.value, list(K), hw.value
+
+
+class RefCloud2Range:
+    """The reference's Cloud2RangeNode (src/cloud2range_node.cpp, verbatim).  One per thread."""
+
+    def __init__(self, p=None):
+        self.R = ref()
+        if self.R is None:
+            raise RuntimeError("oracle/_ref is not built and /root/reference is absent")
+        _bind_nodes(self.R)
+        self.h = self.R.gsref_c2r_create(C.byref(p) if p is not None else None)
+        r, c = C.c_int(0), C.c_int(0)
+        da, dl = C.c_double(0), C.c_double(0)
+        K = (C.c_double * 6)()
+        self.R.gsref_c2r_derived(self.h, C.byref(r), C.byref(c), C.byref(da), C.byref(dl), K)
+        self.shape = (r.value, c.value)
+        self.d_azimuth, self.d_altitude, self.K = da.value, dl.value, list(K)
+
+    def close(self):
+        if self.h:
+            self.R.gsref_c2r_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def set_thresholds(self, ground_thr, start_thr):
+        self.R.gsref_c2r_set_thresholds(self.h, ground_thr, start_thr)
+
+    def cloud_cb(self, points):
+        """-> (published mono16 image, published CameraInfo.K[0..8])"""
+        pts, ptr, n, stride = _points_arg(points)
+        img = np.zeros(self.shape, np.uint16)
+        K = (C.c_double * 9)()
+        if self.R.gsref_c2r_cloud_cb(self.h, ptr, n, stride, img, K):
+            raise RuntimeError("the reference node published nothing")
+        return img, list(K)
+
+    def repair_gaps(self, range_image, step=5, depth_threshold=1.0):
+        out = np.zeros(self.shape, np.uint16)
+        self.R.gsref_c2r_repair_gaps(self.h, np.ascontiguousarray(range_image, np.uint16), step, depth_threshold, out)
+        return out
+
+    def create_angle_img(self, range_image):
+        out = np.zeros(self.shape, np.uint16)
+        self.R.gsref_c2r_create_angle_img(self.h, np.ascontiguousarray(range_image, np.uint16), out)
+        return out
+
+    def sg_smooth(self, image, ws):
+        out = np.zeros(self.shape, np.uint16)
+        if self.R.gsref_c2r_sg_smooth(self.h, np.ascontiguousarray(image, np.uint16), ws, out):
+            raise ValueError("std::logic_error")
+        return out
+
+    def erase_ground_bfs(self, range_image, angle_image, ground_thr, start_thr, kernel_size):
+        out = np.zeros(self.shape, np.uint16)
+        if self.R.gsref_c2r_erase_ground_bfs(self.h, np.ascontiguousarray(range_image, np.uint16),
+                                             np.ascontiguousarray(angle_image, np.uint16), ground_thr, start_thr, kernel_size, out):
+            raise ValueError("std::logic_error")
+        return out
+
+
+class RefRange2Cloud:
+    """The reference's Range2CloudNode (src/range2cloud_node.cpp, verbatim).  One per thread."""
+
+    def __init__(self):
+        self.R = ref()
+        if self.R is None:
+            raise RuntimeError("oracle/_ref is not built and /root/reference is absent")
+        _bind_nodes(self.R)
+        self.h = self.R.gsref_r2c_create()
+
+    def close(self):
+        if self.h:
+            self.R.gsref_r2c_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def camera_cb(self, image, K):
+        img = np.ascontiguousarray(image, np.uint16)
+        K9 = (C.c_double * 9)(*(list(K) + [0.0] * 9)[:9])
+        buf = np.zeros((img.size, 4), np.float32)
+        n = self.R.gsref_r2c_camera_cb(self.h, img, img.shape[0], img.shape[1], K9, buf.ctypes.data_as(C.c_void_p), img.size)
+        if n < 0:
+            raise RuntimeError("the reference node published nothing")
+        return buf[:n].copy()
+
+
+def ref_assert_failures():
+    R = ref()
+    _bind_nodes(R)
+    return R.gsref_assert_failures()

@@ -1,2 +1,3 @@
-// empty shim: lib/utils.h includes <pcl/point_types.h> but uses nothing from it (oracle/_ref build only)
+// Forwarding shim (oracle/_ref build, test infrastructure): see gsref_ros.h / gsref_cv.h
 #pragma once
+#include "../gsref_ros.h"
