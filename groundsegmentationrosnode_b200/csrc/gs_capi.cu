@@ -135,6 +135,9 @@ struct gs_ctx {
     Luts lut;
     SgTaps sg;
     void* lut_block = nullptr;  // one device allocation behind all LUTs
+    void* ci_block = nullptr;   // cos / sin tables of gs_backproject_camera_info for the CameraInfo.K values in ci_K
+    double ci_K[6] = {0, 0, 0, 0, 0, 0};
+    bool ci_valid = false;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
@@ -312,6 +315,9 @@ int configure(gs_ctx* ctx, const gs_params* p) {
         fused_release(ctx->fused);
         cudaFree(ctx->lut_block);
         ctx->lut_block = nullptr;
+        cudaFree(ctx->ci_block);
+        ctx->ci_block = nullptr;
+        ctx->ci_valid = false;
     }
     // LUT block: [H] sin_y, [H] cos_y (float) | [H] cos_alt, [H] sin_alt, [W] cos_az, [W] sin_az, [H] sin_y, [H] cos_y (double)
     const int H = k.H, W = k.W;
@@ -509,6 +515,7 @@ void gs_destroy(gs_ctx* ctx) {
     free_stage(ctx);
     fused_release(ctx->fused);
     cudaFree(ctx->lut_block);
+    cudaFree(ctx->ci_block);
     cudaFree(ctx->d_cnt);
     cudaFree(ctx->d_offsets);
     if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
@@ -807,6 +814,59 @@ int gs_backproject(gs_ctx* ctx, const uint16_t* image, float* xyz4_out, uint32_t
     launch_rowcount(L, kp, 1, ctx->d_a, ctx->sc.rowcount);
     launch_backproject(L, kp, ctx->lut, 1, ctx->d_a, ctx->sc.rowcount, ctx->d_xyz, ctx->sc.counts,
                        ctx->params.variant == GS_VARIANT_CLOUD2RANGE);
+    CU(cudaGetLastError());
+    unsigned n = 0;
+    CU(cudaMemcpyAsync(&n, ctx->sc.counts, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (n) CU(cudaMemcpyAsync(xyz4_out, ctx->d_xyz, static_cast<size_t>(n) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *n_out = n;
+    return GS_OK;
+}
+
+int gs_backproject_camera_info(gs_ctx* ctx, const uint16_t* image, int32_t height, int32_t width, const double* K, int range_as_double,
+                               float* xyz4_out, uint32_t* n_out) {
+    if (!ctx || !image || !K || !xyz4_out || !n_out) return fail(ctx, GS_EINVAL, "gs_backproject_camera_info: bad arguments");
+    if (height != ctx->kp.H || width != ctx->kp.W)
+        return fail(ctx, GS_EINVAL, "gs_backproject_camera_info: image is %d x %d, the context %d x %d", height, width, ctx->kp.H, ctx->kp.W);
+    cudaSetDevice(ctx->device);
+    int rc;
+    if ((rc = ensure_stage(ctx)) || (rc = ensure_scratch(ctx, 1))) return rc;
+    const int H = ctx->kp.H, W = ctx->kp.W;
+    if (!ctx->ci_valid || std::memcmp(ctx->ci_K, K, sizeof(ctx->ci_K)) != 0) {
+        // the decoding parameters are the ones the message carries (range2cloud_node.cpp:51-58, alfa_gs.cpp:1010-1015):
+        // altitude = (rows - r) * K[5] + K[0], azimuth = c * K[4]; cos / sin with the host's libm like the reference
+        std::vector<double> host(2 * static_cast<size_t>(H) + 2 * static_cast<size_t>(W));
+        for (int r = 0; r < H; ++r) {
+            const double altitude = (H - r) * K[5] + K[0];
+            host[r] = std::cos(altitude);
+            host[H + r] = std::sin(altitude);
+        }
+        for (int c = 0; c < W; ++c) {
+            const double azimuth = c * K[4];
+            host[2 * H + c] = std::cos(azimuth);
+            host[2 * H + W + c] = std::sin(azimuth);
+        }
+        if (!ctx->ci_block) CU(cudaMalloc(&ctx->ci_block, host.size() * sizeof(double)));
+        CU(cudaMemcpyAsync(ctx->ci_block, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        std::memcpy(ctx->ci_K, K, sizeof(ctx->ci_K));
+        ctx->ci_valid = true;
+    }
+    KParams kp = ctx->kp;
+    kp.min_range = K[2];
+    kp.max_range = K[3];
+    kp.span = K[3] - K[2];
+    Luts lut = ctx->lut;
+    const double* dd = static_cast<const double*>(ctx->ci_block);
+    lut.cos_alt = dd;
+    lut.sin_alt = dd + H;
+    lut.cos_az = dd + 2 * H;
+    lut.sin_az = dd + 2 * H + W;
+    CU(cudaMemcpyAsync(ctx->d_a, image, static_cast<size_t>(kp.P) * 2, cudaMemcpyHostToDevice, ctx->stream));
+    const Launch L = launch_of(ctx);
+    launch_rowcount(L, kp, 1, ctx->d_a, ctx->sc.rowcount);
+    launch_backproject(L, kp, lut, 1, ctx->d_a, ctx->sc.rowcount, ctx->d_xyz, ctx->sc.counts, range_as_double != 0);
     CU(cudaGetLastError());
     unsigned n = 0;
     CU(cudaMemcpyAsync(&n, ctx->sc.counts, 4, cudaMemcpyDeviceToHost, ctx->stream));

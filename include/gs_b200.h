@@ -185,6 +185,13 @@ int gs_label_components(gs_ctx* ctx, const uint16_t* image, const uint16_t* angl
  * double range) chosen by params.variant.  xyz4_out: up to n_rows*n_cols records {x,y,z,1.0f},
  * row-major order of the surviving pixels. */
 int gs_backproject(gs_ctx* ctx, const uint16_t* image, float* xyz4_out, uint32_t* n_out);
+/* The same with the decoding parameters taken from the sensor_msgs/CameraInfo that travels with the image, as
+ * Range2CloudNode::CameraCb does (range2cloud_node.cpp:51-58: min_angle = K[0], min/max range = K[2] / K[3], d_azimuth = K[4],
+ * d_altitude = K[5]; range kept in double, :76) and Alfa_GS::CameraCb with its cinfo argument (alfa_gs.cpp:1010-1015; range
+ * rounded to float, :1027,1045: range_as_double = 0).  K: at least 6 values.  height x width must be the context's shape
+ * (GS_EINVAL otherwise): the context only lends its device buffers, none of its own derived values are used. */
+int gs_backproject_camera_info(gs_ctx* ctx, const uint16_t* image, int32_t height, int32_t width, const double* K,
+                               int range_as_double, float* xyz4_out, uint32_t* n_out);
 /* Alfa_GS::process_pointcloud, hw==0 branch (alfa_gs.cpp:175-244) / Cloud2RangeNode::CloudCb +
  * Range2CloudNode::CameraCb.  Any output pointer may be NULL. */
 int gs_process_frame(gs_ctx* ctx, const void* points, size_t n_points, size_t stride_bytes,

@@ -169,14 +169,22 @@ public:
         ctx_->check(gs_project(ctx_->get(), input_cloud.data(), input_cloud.size(), sizeof(PointT), out.ptr()));
         return out;
     }
+    // the C ABI reads n_rows * n_cols pixels from every image it is handed: anything else is a caller error
+    template <class T>
+    void require_shape(const Image<T>& image, const char* what) const {
+        if (image.rows != n_rows() || image.cols != n_cols())
+            throw std::logic_error(std::string(what) + ": image shape differs from the sensor's range-image shape");
+    }
     // alfa_gs.cpp:300-333 (typed reading)
     Image<uint16_t> RepairGaps(const Image<uint16_t>& no_ground_image, int step, float depth_threshold) {
+        require_shape(no_ground_image, "RepairGaps");
         Image<uint16_t> out(n_rows(), n_cols());
         ctx_->check(gs_repair_gaps(ctx_->get(), no_ground_image.ptr(), step, depth_threshold, out.ptr()));
         return out;
     }
     // alfa_gs.cpp:335-386
     Image<uint16_t> CreateAngleImg(const Image<uint16_t>& range_image) {
+        require_shape(range_image, "CreateAngleImg");
         Image<uint16_t> out(n_rows(), n_cols());
         ctx_->check(gs_angle_image(ctx_->get(), range_image.ptr(), out.ptr()));
         return out;
@@ -218,6 +226,7 @@ public:
     }
     // alfa_gs.cpp:705-713 (cv::filter2D with BORDER_REFLECT101 on the GPU)
     Image<uint16_t> SavitskyGolaySmoothing(const Image<uint16_t>& image, int window_size) {
+        require_shape(image, "SavitskyGolaySmoothing");
         Image<uint16_t> out(n_rows(), n_cols());
         ctx_->check(gs_smooth(ctx_->get(), image.ptr(), window_size, out.ptr()));
         return out;
@@ -226,16 +235,20 @@ public:
     Image<uint16_t> EraseBFS(const Image<uint16_t>& range_image, const Image<uint16_t>& smoothed_image, double ground_angle_threshold,
                              double start_angle_threshold, int kernel_size) {
         if (range_image.rows != smoothed_image.rows || range_image.cols != smoothed_image.cols) return Image<uint16_t>();  // :742-745: empty image
+        require_shape(range_image, "EraseBFS");
         Image<uint16_t> out(n_rows(), n_cols());
         ctx_->check(gs_erase_ground(ctx_->get(), range_image.ptr(), smoothed_image.ptr(), ground_angle_threshold, start_angle_threshold,
                                     kernel_size, out.ptr(), nullptr));
         return out;
     }
-    // alfa_gs.cpp:997-1074: parameters come from the CameraInfo captured at construction (:55-63, :1010-1015)
-    std::vector<PointXYZRGB> CameraCb(const Image<uint16_t>& range_image, const CameraInfo& /*cinfo*/) {
+    // alfa_gs.cpp:997-1074: decodes with the parameters of the CameraInfo it is handed (:1010-1015; the node passes the one it
+    // filled at construction, :55-63), range rounded to float (:1027,1045)
+    std::vector<PointXYZRGB> CameraCb(const Image<uint16_t>& range_image, const CameraInfo& cinfo) {
+        require_shape(range_image, "CameraCb");
         std::vector<float> xyz(static_cast<size_t>(n_rows()) * n_cols() * 4);
         uint32_t n = 0;
-        ctx_->check(gs_backproject(ctx_->get(), range_image.ptr(), xyz.data(), &n));
+        ctx_->check(gs_backproject_camera_info(ctx_->get(), range_image.ptr(), range_image.rows, range_image.cols, cinfo.K.data(), 0,
+                                               xyz.data(), &n));
         std::vector<PointXYZRGB> cloud(n);
         for (uint32_t i = 0; i < n; ++i) {
             PointXYZRGB& p = cloud[i];
@@ -258,6 +271,9 @@ public:
     // function-local statics for its log line (:890-927) are accumulated here per object
     gs_eval CheckNumberOfDetectedRIdGnd(const Image<uint16_t>& og_range_image, const Image<uint16_t>& seg_range_image,
                                         const Image<uint16_t>& labeled_range_image) {
+        require_shape(og_range_image, "CheckNumberOfDetectedRIdGnd");
+        require_shape(seg_range_image, "CheckNumberOfDetectedRIdGnd");
+        require_shape(labeled_range_image, "CheckNumberOfDetectedRIdGnd");
         gs_eval e;
         ctx_->check(gs_evaluate(ctx_->get(), og_range_image.ptr(), seg_range_image.ptr(), labeled_range_image.ptr(), &e));
         eval_sum_[0] += e.iou_g;
@@ -365,6 +381,9 @@ public:
     Image<uint16_t> EraseGroundBFS(const Image<uint16_t>& range_image, const Image<uint16_t>& smoothed_image, double ground_angle_threshold,
                                    double start_angle_threshold, int kernel_size) {
         const gs_derived& d = ctx_->derived();
+        if (range_image.rows != smoothed_image.rows || range_image.cols != smoothed_image.cols) return Image<uint16_t>();  // :728-731: empty image
+        if (range_image.rows != d.n_rows || range_image.cols != d.n_cols)
+            throw std::logic_error("EraseGroundBFS: image shape differs from the sensor's range-image shape");
         Image<uint16_t> out(d.n_rows, d.n_cols);
         ctx_->check(gs_erase_ground(ctx_->get(), range_image.ptr(), smoothed_image.ptr(), ground_angle_threshold, start_angle_threshold,
                                     kernel_size, out.ptr(), nullptr));
@@ -379,27 +398,28 @@ private:
 // ---- src/range2cloud_node.cpp ------------------------------------------------------------------------------------------
 class Range2CloudNode {
 public:
-    // CameraCb (range2cloud_node.cpp:36-99): decodes with the parameters carried in CameraInfo.K (:51-58)
+    // CameraCb (range2cloud_node.cpp:36-99): decodes with the parameters carried in CameraInfo.K (:51-58) — min_angle = K[0],
+    // min / max range = K[2] / K[3], d_azimuth = K[4], d_altitude = K[5] are used as published, nothing is re-derived
     std::vector<PointXYZ> CameraCb(const Image<uint16_t>& range_image, const CameraInfo& cinfo) {
-        if (!ctx_ || cinfo.height != last_.height || cinfo.width != last_.width || cinfo.K != last_.K) {
+        if (range_image.rows != static_cast<int>(cinfo.height) || range_image.cols != static_cast<int>(cinfo.width))
+            throw std::logic_error("Range2CloudNode::CameraCb: image shape differs from the CameraInfo's height x width");
+        if (!ctx_ || range_image.rows != rows_ || range_image.cols != cols_) {
+            // a context of the image's shape lends its device buffers; the decoding parameters travel with every call
             gs_params p;
             gs_default_params(GS_PRESET_CLOUD2RANGE_DEFAULT, &p);
             p.variant = GS_VARIANT_CLOUD2RANGE;
-            p.n_beams = cinfo.height;
+            p.n_beams = range_image.rows;
             p.rpm = 60;
-            p.sample_freq = cinfo.width;  // n_cols = sample_freq * 60 / rpm
-            p.min_angle = cinfo.K[0];
-            p.min_range = cinfo.K[2];
-            p.max_range = cinfo.K[3];
-            // K[5] = d_altitude = (max - min) / (beams - 1): recover max_angle; K[4] = d_azimuth follows from the width
-            p.max_angle = cinfo.K[0] + cinfo.K[5] * (cinfo.height - 1);
+            p.sample_freq = range_image.cols;  // n_cols = sample_freq * 60 / rpm
             p.smoothing = GS_SMOOTH_NONE;
             ctx_ = std::make_shared<Context>(p);
-            last_ = cinfo;
+            rows_ = range_image.rows;
+            cols_ = range_image.cols;
         }
         std::vector<float> xyz(static_cast<size_t>(range_image.rows) * range_image.cols * 4);
         uint32_t n = 0;
-        ctx_->check(gs_backproject(ctx_->get(), range_image.ptr(), xyz.data(), &n));
+        ctx_->check(gs_backproject_camera_info(ctx_->get(), range_image.ptr(), range_image.rows, range_image.cols, cinfo.K.data(), 1,
+                                               xyz.data(), &n));
         std::vector<PointXYZ> cloud(n);
         for (uint32_t i = 0; i < n; ++i) cloud[i] = PointXYZ{xyz[4 * i], xyz[4 * i + 1], xyz[4 * i + 2], 1.0f};
         return cloud;
@@ -407,7 +427,7 @@ public:
 
 private:
     std::shared_ptr<Context> ctx_;
-    CameraInfo last_;
+    int rows_ = 0, cols_ = 0;
 };
 
 }  // namespace gs
