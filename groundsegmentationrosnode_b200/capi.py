@@ -25,7 +25,7 @@ EXPORTS = [
     "gs_get_derived", "gs_set_stream", "gs_set_chunk_frames", "gs_set_option", "gs_get_stats", "gs_reset_stats", "gs_get_phase_cycles",
     "gs_last_error", "gs_project", "gs_angle_image", "gs_smooth", "gs_repair_gaps", "gs_erase_ground",
     "gs_label_one_component", "gs_label_components", "gs_backproject", "gs_process_frame", "gs_process_batch_device",
-    "gs_process_batch_host", "gs_synchronize", "gs_unpack_points", "gs_process_cloud2", "gs_pack_cloud_xyzrgb",
+    "gs_process_batch_host", "gs_process_batch_host_strided", "gs_backproject_camera_info", "gs_synchronize", "gs_unpack_points", "gs_process_cloud2", "gs_pack_cloud_xyzrgb",
     "gs_get_camera_info", "gs_create_labeled_range_image", "gs_evaluate",
 ]
 
@@ -82,6 +82,8 @@ def load(build_if_missing=False):
     L.gs_process_frame.argtypes = [C.c_void_p, vp, C.c_size_t, C.c_size_t, u16p, u16p, u16p, f32p, C.POINTER(C.c_uint32)]
     L.gs_process_batch_device.argtypes = [C.c_void_p, vp, i64p, C.c_int, vp, vp, vp, vp, vp]
     L.gs_process_batch_host.argtypes = [C.c_void_p, vp, i64p, C.c_int, vp, vp, C.c_uint64, i64p]
+    L.gs_process_batch_host_strided.argtypes = [C.c_void_p, vp, C.c_size_t, i64p, C.c_int, vp, vp, C.c_uint64, i64p]
+    L.gs_backproject_camera_info.argtypes = [C.c_void_p, u16p, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_int, f32p, C.POINTER(C.c_uint32)]
     L.gs_synchronize.argtypes = [C.c_void_p]
     L.gs_unpack_points.argtypes = [C.c_void_p, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_int, f32p]
     L.gs_process_cloud2.argtypes = [C.c_void_p, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u16p, u16p, u16p, f32p,
@@ -322,12 +324,24 @@ class Context:
                                                  C.c_void_p(d_xyz4 or None), C.c_void_p(d_counts or None)))
 
     def process_batch_host(self, h_points, h_offsets, no_ground_out=None, xyz4_out=None, out_offsets=None):
-        """numpy (ideally pinned) buffers; returns (no_ground_out, xyz4_out, out_offsets)."""
+        """numpy (ideally pinned) buffers; h_points is [n, 4] XYZI or [n, 3] XYZ float32 (or any [n, k >= 3] float32 records);
+        returns (no_ground_out, xyz4_out, out_offsets)."""
         offs = np.ascontiguousarray(h_offsets, dtype=np.int64)
         n_frames = len(offs) - 1
         if out_offsets is None:
             out_offsets = np.zeros(n_frames + 1, np.int64)
         cap = 0 if xyz4_out is None else xyz4_out.shape[0]
-        self._ck(self._L.gs_process_batch_host(self._h, _ptr(h_points), _ptr(offs), n_frames, _ptr(no_ground_out), _ptr(xyz4_out), cap,
-                                               _ptr(out_offsets)))
+        stride = 16 if h_points.ndim < 2 else int(h_points.strides[0])
+        self._ck(self._L.gs_process_batch_host_strided(self._h, _ptr(h_points), stride, _ptr(offs), n_frames, _ptr(no_ground_out), _ptr(xyz4_out),
+                                                       cap, _ptr(out_offsets)))
         return no_ground_out, xyz4_out, out_offsets
+
+    def backproject_camera_info(self, image, K, range_as_double):
+        """Back-projection with the decoding parameters of a CameraInfo.K (range2cloud_node.cpp:51-58 / alfa_gs.cpp:1010-1015)."""
+        img = np.ascontiguousarray(image, dtype=np.uint16)
+        H, W = img.shape
+        Kc = (C.c_double * 9)(*(list(K) + [0.0] * 9)[:9])
+        xyz = np.empty((H * W, 4), np.float32)
+        n = C.c_uint32(0)
+        self._ck(self._L.gs_backproject_camera_info(self._h, _ptr(img), H, W, Kc, int(range_as_double), _ptr(xyz), C.byref(n)))
+        return xyz[: n.value].copy()

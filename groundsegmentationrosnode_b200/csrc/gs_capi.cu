@@ -551,6 +551,9 @@ int gs_get_derived(const gs_ctx* ctx, gs_derived* out) {
 
 int gs_set_stream(gs_ctx* ctx, void* cuda_stream) {
     if (!ctx) return GS_EINVAL;
+    cudaSetDevice(ctx->device);
+    // work queued on the old stream uses the context's scratch (remote lists, offsets): let it finish before another stream may touch it
+    CU(cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
     return GS_OK;
 }
@@ -1033,21 +1036,35 @@ int gs_process_batch_device(gs_ctx* ctx, const float* d_points_xyzi, const int64
     return GS_OK;
 }
 
-int gs_process_batch_host(gs_ctx* ctx, const float* h_points_xyzi, const int64_t* h_offsets, int n_frames, uint16_t* h_no_ground_out,
-                          float* h_xyz4_out, uint64_t xyz4_capacity, int64_t* h_out_offsets) {
-    if (!ctx || !h_offsets || n_frames < 0 || (n_frames && !h_points_xyzi)) return fail(ctx, GS_EINVAL, "gs_process_batch_host: bad arguments");
+int gs_process_batch_host_strided(gs_ctx* ctx, const void* h_points, size_t stride_bytes, const int64_t* h_offsets, int n_frames,
+                                  uint16_t* h_no_ground_out, float* h_xyz4_out, uint64_t xyz4_capacity, int64_t* h_out_offsets) {
+    if (!ctx || !h_offsets || n_frames < 0 || (n_frames && !h_points)) return fail(ctx, GS_EINVAL, "gs_process_batch_host: bad arguments");
+    if (stride_bytes < 12 || (stride_bytes & 3)) return fail(ctx, GS_EINVAL, "gs_process_batch_host: records are x, y, z floats plus optional payload, %zu bytes is not a record size", stride_bytes);
     if (h_xyz4_out && !h_out_offsets) return fail(ctx, GS_EINVAL, "gs_process_batch_host: h_out_offsets is required with h_xyz4_out");
     if (n_frames == 0) return GS_OK;
+    // every offset is checked before anything is copied: a bad table must not leave DMA in flight on the caller's buffers
+    if (h_offsets[0] < 0) return fail(ctx, GS_EINVAL, "offsets must be non-negative");
+    long long batch_max = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        if (h_offsets[f + 1] < h_offsets[f]) return fail(ctx, GS_EINVAL, "offsets must be non-decreasing (frame %d)", f);
+        batch_max = std::max<long long>(batch_max, h_offsets[f + 1] - h_offsets[f]);
+    }
     cudaSetDevice(ctx->device);
     const size_t P = ctx->kp.P;
+    const bool want_cloud = h_xyz4_out != nullptr;
+    const bool repack = stride_bytes != 16;  // e.g. 12-byte XYZ records: a quarter less PCIe traffic than XYZI; repacked to 16 bytes on the device
     int rc;
-    // slot size: enough frames per wave to fill the GPU, small enough to pipeline copies against compute
-    // The copies dominate (PCIe moves a frame in ~35 us, the GPU computes it in ~3 us), so waves are kept small: the first
-    // H2D and the last D2H overlap nothing, and that fill / drain time is proportional to the wave.  Two frames per
-    // co-resident cluster of the fused kernel keep its persistent grid busy.
-    const int auto_wave = fused_supported(ctx->fused) ? std::max(2 * ctx->fused.max_clusters, 16) : 148;
-    const int wave = std::min(n_frames, ctx->chunk_frames > 0 ? ctx->chunk_frames : auto_wave);
-    if (ctx->slot_frames < wave) {
+    // Wave size.  The copies dominate (PCIe moves a 64 x 2048 frame in ~35 us, the GPU computes it in ~3 us), so waves are kept
+    // small: the first H2D and the last D2H overlap nothing, and that fill / drain time is proportional to the wave.  Two frames
+    // per co-resident cluster of the fused kernel keep its persistent grid busy.  Large images are bounded by a byte budget
+    // per slot (outputs + worst-case cloud slabs) instead.
+    const bool fused_ok = fused_supported(ctx->fused) && batch_max <= fused_max_points();
+    const int auto_wave = fused_ok ? std::max(2 * (ctx->fused.max_clusters + ctx->fused.soft_clusters), 16) : 148;
+    const size_t per_frame = P * 2 + (want_cloud ? P * 32 : 0) + static_cast<size_t>(batch_max) * (repack ? stride_bytes + 16 : 16);
+    const int budget_wave = static_cast<int>(std::max<size_t>(1, (static_cast<size_t>(1) << 30) / std::max<size_t>(per_frame, 1)));
+    const int wave = std::max(1, std::min(std::min(n_frames, budget_wave), ctx->chunk_frames > 0 ? ctx->chunk_frames : auto_wave));
+    if (ctx->slot_frames < wave || (want_cloud && !ctx->d_cloud[0])) {
+        CU(cudaStreamSynchronize(ctx->stream));
         for (int k = 0; k < 2; ++k) {
             cudaFree(ctx->d_res[k]); cudaFree(ctx->d_cloud[k]); cudaFree(ctx->d_counts[k]);
             cudaFree(ctx->d_packed[k]); cudaFree(ctx->d_prefix[k]);
@@ -1055,16 +1072,19 @@ int gs_process_batch_host(gs_ctx* ctx, const float* h_points_xyzi, const int64_t
             if (ctx->h_counts[k]) cudaFreeHost(ctx->h_counts[k]);
             ctx->d_res[k] = nullptr; ctx->d_cloud[k] = nullptr; ctx->d_counts[k] = nullptr; ctx->h_counts[k] = nullptr;
         }
+        const int nw = std::max(wave, ctx->slot_frames);
         ctx->slot_frames = 0;
         for (int k = 0; k < 2; ++k) {
-            CU(cudaMalloc(&ctx->d_res[k], static_cast<size_t>(wave) * P * 2));
-            CU(cudaMalloc(&ctx->d_cloud[k], static_cast<size_t>(wave) * P * 16));
-            CU(cudaMalloc(&ctx->d_packed[k], static_cast<size_t>(wave) * P * 16));
-            CU(cudaMalloc(&ctx->d_prefix[k], (static_cast<size_t>(wave) + 1) * sizeof(unsigned long long)));
-            CU(cudaMalloc(&ctx->d_counts[k], static_cast<size_t>(wave) * 4));
-            CU(cudaMallocHost(&ctx->h_counts[k], static_cast<size_t>(wave) * 4));
+            CU(cudaMalloc(&ctx->d_res[k], static_cast<size_t>(nw) * P * 2));
+            if (want_cloud) {  // the cloud slabs are only allocated for callers that ask for clouds
+                CU(cudaMalloc(&ctx->d_cloud[k], static_cast<size_t>(nw) * P * 16));
+                CU(cudaMalloc(&ctx->d_packed[k], static_cast<size_t>(nw) * P * 16));
+                CU(cudaMalloc(&ctx->d_prefix[k], (static_cast<size_t>(nw) + 1) * sizeof(unsigned long long)));
+            }
+            CU(cudaMalloc(&ctx->d_counts[k], static_cast<size_t>(nw) * 4));
+            CU(cudaMallocHost(&ctx->h_counts[k], static_cast<size_t>(nw) * 4));
         }
-        ctx->slot_frames = wave;
+        ctx->slot_frames = nw;
     }
     if ((rc = ensure_offsets(ctx, static_cast<size_t>(n_frames) + 1))) return rc;
     CU(cudaMemcpyAsync(ctx->d_offsets, h_offsets, (static_cast<size_t>(n_frames) + 1) * sizeof(long long), cudaMemcpyHostToDevice,
@@ -1073,14 +1093,19 @@ int gs_process_batch_host(gs_ctx* ctx, const float* h_points_xyzi, const int64_t
     const int n_waves = (n_frames + wave - 1) / wave;
     int64_t out_cursor = 0;
     if (h_out_offsets) h_out_offsets[0] = 0;
-    // software pipeline over waves: H2D(w+1) overlaps compute(w) overlaps D2H(w-1)
+    const unsigned char* h_bytes = static_cast<const unsigned char*>(h_points);
+    // software pipeline over waves: H2D(w+1) overlaps compute(w) overlaps D2H(w-1).
+    // Slot layout of d_in[k]: [packed float4 records of the wave][raw records as they came, when they are not 16 bytes wide]
     auto issue_in = [&](int w) -> int {
         const int k = w & 1;
         const int f0 = w * wave, nf = std::min(wave, n_frames - f0);
         const long long p0 = h_offsets[f0], p1 = h_offsets[f0 + nf];
-        const size_t bytes = static_cast<size_t>(p1 - p0) * 16;
+        const size_t n = static_cast<size_t>(p1 - p0);
+        const size_t packed = (n * 16 + 255) & ~static_cast<size_t>(255);
+        const size_t bytes = repack ? packed + n * stride_bytes : n * 16;
         if (ctx->d_in_cap[k] < bytes) {
             CU(cudaStreamSynchronize(ctx->stream));  // the slot may still be read by an earlier wave
+            CU(cudaStreamSynchronize(ctx->copy_in));
             cudaFree(ctx->d_in[k]);
             ctx->d_in[k] = nullptr;
             ctx->d_in_cap[k] = 0;
@@ -1088,7 +1113,8 @@ int gs_process_batch_host(gs_ctx* ctx, const float* h_points_xyzi, const int64_t
             ctx->d_in_cap[k] = bytes + bytes / 8 + 256;
         }
         if (w >= 2) CU(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_done[k], 0));  // compute of wave w-2 released the slot
-        if (bytes) CU(cudaMemcpyAsync(ctx->d_in[k], h_points_xyzi + 4 * p0, bytes, cudaMemcpyHostToDevice, ctx->copy_in));
+        unsigned char* dst = reinterpret_cast<unsigned char*>(ctx->d_in[k]) + (repack ? packed : 0);
+        if (n) CU(cudaMemcpyAsync(dst, h_bytes + static_cast<size_t>(p0) * stride_bytes, n * stride_bytes, cudaMemcpyHostToDevice, ctx->copy_in));
         CU(cudaEventRecord(ctx->ev_in[k], ctx->copy_in));
         return GS_OK;
     };
@@ -1096,18 +1122,21 @@ int gs_process_batch_host(gs_ctx* ctx, const float* h_points_xyzi, const int64_t
         const int k = w & 1;
         const int f0 = w * wave, nf = std::min(wave, n_frames - f0);
         long long max_points = 0;
-        for (int f = f0; f < f0 + nf; ++f) {
-            if (h_offsets[f + 1] < h_offsets[f]) return fail(ctx, GS_EINVAL, "offsets must be non-decreasing (frame %d)", f);
-            max_points = std::max<long long>(max_points, h_offsets[f + 1] - h_offsets[f]);
-        }
+        for (int f = f0; f < f0 + nf; ++f) max_points = std::max<long long>(max_points, h_offsets[f + 1] - h_offsets[f]);
         CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[k], 0));
         if (w >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[k], 0));  // D2H of wave w-2 drained the slot's outputs
+        if (repack) {
+            const size_t n = static_cast<size_t>(h_offsets[f0 + nf] - h_offsets[f0]);
+            const size_t packed = (n * 16 + 255) & ~static_cast<size_t>(255);
+            launch_unpack_points(launch_of(ctx), reinterpret_cast<unsigned char*>(ctx->d_in[k]) + packed, n, static_cast<unsigned>(stride_bytes), 0, 4, 8,
+                                 stride_bytes >= 16 ? 12 : -1, 0, ctx->d_in[k]);
+        }
         // offsets inside the slot are relative to the wave's first point: pass a shifted base pointer instead
         const float* base = ctx->d_in[k] - 4 * h_offsets[f0];
-        const int rc2 = run_wave(ctx, base, 16, ctx->d_offsets + f0, nf, max_points, nullptr, nullptr, ctx->d_res[k], ctx->d_cloud[k],
+        const int rc2 = run_wave(ctx, base, 16, ctx->d_offsets + f0, nf, max_points, nullptr, nullptr, ctx->d_res[k], want_cloud ? ctx->d_cloud[k] : nullptr,
                                  ctx->d_counts[k]);
         if (rc2) return rc2;
-        if (h_xyz4_out)
+        if (want_cloud)
             launch_pack_clouds(launch_of(ctx), reinterpret_cast<const float4*>(ctx->d_cloud[k]), ctx->d_counts[k], nf, P, ctx->d_prefix[k],
                                reinterpret_cast<float4*>(ctx->d_packed[k]));
         CU(cudaMemcpyAsync(ctx->h_counts[k], ctx->d_counts[k], static_cast<size_t>(nf) * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1118,33 +1147,51 @@ int gs_process_batch_host(gs_ctx* ctx, const float* h_points_xyzi, const int64_t
         const int k = w & 1;
         const int f0 = w * wave, nf = std::min(wave, n_frames - f0);
         CU(cudaEventSynchronize(ctx->ev_done[k]));  // counts are on the host now
+        // the capacity is checked for the whole wave before its copy is issued
+        const int64_t wave_first = out_cursor;
+        int64_t cursor = out_cursor;
+        for (int f = 0; f < nf; ++f) {
+            cursor += ctx->h_counts[k][f];
+            if (want_cloud && static_cast<uint64_t>(cursor) > xyz4_capacity) return fail(ctx, GS_EINVAL, "xyz4 output capacity exceeded at frame %d", f0 + f);
+        }
         CU(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[k], 0));
         if (h_no_ground_out)
             CU(cudaMemcpyAsync(h_no_ground_out + static_cast<size_t>(f0) * P, ctx->d_res[k], static_cast<size_t>(nf) * P * 2,
                                cudaMemcpyDeviceToHost, ctx->copy_out));
-        const int64_t wave_first = out_cursor;
         for (int f = 0; f < nf; ++f) {
-            const unsigned n = ctx->h_counts[k][f];
-            if (h_xyz4_out && static_cast<uint64_t>(out_cursor) + n > xyz4_capacity) return fail(ctx, GS_EINVAL, "xyz4 output capacity exceeded at frame %d", f0 + f);
-            out_cursor += n;
+            out_cursor += ctx->h_counts[k][f];
             if (h_out_offsets) h_out_offsets[f0 + f + 1] = out_cursor;
         }
-        if (h_xyz4_out && out_cursor > wave_first)  // the wave's clouds, packed on the device, in one copy
+        if (want_cloud && out_cursor > wave_first)  // the wave's clouds, packed on the device, in one copy
             CU(cudaMemcpyAsync(h_xyz4_out + 4 * wave_first, ctx->d_packed[k], static_cast<size_t>(out_cursor - wave_first) * 16, cudaMemcpyDeviceToHost,
                                ctx->copy_out));
         CU(cudaEventRecord(ctx->ev_out[k], ctx->copy_out));
         return GS_OK;
     };
-    if ((rc = issue_in(0))) return rc;
-    for (int w = 0; w < n_waves; ++w) {
-        if (w + 1 < n_waves && (rc = issue_in(w + 1))) return rc;
-        if ((rc = issue_compute(w))) return rc;
-        if (w >= 1 && (rc = issue_out(w - 1))) return rc;
+    // one exit: whatever happened, no copy into or out of the caller's buffers and no kernel on the slots is still in flight on return
+    auto pipeline = [&]() -> int {
+        int r;
+        if ((r = issue_in(0))) return r;
+        for (int w = 0; w < n_waves; ++w) {
+            if (w + 1 < n_waves && (r = issue_in(w + 1))) return r;
+            if ((r = issue_compute(w))) return r;
+            if (w >= 1 && (r = issue_out(w - 1))) return r;
+        }
+        return issue_out(n_waves - 1);
+    };
+    rc = pipeline();
+    const cudaError_t e1 = cudaStreamSynchronize(ctx->copy_in), e2 = cudaStreamSynchronize(ctx->stream), e3 = cudaStreamSynchronize(ctx->copy_out);
+    if (rc) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        const cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+        return fail(ctx, GS_ECUDA, "gs_process_batch_host: %s", cudaGetErrorString(e));
     }
-    if ((rc = issue_out(n_waves - 1))) return rc;
-    CU(cudaStreamSynchronize(ctx->copy_out));
-    CU(cudaStreamSynchronize(ctx->stream));
     return GS_OK;
+}
+
+int gs_process_batch_host(gs_ctx* ctx, const float* h_points_xyzi, const int64_t* h_offsets, int n_frames, uint16_t* h_no_ground_out,
+                          float* h_xyz4_out, uint64_t xyz4_capacity, int64_t* h_out_offsets) {
+    return gs_process_batch_host_strided(ctx, h_points_xyzi, 16, h_offsets, n_frames, h_no_ground_out, h_xyz4_out, xyz4_capacity, h_out_offsets);
 }
 
 }  // extern "C"

@@ -27,6 +27,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 #include <math_constants.h>
 
@@ -93,6 +94,27 @@ struct FusedArgs {
     float sg_t[11];            // Savitzky-Golay taps (cloud2range_node.cpp:470), sg_ws = 0: no smoothing
     int sg_ws;
     int use_fast;
+    // frame queue shared by every launch that works on this batch: a cluster starts with frame first_frame + its index and
+    // fetches every further frame with an atomic on *queue (zeroed by the host before the launches): frame = queue_base + old value
+    unsigned* queue;
+    int first_frame, queue_base;
+    int slot_base;             // this launch's clusters use the scratch slots slot_base, slot_base + 1, ... (rlist / rcount / mail)
+    struct SoftMail* mail;     // software clusters only: one mailbox per cluster slot
+};
+
+// Mailbox of one SOFTWARE cluster: CL ordinary CTAs that own the column slabs of one frame like the CTAs of a thread-block
+// cluster do, but exchange their boundary data through global memory (L2) instead of distributed shared memory, and meet
+// at a counter instead of barrier.cluster.  Hardware clusters must sit inside one GPC, which strands SMs (clusters of 4 reach
+// 132 of a B200's 148 SMs); software clusters take whatever SMs are left.  Every CTA writes only its own slots.
+struct SoftMail {
+    unsigned bar;                                   // arrivals since the launch started
+    unsigned next_frame;                            // published by rank 0 once per frame
+    unsigned pad[30];
+    unsigned chg[2][MAX_CL];                        // boundary exchange: "something changed in my slab" per parity and rank
+    unsigned pub[MAX_CL][2][2][4];                  // [rank][parity][column 0 / last column][word]: ground masks of the boundary columns
+    unsigned valid0[MAX_CL][4], validL[MAX_CL][4];  // VALID words of every CTA's column 0 / last column
+    unsigned rowcnt[MAX_CL][MAX_H];                 // surviving pixels per row and slab
+    unsigned char angle0[MAX_CL][MAX_H], angleL[MAX_CL][MAX_H];  // angles of every CTA's column 0 / last column
 };
 
 constexpr int FB = 18;  // fractional bits of the fixed-point cell coordinates
@@ -594,6 +616,25 @@ __device__ __forceinline__ int approx_col(const FusedArgs& A, float x, float y) 
     return min(max((c + A.col_half_fix) >> FB, 0), A.kp.W - 1);
 }
 
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// barrier of a software cluster: every CTA adds one to the mailbox counter and waits until all CL have (epoch counts the
+// arrivals expected so far).  The CTAs of a software cluster are co-resident by construction (cooperative launch, one CTA per SM).
+__device__ __forceinline__ void soft_cluster_sync(unsigned* bar, unsigned& epoch, int CL) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        epoch += static_cast<unsigned>(CL);
+        __threadfence();  // my global stores (mailbox, remote records) before my arrival
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
+        while (static_cast<int>(ld_acquire_gpu(bar) - epoch) < 0) {
+        }
+    }
+    __syncthreads();
+}
+
 struct Smem {
     uint16_t* range;
     uint16_t* tag;
@@ -618,7 +659,8 @@ struct Smem {
 // NW: 64-bit words per column mask (H <= 64 * NW); NT: threads per CTA (1024 x 1 CTA/SM or 512 x 2 CTAs/SM);
 // HT, CWT, CLT: image rows, columns per CTA and CTAs per frame fixed at compile time (0 = read from the arguments; the image
 // is then exactly CLT * CWT wide): the BASELINE sensor shapes get instantiations whose strides, offsets and trip counts are constants.
-template <int NW, int NT, int HT, int CWT, int CLT>
+// SOFT: software clusters (see SoftMail) instead of thread-block clusters; launched without a cluster dimension.
+template <int NW, int NT, int HT, int CWT, int CLT, bool SOFT>
 __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs A) {
     constexpr bool SPEC = HT > 0;
     constexpr Layout LC = layout_hcw(SPEC ? HT : 64, SPEC ? CWT : 512, NW);
@@ -626,9 +668,15 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
     cg::cluster_group cluster = cg::this_cluster();
     const KParams& kp = A.kp;
     const int CL = SPEC ? CLT : A.CL, CW = SPEC ? CWT : A.CW, H = SPEC ? HT : kp.H, W = SPEC ? CLT * CWT : kp.W;
-    const int rank = static_cast<int>(cluster.block_rank());
+    const int rank = SOFT ? static_cast<int>(blockIdx.x % CL) : static_cast<int>(cluster.block_rank());
     const int cluster_id = blockIdx.x / CL;
-    const int n_clusters = gridDim.x / CL;
+    const int slot = A.slot_base + cluster_id;  // scratch slot of this cluster (remote lists, mailbox)
+    SoftMail* const mail = SOFT ? A.mail + slot : nullptr;
+    unsigned soft_epoch = 0;
+    auto csync = [&]() {
+        if constexpr (SOFT) soft_cluster_sync(&mail->bar, soft_epoch, CL);
+        else cluster.sync();
+    };
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col0 = rank * CW;                 // first global column of my slab
     const int myCW = SPEC ? CWT : min(CW, W - col0);  // columns I own (> 0 by construction)
@@ -697,8 +745,8 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
     if (tid == 0) s_misc[0] = 0;  // blocks dealt to me (reset at the end of every frame)
     __syncthreads();
 
-    uint2* rlist = A.rlist + (static_cast<size_t>(cluster_id) * CL + rank) * A.rcap;
-    unsigned* rcount = A.rcount + static_cast<size_t>(cluster_id) * CL;
+    uint2* rlist = A.rlist + (static_cast<size_t>(slot) * CL + rank) * A.rcap;
+    unsigned* rcount = A.rcount + static_cast<size_t>(slot) * CL;
 
     // statistics runs (tests): counters live in shared memory, not in registers of the hot loops
     enum { ST_DROPPED = 0, ST_NEAR, ST_NEAR_ANGLE, ST_REMOTE, ST_FALLBACK, ST_MISMATCH, ST_COUNT };
@@ -766,16 +814,18 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
     };
     long long beg_cur = 0;
     int N_cur = 0;
-    if (cluster_id < A.frames) {
-        beg_cur = A.offsets[cluster_id];
-        N_cur = static_cast<int>(A.offsets[cluster_id + 1] - beg_cur);
+    const int f_first = A.first_frame + cluster_id;
+    if (f_first < A.frames) {
+        beg_cur = A.offsets[f_first];
+        N_cur = static_cast<int>(A.offsets[f_first + 1] - beg_cur);
         float2 xy[2];
         deal_load(A.points + beg_cur, N_cur, 0, xy);
         deal_vote(N_cur, 0, xy);
         deal_rest(A.points + beg_cur, N_cur);
     }
 
-    for (int f = cluster_id; f < A.frames; f += n_clusters) {
+    int f_next = A.frames;
+    for (int f = f_first; f < A.frames; f = f_next) {
         const long long beg = beg_cur;  // A.offsets[f]: loaded for the dealing during the previous frame (or the prologue)
         const int N = N_cur;
         const float4* pts = A.points + beg;
@@ -914,7 +964,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         GS_PHASE(2);
         // remote records and counts: barrier.cluster arrives with release and waits with acquire semantics at cluster scope,
         // which orders the global stores / atomics above before the reads below in the other CTAs of the cluster — no __threadfence
-        cluster.sync();   // #1: all local pixels committed everywhere
+        csync();   // #1: all local pixels committed everywhere
         if (tid == 0) s_misc[0] = 0;  // every thread has read the block count; the next frame's list is built during the output
 
         GS_PHASE(3);
@@ -923,12 +973,24 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             unsigned n_any = 0;
             for (int k = 0; k < CL; ++k) n_any |= __ldcg(&rcount[k]);
             if (n_any) {
-                const unsigned n = min(__ldcg(&rcount[rank]), A.rcap);
-                for (unsigned i = tid; i < n; i += NT) {
-                    const uint2 rec = __ldcg(&rlist[i]);
-                    atomicMax(cluster.map_shared_rank(s_key, rec.x >> 16) + (rec.x & 0xffffu), rec.y);
+                if constexpr (SOFT) {
+                    // nobody can reach into my shared memory: I apply the records addressed to me from every CTA's list
+                    for (int k = 0; k < CL; ++k) {
+                        const uint2* lst = A.rlist + (static_cast<size_t>(slot) * CL + k) * A.rcap;
+                        const unsigned n = min(__ldcg(&rcount[k]), A.rcap);
+                        for (unsigned i = tid; i < n; i += NT) {
+                            const uint2 rec = __ldcg(&lst[i]);
+                            if (static_cast<int>(rec.x >> 16) == rank) atomicMax(s_key + (rec.x & 0xffffu), rec.y);
+                        }
+                    }
+                } else {
+                    const unsigned n = min(__ldcg(&rcount[rank]), A.rcap);
+                    for (unsigned i = tid; i < n; i += NT) {
+                        const uint2 rec = __ldcg(&rlist[i]);
+                        atomicMax(cluster.map_shared_rank(s_key, rec.x >> 16) + (rec.x & 0xffffu), rec.y);
+                    }
                 }
-                cluster.sync();  // #2
+                csync();  // #2: every record is applied before its list is refilled / before the keys are compacted
             }
         }
         // compact the keys to the u16 range slab in place (the low half of every key is the winner's range); the freed
@@ -1124,7 +1186,16 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         // the left neighbour's right halo, my last column its right neighbour's left halo (column W-1's right neighbour is
         // column 0: Label::WrapCols).  After the barrier nobody reads another CTA's angle slab or link words any more, which
         // saves the cluster barrier that used to follow the link stage.
-        {
+        if constexpr (SOFT) {
+            for (int r = tid; r < H; r += NT) {
+                mail->angle0[rank][r] = s_angle[r * S8];
+                mail->angleL[rank][r] = s_angle[r * S8 + myCW - 1];
+            }
+            if (tid < NWD) {
+                mail->valid0[rank][tid] = MW(MK_VALID, tid, 0);
+                mail->validL[rank][tid] = MW(MK_VALID, tid, myCW - 1);
+            }
+        } else {
             uint8_t* to_left = cluster.map_shared_rank(s_halo_angle, left_rank);
             uint8_t* to_right = cluster.map_shared_rank(s_haloL_angle, right_rank);
             for (int r = tid; r < H; r += NT) {
@@ -1137,7 +1208,19 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             }
         }
         GS_PHASE(5);
-        cluster.sync();  // #4: angle slabs, VALID masks and halos complete in the whole cluster
+        csync();  // #4: angle slabs, VALID masks and halos complete in the whole cluster
+        if constexpr (SOFT) {
+            // pull my halos out of the neighbours' mailbox slots (L2 reads: the lines were written by other SMs)
+            for (int r = tid; r < H; r += NT) {
+                s_halo_angle[r] = __ldcg(&mail->angle0[right_rank][r]);
+                s_haloL_angle[r] = __ldcg(&mail->angleL[left_rank][r]);
+            }
+            if (tid < NWD) {
+                s_halo32[0 * 4 + tid] = __ldcg(&mail->valid0[right_rank][tid]);
+                s_haloL_valid[tid] = __ldcg(&mail->validL[left_rank][tid]);
+            }
+            __syncthreads();
+        }
 
         GS_PHASE(6);
         // ================================================================================ G: links, runs, seeds, ground label
@@ -1461,24 +1544,36 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                             gnd = root != 0xffffu && (s_par[root] & 0x8000u) != 0;
                         }
                         const unsigned m = __ballot_sync(0xffffffffu, gnd);
-                        if (lane == 0) s_pub[(pk * 2 + warp) * 4 + w] = m;
+                        if (lane == 0) {
+                            s_pub[(pk * 2 + warp) * 4 + w] = m;
+                            if constexpr (SOFT) mail->pub[rank][pk][warp][w] = m;
+                        }
                     }
                 } else if (warp == 2 && lane < CL) {
-                    cluster.map_shared_rank(s_chg, lane)[pk * MAX_CL + rank] = static_cast<unsigned>(changed_prev);
+                    if constexpr (SOFT) {
+                        if (lane == 0) mail->chg[pk][rank] = static_cast<unsigned>(changed_prev);
+                    } else {
+                        cluster.map_shared_rank(s_chg, lane)[pk * MAX_CL + rank] = static_cast<unsigned>(changed_prev);
+                    }
                 }
-                cluster.sync();
+                csync();
                 unsigned anyone = 0;
-                for (int k = 0; k < CL; ++k) anyone |= s_chg[pk * MAX_CL + k];
+                if constexpr (SOFT) {
+                    for (int k = 0; k < CL; ++k) anyone |= __ldcg(&mail->chg[pk][k]);
+                } else {
+                    for (int k = 0; k < CL; ++k) anyone |= s_chg[pk * MAX_CL + k];
+                }
                 if (!anyone) break;
                 bool changed = false;
                 if (warp < 2) {
                     // warp 0: my column 0 against the left neighbour's last column (link = its HM, static halo slot 3)
                     // warp 1: my last column against the right neighbour's column 0 (link = my HM)
                     const int nb_rank = warp == 0 ? left_rank : right_rank;
-                    const unsigned* their_pub = cluster.map_shared_rank(s_pub, nb_rank) + (pk * 2 + (warp == 0 ? 1 : 0)) * 4;
+                    const unsigned* their_pub = SOFT ? &mail->pub[nb_rank][pk][warp == 0 ? 1 : 0][0]
+                                                     : cluster.map_shared_rank(s_pub, nb_rank) + (pk * 2 + (warp == 0 ? 1 : 0)) * 4;
                     const int c = warp == 0 ? 0 : myCW - 1;
                     for (int w = 0; w < NWD; ++w) {
-                        const unsigned theirs = their_pub[w];
+                        const unsigned theirs = SOFT ? __ldcg(their_pub + w) : their_pub[w];
                         const unsigned mine = s_pub[(pk * 2 + warp) * 4 + w];
                         const unsigned link = warp == 0 ? s_halo32[3 * 4 + w] : MW(MK_HM, w, c);
                         if (lane == 0) s_halo32[(warp == 0 ? 2 : 1) * 4 + w] = theirs;  // kept for the label stage (gl / gr)
@@ -1600,11 +1695,31 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                 s_grp[r * NG + gidx] = run;
                 run += __popc(s_rowmask[r * NG + gidx]);
             }
-            for (int k = 0; k < CL; ++k) cluster.map_shared_rank(s_rowcnt_all, k)[rank * Hp + r] = run;
+            if constexpr (SOFT) {
+                s_rowcnt_all[rank * Hp + r] = run;
+                mail->rowcnt[rank][r] = run;
+            } else {
+                for (int k = 0; k < CL; ++k) cluster.map_shared_rank(s_rowcnt_all, k)[rank * Hp + r] = run;
+            }
+        }
+        // the frame this cluster takes next: rank 0 draws it from the queue all launches of the batch share and publishes it
+        if (rank == 0 && tid == NT - 1) {
+            const unsigned nf = static_cast<unsigned>(A.queue_base) + atomicAdd(A.queue, 1u);
+            if constexpr (SOFT) mail->next_frame = nf;
+            else
+                for (int k = 0; k < CL; ++k) cluster.map_shared_rank(s_misc, k)[5] = nf;
         }
 #undef MW
         GS_PHASE(12);
-        cluster.sync();  // #: row counts of every slab everywhere
+        csync();  // #: row counts of every slab (and the next frame) everywhere
+        if constexpr (SOFT) {
+            for (int t = tid; t < CL * H; t += NT) {
+                const int k = t / H, r = t - k * H;
+                if (k != rank) s_rowcnt_all[k * Hp + r] = __ldcg(&mail->rowcnt[k][r]);
+            }
+            if (tid == 0) s_misc[5] = __ldcg(&mail->next_frame);
+            __syncthreads();
+        }
         if (warp == 0) {
             // rowbase[r] = points in rows above (all slabs) + points of row r in the slabs left of mine
             unsigned carry = 0;
@@ -1632,7 +1747,8 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
 
         GS_PHASE(13);
         // the next frame of this cluster: pull the sampled points of its block dealing (P0) into L2 while the output streams out
-        const int fn = f + n_clusters;
+        const int fn = static_cast<int>(min(s_misc[5], static_cast<unsigned>(A.frames)));
+        f_next = fn;
         long long begn = 0;
         int Nn = 0;
         if (fn < A.frames) {  // uniform
@@ -1695,7 +1811,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             atomicAdd(&A.cnt->fast_mismatch, static_cast<unsigned long long>(s_stat[ST_MISMATCH]));
         }
     }
-    cluster.sync();  // no CTA exits while a neighbour may still address its shared memory
+    if constexpr (!SOFT) cluster.sync();  // no CTA exits while a neighbour may still address its shared memory
 }
 
 // ====================================================================================================================
@@ -1723,16 +1839,19 @@ struct FusedPlan {
 
 namespace {
 // the instantiation that serves (NW, threads, H, columns per CTA): specialised for the BASELINE sensor shapes, generic otherwise
-const void* select_kernel(int NW, int nt, int H, int CW, int CL, int W) {
+const void* select_kernel(int NW, int nt, int H, int CW, int CL, int W, bool soft) {
+#define GS_KF(...) (soft ? reinterpret_cast<const void*>(k_frame<__VA_ARGS__, true>) : reinterpret_cast<const void*>(k_frame<__VA_ARGS__, false>))
     if (nt == 1024 && W == CL * CW) {
-        if (NW == 1 && H == 64 && CW == 512 && CL == 4) return reinterpret_cast<const void*>(k_frame<1, 1024, 64, 512, 4>);   // C2 / C4: 64 x 2048 on 4 CTAs
-        if (NW == 1 && H == 64 && CW == 450 && CL == 4) return reinterpret_cast<const void*>(k_frame<1, 1024, 64, 450, 4>);   // the reference's Alfa_GS default: 64 x 1800 (alfa_gs.cpp:16-38)
-        if (NW == 1 && H == 64 && CW == 500 && CL == 4) return reinterpret_cast<const void*>(k_frame<1, 1024, 64, 500, 4>);   // the reference's cloud2range default: 64 x 2000 (cloud2range_node.cpp:274-329)
-        if (NW == 1 && H == 16 && CW == 900 && CL == 2) return reinterpret_cast<const void*>(k_frame<1, 1024, 16, 900, 2>);   // C1: 16 x 1800 on 2 CTAs
-        if (NW == 2 && H == 128 && CW == 256 && CL == 8) return reinterpret_cast<const void*>(k_frame<2, 1024, 128, 256, 8>);  // C3 / C5: 128 x 2048 on 8 CTAs
+        if (NW == 1 && H == 64 && CW == 512 && CL == 4) return GS_KF(1, 1024, 64, 512, 4);   // C2 / C4: 64 x 2048 on 4 CTAs
+        if (NW == 1 && H == 64 && CW == 450 && CL == 4) return GS_KF(1, 1024, 64, 450, 4);   // the reference's Alfa_GS default: 64 x 1800 (alfa_gs.cpp:16-38)
+        if (NW == 1 && H == 64 && CW == 500 && CL == 4) return GS_KF(1, 1024, 64, 500, 4);   // the reference's cloud2range default: 64 x 2000 (cloud2range_node.cpp:274-329)
+        if (NW == 1 && H == 16 && CW == 900 && CL == 2) return GS_KF(1, 1024, 16, 900, 2);   // C1: 16 x 1800 on 2 CTAs
+        if (NW == 2 && H == 128 && CW == 256 && CL == 8) return GS_KF(2, 1024, 128, 256, 8);  // C3 / C5: 128 x 2048 on 8 CTAs
     }
-    if (nt == 1024) return NW == 1 ? reinterpret_cast<const void*>(k_frame<1, 1024, 0, 0, 0>) : reinterpret_cast<const void*>(k_frame<2, 1024, 0, 0, 0>);
-    return NW == 1 ? reinterpret_cast<const void*>(k_frame<1, 512, 0, 0, 0>) : reinterpret_cast<const void*>(k_frame<2, 512, 0, 0, 0>);
+    if (nt == 1024) return NW == 1 ? GS_KF(1, 1024, 0, 0, 0) : GS_KF(2, 1024, 0, 0, 0);
+    if (soft) return nullptr;  // the two-CTAs-per-SM experiment exists with thread-block clusters only
+    return NW == 1 ? reinterpret_cast<const void*>(k_frame<1, 512, 0, 0, 0, false>) : reinterpret_cast<const void*>(k_frame<2, 512, 0, 0, 0, false>);
+#undef GS_KF
 }
 }  // namespace
 
@@ -1769,7 +1888,7 @@ int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const Sg
         if (force_cl && atoi(force_cl) != CL) continue;
         Layout l;
         if (!layout_for(kp, CL, NW, &l) || l.total > smem_cap) continue;
-        const void* kern = select_kernel(NW, nt, kp.H, l.CW, CL, kp.W);
+        const void* kern = select_kernel(NW, nt, kp.H, l.CW, CL, kp.W, false);
         // the attribute is per function, not per context: always ask for the device maximum
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess) {
             cudaGetLastError();
@@ -1800,8 +1919,30 @@ int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const Sg
         }
     }
     if (max_clusters < 1) return 0;  // no cluster shape fits here: staged kernels
-    if (getenv("GS_DEBUG_PLAN")) fprintf(stderr, "gs fused plan: %d x %d image, %d threads, cluster %d, %d columns per CTA, %zu B smem, %d co-resident clusters on %d SMs\n",
-                                         kp.H, kp.W, nt, lay.CL, lay.CW, lay.total, max_clusters, n_sms);
+    // Thread-block clusters are placed inside one GPC, which strands SMs (clusters of 4: 132 of 148).  SOFTWARE clusters — the same
+    // kernel with its cluster exchanges through global memory, launched cooperatively beside the cluster kernel — take the SMs that
+    // are left (GS_FUSED_MODE=hybrid, the default), or all of them (=soft); =hw keeps thread-block clusters only.
+    const char* mode_env = getenv("GS_FUSED_MODE");
+    int fmode = FUSED_MODE_HYBRID;
+    if (mode_env && !strcmp(mode_env, "hw")) fmode = FUSED_MODE_HW;
+    if (mode_env && !strcmp(mode_env, "soft")) fmode = FUSED_MODE_SOFT;
+    fs.kernel_soft = nt == 1024 ? select_kernel(NW, nt, kp.H, lay.CW, lay.CL, kp.W, true) : nullptr;
+    fs.soft_clusters = 0;
+    if (fs.kernel_soft && fmode != FUSED_MODE_HW) {
+        int coop = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        if (coop && cudaFuncSetAttribute(fs.kernel_soft, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fs.kernel_soft, nt, lay.total) == cudaSuccess && per_sm >= 1) {
+            const int free_sms = fmode == FUSED_MODE_SOFT ? n_sms : n_sms - max_clusters * lay.CL;
+            fs.soft_clusters = free_sms / lay.CL;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    if (fs.soft_clusters < 1) fmode = FUSED_MODE_HW;
+    fs.mode = fmode;
+    if (getenv("GS_DEBUG_PLAN")) fprintf(stderr, "gs fused plan: %d x %d image, %d threads, cluster %d, %d columns per CTA, %zu B smem, %d co-resident clusters on %d SMs, mode %d, %d software clusters\n",
+                                         kp.H, kp.W, nt, lay.CL, lay.CW, lay.total, max_clusters, n_sms, fmode, fs.soft_clusters);
     fs.cluster = lay.CL;
     fs.threads = nt;
     fs.cols_per_cta = lay.CW;
@@ -1835,8 +1976,15 @@ bool fused_supported(const FusedState& fs) { return fs.configured && !fs.disable
 void fused_release(FusedState& fs) {
     cudaFree(fs.d_const);
     cudaFree(fs.d_rowbase);
+    cudaFree(fs.d_mail);
+    if (fs.stream2) cudaStreamDestroy(fs.stream2);
+    if (fs.ev_fork) cudaEventDestroy(fs.ev_fork);
+    if (fs.ev_join) cudaEventDestroy(fs.ev_join);
     fs.d_const = nullptr;
     fs.d_rowbase = nullptr;
+    fs.d_mail = nullptr;
+    fs.stream2 = nullptr;
+    fs.ev_fork = fs.ev_join = nullptr;
     fs.rowbase_cap = 0;
     fs.configured = false;
 }
@@ -1852,10 +2000,13 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
     const int NW = kp.H <= 64 ? 1 : 2;
     Layout lay;
     if (!layout_for(kp, fs.cluster, NW, &lay)) return static_cast<int>(cudaErrorInvalidConfiguration);
-    const int n_clusters = std::min(frames, fs.max_clusters);
+    // how the frames are shared out: clusters of the cluster kernel first, software clusters for what is left
+    const int n_hw = fs.mode == FUSED_MODE_SOFT ? 0 : std::min(frames, fs.max_clusters);
+    const int n_soft = fs.mode == FUSED_MODE_HW ? 0 : std::min(frames - n_hw, fs.soft_clusters);
+    const int slots = fs.max_clusters + fs.soft_clusters;
     // remote-record scratch: every point of a frame may be remote in the worst case (shuffled clouds)
     const unsigned rcap = static_cast<unsigned>(std::max<long long>((max_points + 1023) / 1024 * 1024, 1024));
-    const size_t need = static_cast<size_t>(fs.max_clusters) * lay.CL * (static_cast<size_t>(rcap) * sizeof(uint2) + sizeof(unsigned));
+    const size_t need = static_cast<size_t>(slots) * lay.CL * (static_cast<size_t>(rcap) * sizeof(uint2) + sizeof(unsigned));
     if (fs.rowbase_cap < need) {
         cudaFree(fs.d_rowbase);
         fs.d_rowbase = nullptr;
@@ -1863,6 +2014,25 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
         const cudaError_t e = cudaMalloc(&fs.d_rowbase, need);
         if (e != cudaSuccess) return static_cast<int>(e);
         fs.rowbase_cap = need;
+    }
+    // frame queue + the mailboxes of the software clusters: one allocation, zeroed before every batch
+    const size_t mail_bytes = 128 + static_cast<size_t>(slots) * sizeof(SoftMail);
+    if (!fs.d_mail) {
+        cudaError_t e = cudaMalloc(&fs.d_mail, mail_bytes);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        if (fs.soft_clusters > 0) {
+            // lowest priority: the cluster kernel is placed first (its clusters need whole TPC groups of a GPC), the software clusters
+            // then take the SMs that are left
+            int prio_lo = 0, prio_hi = 0;
+            cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+            if ((e = cudaStreamCreateWithPriority(&fs.stream2, cudaStreamNonBlocking, prio_lo)) != cudaSuccess) return static_cast<int>(e);
+            if ((e = cudaEventCreateWithFlags(&fs.ev_fork, cudaEventDisableTiming)) != cudaSuccess) return static_cast<int>(e);
+            if ((e = cudaEventCreateWithFlags(&fs.ev_join, cudaEventDisableTiming)) != cudaSuccess) return static_cast<int>(e);
+        }
+    }
+    {
+        const cudaError_t e = cudaMemsetAsync(fs.d_mail, 0, mail_bytes, L.stream);
+        if (e != cudaSuccess) return static_cast<int>(e);
     }
     FusedArgs a;
     a.kp = kp;
@@ -1933,23 +2103,62 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
     }
     a.rlist = reinterpret_cast<uint2*>(fs.d_rowbase);
     a.rcount = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(fs.d_rowbase) +
-                                           static_cast<size_t>(fs.max_clusters) * lay.CL * rcap * sizeof(uint2));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(n_clusters * lay.CL));
-    cfg.blockDim = dim3(fs.threads);
-    cfg.dynamicSmemBytes = lay.total;
-    cfg.stream = L.stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = static_cast<unsigned>(lay.CL);
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    void* kargs[] = {&a};
-    const cudaError_t e = cudaLaunchKernelExC(&cfg, fs.kernel, kargs);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    ++*L.n_launches;
+                                           static_cast<size_t>(slots) * lay.CL * rcap * sizeof(uint2));
+    a.queue = reinterpret_cast<unsigned*>(fs.d_mail);
+    a.mail = reinterpret_cast<SoftMail*>(reinterpret_cast<unsigned char*>(fs.d_mail) + 128);
+    a.queue_base = n_hw + n_soft;
+    const bool two = n_hw > 0 && n_soft > 0;
+    if (two) {
+        // the software clusters run beside the cluster kernel on a second stream, ordered after the work already queued on L.stream
+        // (inputs, the memset above) and joined back into it below
+        cudaError_t e;
+        if ((e = cudaEventRecord(fs.ev_fork, L.stream)) != cudaSuccess) return static_cast<int>(e);
+        if ((e = cudaStreamWaitEvent(fs.stream2, fs.ev_fork, 0)) != cudaSuccess) return static_cast<int>(e);
+    }
+    if (n_hw > 0) {
+        a.first_frame = 0;
+        a.slot_base = 0;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(static_cast<unsigned>(n_hw * lay.CL));
+        cfg.blockDim = dim3(fs.threads);
+        cfg.dynamicSmemBytes = lay.total;
+        cfg.stream = L.stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = static_cast<unsigned>(lay.CL);
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        void* kargs[] = {&a};
+        const cudaError_t e = cudaLaunchKernelExC(&cfg, fs.kernel, kargs);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        ++*L.n_launches;
+    }
+    if (n_soft > 0) {
+        cudaStream_t st = two ? fs.stream2 : L.stream;
+        cudaError_t e;
+        a.first_frame = n_hw;
+        a.slot_base = fs.max_clusters;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(static_cast<unsigned>(n_soft * lay.CL));
+        cfg.blockDim = dim3(fs.threads);
+        cfg.dynamicSmemBytes = lay.total;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: the software clusters wait for each other
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        void* kargs[] = {&a};
+        e = cudaLaunchKernelExC(&cfg, fs.kernel_soft, kargs);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        ++*L.n_launches;
+        if (two) {
+            if ((e = cudaEventRecord(fs.ev_join, st)) != cudaSuccess) return static_cast<int>(e);
+            if ((e = cudaStreamWaitEvent(L.stream, fs.ev_join, 0)) != cudaSuccess) return static_cast<int>(e);
+        }
+    }
     return 0;
 }
 

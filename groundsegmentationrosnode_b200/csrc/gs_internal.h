@@ -99,6 +99,7 @@ void launch_label_image(const Launch& L, const KParams& kp, const void* points32
 void launch_evaluate(const Launch& L, const KParams& kp, const uint16_t* og, const uint16_t* seg, const uint16_t* lab, unsigned long long* out9);
 
 
+enum { FUSED_MODE_HW = 0, FUSED_MODE_HYBRID = 1, FUSED_MODE_SOFT = 2 };
 // ---- fused single-kernel pipeline (gs_fused.cu): one thread-block cluster per frame, images resident in (distributed)
 // shared memory from the projection to the back-projection.
 struct FusedState {
@@ -111,6 +112,12 @@ struct FusedState {
     size_t smem_bytes = 0;
     int n_sms = 0;
     int max_clusters = 0;    // co-resident clusters (persistent grid size)
+    int mode = 0;            // FUSED_MODE_*
+    const void* kernel_soft = nullptr;  // the software-cluster instantiation of the same shape
+    int soft_clusters = 0;   // software clusters launched beside (hybrid) or instead of (soft) the cluster kernel
+    void* d_mail = nullptr;  // frame queue + software-cluster mailboxes
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     void* d_const = nullptr; // device copy of the per-configuration constants
     unsigned* d_rowbase = nullptr;
     size_t rowbase_cap = 0;

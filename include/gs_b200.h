@@ -131,7 +131,7 @@ void gs_destroy(gs_ctx* ctx);
 int gs_set_params(gs_ctx* ctx, const gs_params* p);
 int gs_get_params(const gs_ctx* ctx, gs_params* out);
 int gs_get_derived(const gs_ctx* ctx, gs_derived* out);
-/* all work of the context is enqueued on this cudaStream_t (0 = the context's own stream) */
+/* all work of the context is enqueued on this cudaStream_t (0 = the context's own stream); the old stream is drained first */
 int gs_set_stream(gs_ctx* ctx, void* cuda_stream);
 /* frames processed per wave by the batch calls (scratch = chunk * ~20 B/pixel, kept L2 resident) */
 int gs_set_chunk_frames(gs_ctx* ctx, int frames);
@@ -250,6 +250,13 @@ int gs_process_batch_device(gs_ctx* ctx, const float* d_points_xyzi, const int64
 int gs_process_batch_host(gs_ctx* ctx, const float* h_points_xyzi, const int64_t* h_offsets,
                           int n_frames, uint16_t* h_no_ground_out, float* h_xyz4_out,
                           uint64_t xyz4_capacity, int64_t* h_out_offsets);
+/* The same for records of stride_bytes (a multiple of 4, >= 12) with x, y, z floats first: 12-byte XYZ records move a quarter
+ * less over PCIe than XYZI (the path never reads the intensity, alfa_gs.cpp:259-267), 32-byte pcl::PointXYZRGB records are
+ * accepted as they are; anything but 16 bytes is repacked on the device.  All offsets are validated before the first copy is
+ * issued (GS_EINVAL), and on every return — success or error — no copy from or into the caller's buffers is still in flight. */
+int gs_process_batch_host_strided(gs_ctx* ctx, const void* h_points, size_t stride_bytes, const int64_t* h_offsets,
+                                  int n_frames, uint16_t* h_no_ground_out, float* h_xyz4_out,
+                                  uint64_t xyz4_capacity, int64_t* h_out_offsets);
 int gs_synchronize(gs_ctx* ctx);
 
 #ifdef __cplusplus

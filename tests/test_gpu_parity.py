@@ -353,7 +353,8 @@ def test_fused_union_paths_agree_with_oracle(oracle, preset):
             l0 = ctx.stats().kernel_launches
             ctx.process_batch_device(d_pts.data_ptr(), offsets, F, 0, 0, d_res.data_ptr(), 0, d_cnt.data_ptr())
             ctx.synchronize()
-            assert ctx.stats().kernel_launches - l0 == 1, "the fused kernel should have taken this batch"
+            # one launch of the cluster kernel, plus one of its software-cluster twin when SMs are left over (hybrid mode)
+            assert 1 <= ctx.stats().kernel_launches - l0 <= 2, "the fused kernel should have taken this batch"
             res = d_res.cpu().numpy().view(np.uint16)
             for f in range(F):
                 assert np.array_equal(res[f], want[f % 6]["no_ground"]), "frame %d, cas=%d" % (f, cas)
@@ -586,3 +587,103 @@ def test_random_sensor_configurations(oracle, seed):
         for k in ("range", "angle", "no_ground"):
             assert np.array_equal(got2[k], want[k]), "staged " + k
         assert np.array_equal(got2["xyz"], want["xyz"])
+
+
+def test_large_batch_uses_every_launch_of_the_fused_path(oracle):
+    """More frames than co-resident clusters: the cluster kernel and (hybrid mode) the software clusters beside it draw frames
+    from one queue; every frame must equal the oracle's, whatever cluster processed it."""
+    import torch
+
+    p = P.preset(P.GS_PRESET_HDL64E_2048)
+    H, W = p.shape
+    pool, offs = synth.make_pool(p, 3, seed0=synth.SEED0 + 90)
+    want = [oracle.process_frame(p, pool[offs[i]:offs[i + 1]]) for i in range(3)]
+    F = 150
+    pts, offsets = synth.tile_pool(pool, offs, F)
+    d_pts = torch.from_numpy(pts).cuda()
+    d_res = torch.zeros((F, H, W), dtype=torch.int16, device="cuda")
+    d_xyz = torch.zeros((F, H * W, 4), dtype=torch.float32, device="cuda")
+    d_cnt = torch.zeros(F, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    with capi.Context(p) as ctx:
+        for rep in range(2):  # the second batch reuses the queue and the mailboxes
+            d_res.zero_()
+            d_cnt.zero_()
+            torch.cuda.synchronize()
+            l0 = ctx.stats().kernel_launches
+            ctx.process_batch_device(d_pts.data_ptr(), offsets, F, 0, 0, d_res.data_ptr(), d_xyz.data_ptr(), d_cnt.data_ptr())
+            ctx.synchronize()
+            assert 1 <= ctx.stats().kernel_launches - l0 <= 2
+            res = d_res.cpu().numpy().view(np.uint16)
+            cnt = d_cnt.cpu().numpy()
+            for f in range(F):
+                w = want[f % 3]
+                assert np.array_equal(res[f], w["no_ground"]), (rep, f)
+                assert cnt[f] == w["xyz"].shape[0]
+            xyz = d_xyz[F - 1, : cnt[F - 1]].cpu().numpy()
+            assert np.array_equal(xyz, want[(F - 1) % 3]["xyz"])
+
+
+def test_backproject_with_foreign_camera_info(ctxs, oracle):
+    """Range2CloudNode::CameraCb decodes with K[0], K[2..5] as published (range2cloud_node.cpp:51-58): a CameraInfo whose
+    d_azimuth / d_altitude are not what this library would derive must be honoured bit for bit."""
+    p = P.preset(P.GS_PRESET_VLP16).copy(variant=P.GS_VARIANT_CLOUD2RANGE)
+    ctx = ctxs(p)
+    pts = synth.make_frame(p, synth.SEED0 + 62)
+    img = oracle.process_frame(p, pts)["no_ground"]
+    d = oracle.derive(p)
+    K = [p.min_angle, p.max_angle, p.min_range * 1.5, p.max_range * 0.9, d.d_azimuth * (1 + 3e-16), d.d_altitude * (1 - 2e-16)]
+    rows, cols = np.nonzero(img)
+    rng = (img[rows, cols].astype(np.float64) - 1) / 65534 * (K[3] - K[2]) + K[2]
+    alt = (img.shape[0] - rows) * K[5] + K[0]
+    az = cols * K[4]
+    got = ctx.backproject_camera_info(img, K, True)
+    want = np.stack([np.cos(alt) * np.cos(az) * rng, np.cos(alt) * np.sin(az) * rng, np.sin(alt) * rng], 1).astype(np.float32)
+    assert np.array_equal(got[:, :3], want) and np.all(got[:, 3] == 1.0)
+    ref = oracle.ref()
+    if ref is not None:  # the reference's own node on the same message
+        assert np.array_equal(got, oracle.RefRange2Cloud().camera_cb(img, K))
+    rngf = rng.astype(np.float32).astype(np.float64)  # Alfa_GS::CameraCb rounds the range to float (alfa_gs.cpp:1027,1045)
+    got_f = ctx.backproject_camera_info(img, K, False)
+    want_f = np.stack([np.cos(alt) * np.cos(az) * rngf, np.cos(alt) * np.sin(az) * rngf, np.sin(alt) * rngf], 1).astype(np.float32)
+    assert np.array_equal(got_f[:, :3], want_f)
+    with pytest.raises(capi.GsError):
+        ctx.backproject_camera_info(img[:-1], K, True)  # not the context's shape
+
+
+def test_host_batch_record_strides_and_error_exits(ctxs, oracle):
+    """gs_process_batch_host_strided: 12-byte XYZ and 32-byte PointXYZRGB records give the XYZI result; a bad offset table is
+    refused before anything is copied and a too small cloud buffer is reported — the context stays usable after both."""
+    p = P.preset(P.GS_PRESET_VLP16)
+    ctx = ctxs(p, "production")
+    H, W = p.shape
+    pool, offs = synth.make_pool(p, 4, seed0=synth.SEED0 + 95)
+    pts, offsets = synth.tile_pool(pool, offs, 9)
+    F = len(offsets) - 1
+    want = [oracle.process_frame(p, pool[offs[i]:offs[i + 1]]) for i in range(4)]
+
+    def run(points, cap=None, offsets_=offsets):
+        h_res = np.zeros((F, H, W), np.uint16)
+        h_xyz = np.zeros((cap if cap is not None else F * H * W, 4), np.float32)
+        _, _, out_offs = ctx.process_batch_host(points, offsets_, h_res, h_xyz)
+        return h_res, h_xyz, out_offs
+
+    ctx.set_chunk_frames(4)
+    for points in (pts, np.ascontiguousarray(pts[:, :3]), np.concatenate([pts, np.zeros_like(pts)], 1)):
+        assert points.strides[0] in (16, 12, 32)
+        h_res, h_xyz, out_offs = run(points)
+        for f in range(F):
+            w = want[f % 4]
+            assert np.array_equal(h_res[f], w["no_ground"])
+            assert np.array_equal(h_xyz[out_offs[f]:out_offs[f + 1]], w["xyz"])
+    bad = offsets.copy()
+    bad[5] = bad[4] - 7
+    with pytest.raises(capi.GsError) as ei:
+        run(pts, offsets_=bad)
+    assert ei.value.code == P.GS_EINVAL
+    with pytest.raises(capi.GsError) as ei:
+        run(pts, cap=int(want[0]["xyz"].shape[0]) + 10)  # room for the first frame only
+    assert ei.value.code == P.GS_EINVAL
+    h_res, h_xyz, out_offs = run(pts)  # and the context still works
+    assert np.array_equal(h_res[F - 1], want[(F - 1) % 4]["no_ground"])
+    ctx.set_chunk_frames(0)
