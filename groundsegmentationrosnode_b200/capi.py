@@ -25,8 +25,10 @@ EXPORTS = [
     "gs_get_derived", "gs_set_stream", "gs_set_chunk_frames", "gs_set_option", "gs_get_stats", "gs_reset_stats", "gs_get_phase_cycles",
     "gs_last_error", "gs_project", "gs_angle_image", "gs_smooth", "gs_repair_gaps", "gs_erase_ground",
     "gs_label_one_component", "gs_label_components", "gs_backproject", "gs_process_frame", "gs_process_batch_device",
-    "gs_process_batch_host", "gs_process_batch_host_strided", "gs_backproject_camera_info", "gs_synchronize", "gs_unpack_points", "gs_process_cloud2", "gs_pack_cloud_xyzrgb",
+    "gs_process_batch_host", "gs_process_batch_host_strided", "gs_process_batch_device_labels", "gs_label_components_batch_device", "gs_backproject_camera_info", "gs_synchronize", "gs_unpack_points", "gs_process_cloud2", "gs_pack_cloud_xyzrgb",
     "gs_get_camera_info", "gs_create_labeled_range_image", "gs_evaluate",
+    "gs_multi_create", "gs_multi_destroy", "gs_multi_n_gpus", "gs_multi_worker_info", "gs_multi_last_error", "gs_multi_host_alloc",
+    "gs_multi_host_free", "gs_multi_process_batch_host",
 ]
 
 
@@ -82,6 +84,8 @@ def load(build_if_missing=False):
     L.gs_process_frame.argtypes = [C.c_void_p, vp, C.c_size_t, C.c_size_t, u16p, u16p, u16p, f32p, C.POINTER(C.c_uint32)]
     L.gs_process_batch_device.argtypes = [C.c_void_p, vp, i64p, C.c_int, vp, vp, vp, vp, vp]
     L.gs_process_batch_host.argtypes = [C.c_void_p, vp, i64p, C.c_int, vp, vp, C.c_uint64, i64p]
+    L.gs_process_batch_device_labels.argtypes = [C.c_void_p, vp, i64p, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_double]
+    L.gs_label_components_batch_device.argtypes = [C.c_void_p, vp, vp, C.c_int, C.c_double, vp, vp]
     L.gs_process_batch_host_strided.argtypes = [C.c_void_p, vp, C.c_size_t, i64p, C.c_int, vp, vp, C.c_uint64, i64p]
     L.gs_backproject_camera_info.argtypes = [C.c_void_p, u16p, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_int, f32p, C.POINTER(C.c_uint32)]
     L.gs_synchronize.argtypes = [C.c_void_p]
@@ -92,6 +96,16 @@ def load(build_if_missing=False):
     L.gs_get_camera_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     L.gs_create_labeled_range_image.argtypes = [C.c_void_p, vp, C.c_size_t, u16p]
     L.gs_evaluate.argtypes = [C.c_void_p, u16p, u16p, u16p, C.POINTER(GsEval)]
+    L.gs_multi_create.argtypes = [C.POINTER(GsParams), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+    L.gs_multi_destroy.argtypes = [C.c_void_p]
+    L.gs_multi_destroy.restype = None
+    L.gs_multi_n_gpus.argtypes = [C.c_void_p]
+    L.gs_multi_worker_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.gs_multi_last_error.argtypes = [C.c_void_p]
+    L.gs_multi_last_error.restype = C.c_char_p
+    L.gs_multi_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.gs_multi_host_free.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.gs_multi_process_batch_host.argtypes = [C.c_void_p, vp, C.c_size_t, i64p, C.c_int, vp, vp, C.c_uint64, i64p, vp]
     _lib = L
     return L
 
@@ -267,6 +281,13 @@ class Context:
                                           _ptr(ang), _ptr(res), _ptr(xyz), C.byref(n)))
         return dict(range=rng, angle=ang, no_ground=res, xyz=xyz[: n.value].copy())
 
+    def process_frame_into(self, points, no_ground_out, xyz4_out):
+        """One frame with caller-owned (ideally pinned) buffers: no-ground image and cloud only.  Returns the number of points."""
+        n = C.c_uint32(0)
+        self._ck(self._L.gs_process_frame(self._h, _ptr(points), points.shape[0], points.strides[0] if points.shape[0] else 16, None,
+                                          None, _ptr(no_ground_out), _ptr(xyz4_out), C.byref(n)))
+        return n.value
+
     # ---- wire formats (N1)
     def unpack_points(self, data, point_step, off_x, off_y, off_z, off_intensity=-1, big_endian=False):
         """PointCloud2-style byte buffer -> (n, 4) float32 {x, y, z, intensity}"""
@@ -323,6 +344,19 @@ class Context:
                                                  C.c_void_p(d_angle or None), C.c_void_p(d_no_ground or None),
                                                  C.c_void_p(d_xyz4 or None), C.c_void_p(d_counts or None)))
 
+    def process_batch_device_labels(self, d_points, h_offsets, n_frames, d_no_ground=0, d_xyz4=0, d_counts=0, d_labels=0, beta=0.0,
+                                    d_range=0, d_angle=0, d_n_components=0):
+        """process_batch_device plus the Labeler CCL labels (int32 [n_frames, H, W]).  Raw device pointers.  Asynchronous."""
+        offs = np.ascontiguousarray(h_offsets, dtype=np.int64)
+        self._ck(self._L.gs_process_batch_device_labels(self._h, C.c_void_p(d_points), _ptr(offs), n_frames, C.c_void_p(d_range or None),
+                                                        C.c_void_p(d_angle or None), C.c_void_p(d_no_ground or None), C.c_void_p(d_xyz4 or None),
+                                                        C.c_void_p(d_counts or None), C.c_void_p(d_labels or None),
+                                                        C.c_void_p(d_n_components or None), float(beta)))
+
+    def label_components_batch_device(self, d_images, d_angles, n_frames, beta, d_labels, d_n_components=0):
+        self._ck(self._L.gs_label_components_batch_device(self._h, C.c_void_p(d_images), C.c_void_p(d_angles), n_frames, float(beta),
+                                                          C.c_void_p(d_labels), C.c_void_p(d_n_components or None)))
+
     def process_batch_host(self, h_points, h_offsets, no_ground_out=None, xyz4_out=None, out_offsets=None):
         """numpy (ideally pinned) buffers; h_points is [n, 4] XYZI or [n, 3] XYZ float32 (or any [n, k >= 3] float32 records);
         returns (no_ground_out, xyz4_out, out_offsets)."""
@@ -345,3 +379,67 @@ class Context:
         n = C.c_uint32(0)
         self._ck(self._L.gs_backproject_camera_info(self._h, _ptr(img), H, W, Kc, int(range_as_double), _ptr(xyz), C.byref(n)))
         return xyz[: n.value].copy()
+
+
+class MultiGpu:
+    """gs_multi: one worker thread + gs_ctx per GPU, frames sharded in contiguous blocks, no collective."""
+
+    def __init__(self, params, devices=None):
+        self._L = load()
+        h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices) if devices else None
+        rc = self._L.gs_multi_create(C.byref(params), arr, len(devices) if devices else 0, C.byref(h))
+        if rc != GS_OK:
+            raise GsError(rc, "gs_multi_create failed (%s)" % ("no usable CUDA device" if rc == GS_ECUDA else "invalid parameters / devices"))
+        self._h = h
+        self.n_gpus = self._L.gs_multi_n_gpus(h)
+        self.shape = (params.n_beams, params.n_cols)
+        self._bufs = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for ptr, n in self._bufs:
+                self._L.gs_multi_host_free(self._h, ptr, n)
+            self._bufs = []
+            self._L.gs_multi_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def workers(self):
+        out = []
+        for g in range(self.n_gpus):
+            d, n, b = C.c_int(0), C.c_int(0), C.c_int(0)
+            self._L.gs_multi_worker_info(self._h, g, C.byref(d), C.byref(n), C.byref(b))
+            out.append({"device": d.value, "numa_node": n.value, "cpu_bound": bool(b.value)})
+        return out
+
+    def host_array(self, shape, dtype):
+        """A pinned numpy array whose pages were first touched shard by shard (NUMA-local to the GPU that will copy them)."""
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape)) * dt.itemsize
+        p = C.c_void_p()
+        rc = self._L.gs_multi_host_alloc(self._h, max(n, 1), C.byref(p))
+        if rc != GS_OK:
+            raise GsError(rc, "gs_multi_host_alloc(%d bytes) failed" % n)
+        self._bufs.append((p, max(n, 1)))
+        buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+
+    def process_batch_host(self, h_points, h_offsets, no_ground_out=None, xyz4_out=None):
+        """-> (no_ground_out, xyz4_out, first[n_frames], count[n_frames])"""
+        offs = np.ascontiguousarray(h_offsets, dtype=np.int64)
+        n_frames = len(offs) - 1
+        first = np.zeros(n_frames, np.int64)
+        count = np.zeros(n_frames, np.uint32)
+        cap = 0 if xyz4_out is None else xyz4_out.shape[0]
+        stride = 16 if h_points.ndim < 2 else int(h_points.strides[0])
+        rc = self._L.gs_multi_process_batch_host(self._h, _ptr(h_points), stride, _ptr(offs), n_frames, _ptr(no_ground_out), _ptr(xyz4_out), cap,
+                                                 _ptr(first), _ptr(count))
+        if rc != GS_OK:
+            raise GsError(rc, self._L.gs_multi_last_error(self._h).decode())
+        return no_ground_out, xyz4_out, first, count

@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(os.path.dirname(HERE), "libgs_b200.so")
-SOURCES = ["gs_capi.cu", "gs_kernels.cu", "gs_fused.cu"]
+SOURCES = ["gs_capi.cu", "gs_kernels.cu", "gs_fused.cu", "gs_multi.cpp"]
 HEADERS = ["gs_internal.h", "gs_math.cuh", os.path.join("..", "..", "include", "gs_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",

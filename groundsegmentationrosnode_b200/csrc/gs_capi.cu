@@ -168,6 +168,9 @@ struct gs_ctx {
     int slot_frames = 0;
     long long* d_offsets = nullptr;
     size_t d_offsets_cap = 0;
+    // wave scratch of gs_process_batch_device_labels: no-ground and angle images the CCL kernels read
+    uint16_t *lab_res = nullptr, *lab_ang = nullptr;
+    int lab_frames = 0;
     FusedState fused;
     std::string err;
 };
@@ -231,6 +234,8 @@ void free_stage(gs_ctx* c) {
     cudaFree(c->d_xyz);
     c->d_points = nullptr; c->d_points_cap = 0;
     c->d_a = c->d_b = c->d_c = nullptr; c->d_lab = nullptr; c->d_lab32 = nullptr; c->d_xyz = nullptr;
+    cudaFree(c->lab_res); cudaFree(c->lab_ang);
+    c->lab_res = c->lab_ang = nullptr; c->lab_frames = 0;
     for (int k = 0; k < 2; ++k) {
         cudaFree(c->d_in[k]); cudaFree(c->d_res[k]); cudaFree(c->d_cloud[k]); cudaFree(c->d_counts[k]);
         cudaFree(c->d_packed[k]); cudaFree(c->d_prefix[k]);
@@ -459,8 +464,9 @@ int gs_default_params(int preset, gs_params* out) {
         case GS_PRESET_OS1_128:  // cloud2range_node.cpp:281-300, beams doubled, sample_freq 20480
             *out = make_params(128, 20480, -0.392699, 0.392699, 0.3, 120.0, 0.09, 7, GS_VARIANT_ALFA_GS, GS_SMOOTH_NONE);
             return GS_OK;
-        case GS_PRESET_CLOUD2RANGE_DEFAULT:  // cloud2range_node.cpp:281-300 as shipped
+        case GS_PRESET_CLOUD2RANGE_DEFAULT:  // cloud2range_node.cpp:281-300 as shipped; CloudCb runs RepairGaps + SG (:468-470)
             *out = make_params(64, 20000, -0.392699, 0.392699, 0.3, 120.0, 0.09, 7, GS_VARIANT_CLOUD2RANGE, GS_SMOOTH_SG);
+            out->repair_gaps = 1;
             return GS_OK;
         case GS_PRESET_HDL32:  // cloud2range_node.cpp:122-135
             *out = make_params(32, 18000, -0.535293, 0.186227, 0.5, 100.0, 0.087266, 5, GS_VARIANT_ALFA_GS, GS_SMOOTH_NONE);
@@ -797,8 +803,7 @@ int gs_label_components(gs_ctx* ctx, const uint16_t* image, const uint16_t* angl
     CU(cudaMemcpyAsync(ctx->d_b, angle, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(&ctx->d_cnt->components, 0, sizeof(unsigned long long), ctx->stream));
     const Launch L = launch_of(ctx);
-    launch_ccl(L, kp, 1, ctx->d_a, ctx->d_b, nullptr, edge_cutoff(beta), ctx->sc.parent);
-    launch_components(L, kp, 1, ctx->d_a, ctx->sc.parent, ctx->d_lab32, ctx->d_cnt);
+    launch_components_batch(L, kp, 1, ctx->d_a, ctx->d_b, edge_cutoff(beta), ctx->d_lab32, nullptr, ctx->d_cnt);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(labels_out, ctx->d_lab32, static_cast<size_t>(kp.P) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if ((rc = fetch_counters(ctx))) return rc;
@@ -1032,6 +1037,67 @@ int gs_process_batch_device(gs_ctx* ctx, const float* d_points_xyzi, const int64
                       d_angle_out ? d_angle_out + o : nullptr, d_no_ground_out ? d_no_ground_out + o : nullptr,
                       d_xyz4_out ? d_xyz4_out + 4 * o : nullptr, d_counts_out ? d_counts_out + f0 : nullptr);
         if (rc) return rc;
+    }
+    return GS_OK;
+}
+
+int gs_label_components_batch_device(gs_ctx* ctx, const uint16_t* d_images, const uint16_t* d_angles, int n_frames, double beta,
+                                     int32_t* d_labels_out, uint32_t* d_n_components_out) {
+    if (!ctx || n_frames < 0 || (n_frames && (!d_images || !d_angles || !d_labels_out))) return fail(ctx, GS_EINVAL, "gs_label_components_batch_device: bad arguments");
+    if (n_frames == 0) return GS_OK;
+    cudaSetDevice(ctx->device);
+    launch_components_batch(launch_of(ctx), ctx->kp, n_frames, d_images, d_angles, edge_cutoff(beta), d_labels_out, d_n_components_out, nullptr);
+    CU(cudaGetLastError());
+    return GS_OK;
+}
+
+int gs_process_batch_device_labels(gs_ctx* ctx, const float* d_points_xyzi, const int64_t* h_offsets, int n_frames, uint16_t* d_range_out,
+                                   uint16_t* d_angle_out, uint16_t* d_no_ground_out, float* d_xyz4_out, uint32_t* d_counts_out,
+                                   int32_t* d_labels_out, uint32_t* d_n_components_out, double beta) {
+    if (!d_labels_out)
+        return gs_process_batch_device(ctx, d_points_xyzi, h_offsets, n_frames, d_range_out, d_angle_out, d_no_ground_out, d_xyz4_out, d_counts_out);
+    if (!ctx || !h_offsets || n_frames < 0 || (n_frames && !d_points_xyzi)) return fail(ctx, GS_EINVAL, "gs_process_batch_device_labels: bad arguments");
+    if (n_frames == 0) return GS_OK;
+    for (int f = 0; f < n_frames; ++f)
+        if (h_offsets[f + 1] < h_offsets[f]) return fail(ctx, GS_EINVAL, "offsets must be non-decreasing (frame %d)", f);
+    cudaSetDevice(ctx->device);
+    const size_t P = ctx->kp.P;
+    // Waves: the CCL kernels read the no-ground and angle images of the wave the fused kernel has just written; a wave is sized
+    // so that those two images stay in L2 (126 MB) between the two, i.e. the labels cost their own 4 P bytes per frame and
+    // little else.  Images the caller does not ask for live in wave-sized scratch.
+    const size_t l2_budget = static_cast<size_t>(80) << 20;
+    int wave = static_cast<int>(std::max<size_t>(8, std::min<size_t>(static_cast<size_t>(n_frames), l2_budget / (P * 4))));
+    if (fused_supported(ctx->fused)) {  // whole rounds of the persistent grid: no cluster idles through the last frames of a wave
+        const int grid = ctx->fused.max_clusters + ctx->fused.soft_clusters;
+        if (wave > grid) wave -= wave % grid;
+    }
+    const bool need_res = d_no_ground_out == nullptr, need_ang = d_angle_out == nullptr;
+    if ((need_res || need_ang) && ctx->lab_frames < wave) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->lab_res);
+        cudaFree(ctx->lab_ang);
+        ctx->lab_res = ctx->lab_ang = nullptr;
+        ctx->lab_frames = 0;
+        CU(cudaMalloc(&ctx->lab_res, static_cast<size_t>(wave) * P * 2));
+        CU(cudaMalloc(&ctx->lab_ang, static_cast<size_t>(wave) * P * 2));
+        ctx->lab_frames = wave;
+    }
+    int rc;
+    if ((rc = ensure_offsets(ctx, static_cast<size_t>(n_frames) + 1))) return rc;
+    CU(cudaMemcpyAsync(ctx->d_offsets, h_offsets, (static_cast<size_t>(n_frames) + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    const int k_beta = edge_cutoff(beta);
+    for (int f0 = 0; f0 < n_frames; f0 += wave) {
+        const int nf = std::min(wave, n_frames - f0);
+        long long max_points = 0;
+        for (int f = f0; f < f0 + nf; ++f) max_points = std::max<long long>(max_points, h_offsets[f + 1] - h_offsets[f]);
+        const size_t o = static_cast<size_t>(f0) * P;
+        uint16_t* res = need_res ? ctx->lab_res : d_no_ground_out + o;
+        uint16_t* ang = need_ang ? ctx->lab_ang : d_angle_out + o;
+        rc = run_wave(ctx, d_points_xyzi, 16, ctx->d_offsets + f0, nf, max_points, d_range_out ? d_range_out + o : nullptr, ang, res,
+                      d_xyz4_out ? d_xyz4_out + 4 * o : nullptr, d_counts_out ? d_counts_out + f0 : nullptr);
+        if (rc) return rc;
+        launch_components_batch(launch_of(ctx), ctx->kp, nf, res, ang, k_beta, d_labels_out + o, d_n_components_out ? d_n_components_out + f0 : nullptr, nullptr);
+        CU(cudaGetLastError());
     }
     return GS_OK;
 }

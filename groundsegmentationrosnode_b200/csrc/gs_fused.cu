@@ -93,6 +93,7 @@ struct FusedArgs {
     int alt_gate_lo, alt_gate_span;  // rn(altitude * alt_to_fix) - alt_gate_lo <= alt_gate_span (unsigned): certainly inside the altitude gates
     float sg_t[11];            // Savitzky-Golay taps (cloud2range_node.cpp:470), sg_ws = 0: no smoothing
     int sg_ws;
+    int repair;                // typed RepairGaps(range, 5, 1.0f) feeds the angle image (cloud2range_node.cpp:468-469)
     int use_fast;
     // frame queue shared by every launch that works on this batch: a cluster starts with frame first_frame + its index and
     // fetches every further frame with an atomic on *queue (zeroed by the host before the launches): frame = queue_base + old value
@@ -1027,6 +1028,45 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             }
         }
 
+        // Cloud2RangeNode::CloudCb runs RepairGaps(range_image, 5, 1.0f) and builds the angle image from the repaired image, while
+        // EraseGroundBFS keeps the original one (cloud2range_node.cpp:468-473).  Typed reading: depths are the encoded
+        // u16 values as floats, in-painted top to bottom inside a column (repaired pixels feed later ones), written back truncated.
+        // The repaired slab lives in the tag slab, idle between the key compaction and the forest.
+        const uint16_t* s_walk = s_range;
+        if (A.repair) {  // uniform
+            uint16_t* s_rep = s_tag;
+            {
+                const uint4* src = reinterpret_cast<const uint4*>(s_range);
+                uint4* dst = reinterpret_cast<uint4*>(s_rep);
+                const int n16 = (H * S16 * 2 + 15) / 16;
+                for (int i = tid; i < n16; i += NT) dst[i] = src[i];
+            }
+            __syncthreads();
+            constexpr int STEP = 5;
+            for (int c = tid; c < myCW; c += NT) {
+                for (int r = 0; r < H; ++r) {
+                    if (s_rep[r * S16 + c] != 0) continue;  // curr_depth < 0.001f
+                    int counter = 0;
+                    float sum = 0.0f;
+                    for (int i = 1; i < STEP; ++i) {
+                        if (r - i < 0) continue;
+                        const float prev = static_cast<float>(s_rep[(r - i) * S16 + c]);
+                        for (int j = 1; j < STEP; ++j) {
+                            if (r + j > H - 1) continue;
+                            const float next = static_cast<float>(s_rep[(r + j) * S16 + c]);
+                            if (prev > 0.001f && next > 0.001f && fabsf(__fsub_rn(prev, next)) < 1.0f) {
+                                sum = __fadd_rn(sum, __fadd_rn(prev, next));
+                                counter += 2;
+                            }
+                        }
+                    }
+                    if (counter > 0) s_rep[r * S16 + c] = static_cast<uint16_t>(__float2int_rz(__fdiv_rn(sum, static_cast<float>(counter))));
+                }
+            }
+            __syncthreads();
+            s_walk = s_rep;
+        }
+
         GS_PHASE(4);
         // ================================================================================ A: angle image (column walks)
         // one thread per (column, 32-row segment); bottom -> top like the reference (alfa_gs.cpp:347-382).  `checked`: statistics
@@ -1042,7 +1082,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                 float p_z = 0.0f, p_x = 0.0f;  // prev_r * sinf(prev_angle_y), prev_r * cosf(prev_angle_y) (float products, :366-367)
                 bool has_prev = false;
                 for (int r = hi + 1; r < H; ++r) {
-                    const unsigned e = s_range[r * S16 + c];
+                    const unsigned e = s_walk[r * S16 + c];
                     if (e) {
                         const float pr = __double2float_rn(decode_range_d(kp, e));  // prev_r = range (:379)
                         p_z = __fmul_rn(pr, s_sin_y[r]);
@@ -1055,7 +1095,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                     // column-1 quirk (SURVEY.md A.2 iii): prev_col starts at 1 (:340) with prev_r = 0, prev_angle_y = 0
                     bool col0_empty = true;
                     for (int r = 0; r < H; ++r)
-                        if (s_range[r * S16]) { col0_empty = false; break; }
+                        if (s_walk[r * S16]) { col0_empty = false; break; }
                     if (col0_empty) {
                         has_prev = true;
                         p_z = __fmul_rn(0.0f, 0.0f);  // 0 * sinf(0)
@@ -1063,7 +1103,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                     }
                 }
                 unsigned vbits = 0;
-                const uint16_t* p_rng = s_range + hi * S16 + c;
+                const uint16_t* p_rng = s_walk + hi * S16 + c;
                 uint8_t* p_ang = s_angle + hi * S8 + c;
 #pragma unroll 4
                 for (int r = hi; r >= lo; --r, p_rng -= S16, p_ang -= S8) {
@@ -1114,6 +1154,18 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         };
         if ((A.stats & 1) || !A.use_fast) angle_walk(std::true_type{});
         else angle_walk(std::false_type{});
+        if (A.repair) {
+            // the ground search sees the ORIGINAL range image (cloud2range_node.cpp:473): VALID words from it, not from the repaired one
+            const int nword = (H + 31) / 32;
+            for (int sgm = tid; sgm < myCW * nword; sgm += NT) {
+                const int c = sgm % myCW, wseg = sgm / myCW;
+                const int lo = wseg * 32, hi = min(lo + 31, H - 1);
+                unsigned vbits = 0;
+                for (int r = lo; r <= hi; ++r)
+                    if (s_range[r * S16 + c]) vbits |= 1u << (r - lo);
+                s_m32[(MK_VALID * NWD + wseg) * CW + c] = vbits;
+            }
+        }
         __syncthreads();
         if (A.sg_ws > 0) {
             // Alfa_GS::SavitskyGolaySmoothing (alfa_gs.cpp:705-713) = cv::filter2D with a ws x 1 kernel and BORDER_REFLECT101:
@@ -1863,7 +1915,6 @@ int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const Sg
     fs.repair = repair;
     fs.configured = false;
     // what the fused kernel covers; everything else runs on the staged kernels
-    if (repair) return 0;  // RepairGaps (N2) runs on the staged kernels
     if (kp.pixel_policy != GS_PIXEL_LAST) return 0;
     if (kp.H > MAX_H || kp.W < 2 || (kp.H & (kp.H - 1)) != 0) return 0;  // beam counts that are powers of two (16 / 32 / 64 / 128)
     const int NW = kp.H <= 64 ? 1 : 2;
@@ -2091,6 +2142,7 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
         a.gates_dev = reinterpret_cast<const GateConsts*>(static_cast<const unsigned char*>(fs.d_const) + sizeof(KParams));
         a.col_limit = c2r ? kp.W - 1 : kp.W;
         a.sg_ws = fs.smooth ? fs.sg.ws : 0;
+        a.repair = fs.repair ? 1 : 0;
         for (int k = 0; k < 11; ++k) a.sg_t[k] = fs.sg.t[k];
         a.range_lo_in = kp.min_range + 1e-9;
         a.range_hi_in = kp.max_range - 1e-9;

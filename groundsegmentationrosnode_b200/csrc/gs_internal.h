@@ -84,6 +84,10 @@ void launch_one_component(const Launch& L, const KParams& kp, const uint16_t* ra
                           int* parent, int row, int col, int label, uint8_t* label_image);
 void launch_components(const Launch& L, const KParams& kp, int frames, const uint16_t* image, int* parent,
                        int32_t* labels, Counters* cnt);
+// the Labeler as an all-components CCL on `frames` images (shared-memory tiles + seam unions + flatten); labels: [frames][P] int32,
+// n_components: [frames] or NULL, cnt->components accumulates the total when cnt is given
+void launch_components_batch(const Launch& L, const KParams& kp, int frames, const uint16_t* image, const uint16_t* angle, int k_edge,
+                             int32_t* labels, unsigned* n_components, Counters* cnt);
 void launch_erase(const Launch& L, const KParams& kp, int frames, const uint16_t* range, const uint8_t* label, uint16_t* res,
                   unsigned* rowcount);
 void launch_backproject(const Launch& L, const KParams& kp, const Luts& lut, int frames, const uint16_t* image,

@@ -429,6 +429,134 @@ __global__ void __launch_bounds__(256) k_components(const uint16_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// K3b — the Labeler as an all-components CCL on whole batches (north-star kernel 4, BASELINE configs C3 / C5):
+// Label::LabelOneComponent (Labeler/label.cpp:48-104) driven over every unlabelled non-empty pixel = connected components
+// of the non-empty pixels under |angle difference| <= K_beta, 4-neighbours with column wrap (Label::WrapCols, :33-45);
+// canonical label = smallest flat index of the component, -1 for empty pixels.
+//   k_ccl_tile    one CTA per (H x TW tile, frame): the tile's angles in shared memory, vertical runs labelled by a column
+//                 walk (no atomics), one union per pair of horizontally linked runs (the link of row r is skipped when row
+//                 r-1 joins the same two runs), roots = smallest index; writes the tile-local result as flat indices
+//   k_ccl_seams   unions across the tile seams (and the wrap seam W-1 | 0) on the label image itself
+//   k_ccl_flatten every pixel takes its root's index; counts the components of each frame
+// The label image is its own union-find forest between the kernels: labels[p] = flat index of p's parent, roots point to
+// themselves and are the smallest index of their tree.
+// ------------------------------------------------------------------------------------------------
+// find with path halving.  Parents only ever move to smaller indices of the same tree (roots are hung with atomicMin, the
+// halving step uses atomicMin too), so concurrent finds and unions cannot lose a link; without the halving the "smaller index
+// wins" rule builds chains as long as a component is wide and every find walks them.
+__device__ __forceinline__ int ufs_find(int* par, int i) {
+    for (;;) {
+        const int p = *reinterpret_cast<volatile int*>(par + i);
+        if (p == i) return i;
+        const int gp = *reinterpret_cast<volatile int*>(par + p);
+        if (gp == p) return p;
+        atomicMin(par + i, gp);
+        i = gp;
+    }
+}
+__device__ __forceinline__ void ufs_unite(int* par, int a, int b) {  // shared or global forest, the smaller index becomes the root
+    for (;;) {
+        a = ufs_find(par, a);
+        b = ufs_find(par, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }
+        const int old = atomicMin(par + a, b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+constexpr unsigned short CCL_EMPTY = 0xffffu;
+
+__global__ void __launch_bounds__(256) k_ccl_tile(const uint16_t* __restrict__ image, const uint16_t* __restrict__ angle, int k_edge, int TW,
+                                                  int32_t* __restrict__ labels, KParams kp) {
+    extern __shared__ __align__(16) unsigned char ccl_smem[];
+    const int H = kp.H, W = kp.W;
+    const int c0 = blockIdx.x * TW, tw = min(TW, W - c0);
+    const size_t base = static_cast<size_t>(blockIdx.y) * kp.P;
+    int* par = reinterpret_cast<int*>(ccl_smem);                               // [H][TW] tile-local row-major index of the parent
+    unsigned short* ang = reinterpret_cast<unsigned short*>(par + H * TW);     // [H][TW] angle, CCL_EMPTY for empty pixels
+    const int n = H * TW;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int r = t / TW, c = t - r * TW;
+        unsigned short a = CCL_EMPTY;
+        if (c < tw) {
+            const size_t g = base + static_cast<size_t>(r) * W + c0 + c;
+            if (image[g] != 0) a = min(static_cast<unsigned>(angle[g]), 0xfffeu);
+        }
+        ang[t] = a;
+    }
+    __syncthreads();
+    auto linked = [&](int t, int u) -> bool {
+        const int a = ang[t], b = ang[u];
+        return a != CCL_EMPTY && b != CCL_EMPTY && abs(a - b) <= k_edge;
+    };
+    // vertical runs: the top pixel of a run is its root
+    for (int c = threadIdx.x; c < tw; c += blockDim.x) {
+        int top = c;
+        for (int r = 0; r < H; ++r) {
+            const int t = r * TW + c;
+            if (r == 0 || !linked(t - TW, t)) top = t;
+            par[t] = top;
+        }
+    }
+    __syncthreads();
+    // horizontal links: one union per pair of runs
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int r = t / TW, c = t - r * TW;
+        if (c + 1 >= tw || !linked(t, t + 1)) continue;
+        if (r > 0 && linked(t - TW, t - TW + 1) && linked(t - TW, t) && linked(t - TW + 1, t + 1)) continue;  // row r-1 joins the same runs
+        ufs_unite(par, t, t + 1);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int r = t / TW, c = t - r * TW;
+        if (c >= tw) continue;
+        int out = -1;
+        if (ang[t] != CCL_EMPTY) {
+            const int root = ufs_find(par, t);
+            const int rr = root / TW;
+            out = rr * W + c0 + (root - rr * TW);
+        }
+        labels[base + static_cast<size_t>(r) * W + c0 + c] = out;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_ccl_seams(const uint16_t* __restrict__ image, const uint16_t* __restrict__ angle, int k_edge, int TW,
+                                                   int n_tiles, int32_t* __restrict__ labels, KParams kp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kp.H * n_tiles) return;
+    const int r = i / n_tiles, b = i - r * n_tiles;
+    // seam b: last column of tile b | first column of tile b + 1; the last seam is the wrap W-1 | 0
+    const int cl = min((b + 1) * TW, kp.W) - 1;
+    const int cr = (cl + 1 == kp.W) ? 0 : cl + 1;
+    if (cl == cr) return;  // one-column image
+    const size_t base = static_cast<size_t>(blockIdx.y) * kp.P;
+    const int pl = r * kp.W + cl, pr = r * kp.W + cr;
+    if (image[base + pl] == 0 || image[base + pr] == 0) return;
+    if (abs(static_cast<int>(angle[base + pl]) - static_cast<int>(angle[base + pr])) > k_edge) return;
+    ufs_unite(labels + base, pl, pr);
+}
+
+__global__ void __launch_bounds__(256) k_ccl_flatten(int32_t* __restrict__ labels, unsigned* __restrict__ n_components, Counters* cnt, KParams kp) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    bool root = false;
+    if (p < kp.P) {
+        int32_t* L = labels + static_cast<size_t>(blockIdx.y) * kp.P;
+        if (L[p] >= 0) {
+            const int rt = ufs_find(L, p);
+            L[p] = rt;
+            root = rt == p;
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, root);
+    if ((threadIdx.x & 31) == 0 && m) {
+        if (n_components) atomicAdd(n_components + blockIdx.y, static_cast<unsigned>(__popc(m)));
+        if (cnt) atomicAdd(&cnt->components, static_cast<unsigned long long>(__popc(m)));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4 — dilation taps + erase, then ordered compaction + back-projection.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned block_sum_256(unsigned v, unsigned* smem) {
@@ -786,6 +914,27 @@ void launch_one_component(const Launch& L, const KParams& kp, const uint16_t* ra
 void launch_components(const Launch& L, const KParams& kp, int frames, const uint16_t* image, int* parent, int32_t* labels,
                        Counters* cnt) {
     k_components<<<pixel_grid(kp, frames), 256, 0, L.stream>>>(image, parent, labels, cnt, kp);
+    GS_COUNT(L);
+}
+
+int ccl_tile_width(const KParams& kp) {
+    int tw = 512;
+    while (tw > 8 && static_cast<long long>(tw) * kp.H > 8192) tw >>= 1;
+    return tw;
+}
+
+void launch_components_batch(const Launch& L, const KParams& kp, int frames, const uint16_t* image, const uint16_t* angle, int k_edge,
+                             int32_t* labels, unsigned* n_components, Counters* cnt) {
+    const int TW = ccl_tile_width(kp);
+    const int n_tiles = (kp.W + TW - 1) / TW;
+    const size_t smem = static_cast<size_t>(kp.H) * TW * 6;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_ccl_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));  // per device
+    if (n_components) cudaMemsetAsync(n_components, 0, static_cast<size_t>(frames) * sizeof(unsigned), L.stream);
+    k_ccl_tile<<<dim3(n_tiles, frames), 256, smem, L.stream>>>(image, angle, k_edge, TW, labels, kp);
+    GS_COUNT(L);
+    k_ccl_seams<<<dim3((kp.H * n_tiles + 255) / 256, frames), 256, 0, L.stream>>>(image, angle, k_edge, TW, n_tiles, labels, kp);
+    GS_COUNT(L);
+    k_ccl_flatten<<<pixel_grid(kp, frames), 256, 0, L.stream>>>(labels, n_components, cnt, kp);
     GS_COUNT(L);
 }
 

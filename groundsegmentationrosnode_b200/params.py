@@ -89,11 +89,11 @@ class GsStats(C.Structure):
 
 
 def _mk(n_beams, sample_freq, min_angle, max_angle, min_range, max_range, ground, window, variant=GS_VARIANT_ALFA_GS,
-        smoothing=GS_SMOOTH_NONE, rpm=600, start=0.523598):
+        smoothing=GS_SMOOTH_NONE, rpm=600, start=0.523598, repair_gaps=0):
     return GsParams(n_beams=n_beams, rpm=rpm, sample_freq=sample_freq, min_angle=min_angle, max_angle=max_angle,
                     min_range=min_range, max_range=max_range, ground_angle_threshold=ground,
                     start_angle_threshold=start, window_size=window, erase_ground=1, variant=variant,
-                    pixel_policy=GS_PIXEL_LAST, col_policy=GS_COL_FLAT_ALIAS, smoothing=smoothing, repair_gaps=0,
+                    pixel_policy=GS_PIXEL_LAST, col_policy=GS_COL_FLAT_ALIAS, smoothing=smoothing, repair_gaps=repair_gaps,
                     reserved=0)
 
 
@@ -107,9 +107,9 @@ def preset(which):
         return _mk(64, 20480, -0.453785, 0.09599, 0.5, 100.0, 0.115, 11)
     if which == GS_PRESET_OS1_128:  # cloud2range_node.cpp:281-300, beams doubled, 20480 -> 128 x 2048 (C3/C5)
         return _mk(128, 20480, -0.392699, 0.392699, 0.3, 120.0, 0.09, 7)
-    if which == GS_PRESET_CLOUD2RANGE_DEFAULT:  # cloud2range_node.cpp:281-300 as shipped: OS1-64, 64 x 2000, SG-7
+    if which == GS_PRESET_CLOUD2RANGE_DEFAULT:  # cloud2range_node.cpp:281-300 as shipped: OS1-64, 64 x 2000, RepairGaps + SG-7 (:468-470)
         return _mk(64, 20000, -0.392699, 0.392699, 0.3, 120.0, 0.09, 7, variant=GS_VARIANT_CLOUD2RANGE,
-                   smoothing=GS_SMOOTH_SG)
+                   smoothing=GS_SMOOTH_SG, repair_gaps=1)
     if which == GS_PRESET_HDL32:  # cloud2range_node.cpp:122-135 -> 32 x 1800
         return _mk(32, 18000, -0.535293, 0.186227, 0.5, 100.0, 0.087266, 5)
     raise ValueError("unknown preset %r" % (which,))

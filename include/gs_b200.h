@@ -243,6 +243,20 @@ int gs_evaluate(gs_ctx* ctx, const uint16_t* og_range, const uint16_t* seg_range
 int gs_process_batch_device(gs_ctx* ctx, const float* d_points_xyzi, const int64_t* h_offsets,
                             int n_frames, uint16_t* d_range_out, uint16_t* d_angle_out,
                             uint16_t* d_no_ground_out, float* d_xyz4_out, uint32_t* d_counts_out);
+/* The same with the Labeler driven as an all-components CCL on every frame's no-ground image (north-star kernel 4; BASELINE
+ * configs C3 "full pipeline including Labeler CCL" and C5): d_labels_out, n_frames * P int32 = smallest flat index of the pixel's
+ * component, -1 for erased / empty pixels (canonical min-index relabelling); components join 4-neighbours (column
+ * wrap, Label::WrapCols) whose angles (the image EraseBFS saw: smoothed when smoothing is on) differ by at most the integer
+ * cut-off of `beta` (Labeler/label.cpp:90-99, label.h:41).  d_n_components_out: n_frames u32, may be NULL.  d_labels_out NULL =
+ * gs_process_batch_device.  Reference interface: Label::LabelOneComponent, Labeler/label.cpp:48-104. */
+int gs_process_batch_device_labels(gs_ctx* ctx, const float* d_points_xyzi, const int64_t* h_offsets,
+                                   int n_frames, uint16_t* d_range_out, uint16_t* d_angle_out,
+                                   uint16_t* d_no_ground_out, float* d_xyz4_out, uint32_t* d_counts_out,
+                                   int32_t* d_labels_out, uint32_t* d_n_components_out, double beta);
+/* the CCL alone on device-resident images (n_frames * P u16 each) */
+int gs_label_components_batch_device(gs_ctx* ctx, const uint16_t* d_images, const uint16_t* d_angles,
+                                     int n_frames, double beta, int32_t* d_labels_out,
+                                     uint32_t* d_n_components_out);
 /* HOST buffers (pinned recommended): the same pipeline with the host<->device copies done inside, overlapped with
  * compute over waves of frames.  h_no_ground_out: n_frames * P u16 (may be NULL).  h_xyz4_out (may be NULL): the
  * clouds of all frames packed back to back, xyz4_capacity records long; h_out_offsets (n_frames + 1 entries, in
@@ -258,6 +272,27 @@ int gs_process_batch_host_strided(gs_ctx* ctx, const void* h_points, size_t stri
                                   int n_frames, uint16_t* h_no_ground_out, float* h_xyz4_out,
                                   uint64_t xyz4_capacity, int64_t* h_out_offsets);
 int gs_synchronize(gs_ctx* ctx);
+
+/* ---- multi-GPU host driver: frames are independent, so a batch is sharded frame-parallel over the GPUs of one
+ * box with no collective.  One host thread + one gs_ctx + its streams per GPU; every worker thread is bound to the CPUs next to
+ * its GPU before it creates its context.  The reference runs one frame per callback on one ros::spin thread
+ * (src/alfa_node.cpp:298-319,387); N such nodes on N GPUs is what this replaces. */
+typedef struct gs_multi gs_multi;
+/* devices: CUDA device ordinals (a device may be listed more than once: two shards on one GPU); NULL / 0 = every visible device */
+int gs_multi_create(const gs_params* p, const int* devices, int n_devices, gs_multi** out);
+void gs_multi_destroy(gs_multi* m);
+int gs_multi_n_gpus(const gs_multi* m);
+int gs_multi_worker_info(const gs_multi* m, int shard, int* device, int* numa_node, int* cpu_bound);
+const char* gs_multi_last_error(const gs_multi* m);
+/* page-locked host memory for batch buffers whose pages are first touched by the worker that will copy them (block partition) */
+int gs_multi_host_alloc(gs_multi* m, size_t bytes, void** out);
+int gs_multi_host_free(gs_multi* m, void* p, size_t bytes);
+/* gs_process_batch_host_strided on every GPU at once: shard g of G processes the frames [g * F / G, (g + 1) * F / G).  Shard g
+ * packs its clouds from record g * (xyz4_capacity / G) of h_xyz4_out on; h_out_first[f] / h_out_count[f] (n_frames entries each,
+ * required with h_xyz4_out) locate frame f's cloud.  Outputs are identical to the single-GPU call's, frame by frame. */
+int gs_multi_process_batch_host(gs_multi* m, const void* h_points, size_t stride_bytes, const int64_t* h_offsets,
+                                int n_frames, uint16_t* h_no_ground_out, float* h_xyz4_out, uint64_t xyz4_capacity,
+                                int64_t* h_out_first, uint32_t* h_out_count);
 
 #ifdef __cplusplus
 }

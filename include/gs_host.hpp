@@ -430,5 +430,36 @@ private:
     int rows_ = 0, cols_ = 0;
 };
 
+// ---- multi-GPU host driver -----------------------------------------------------------------------------
+// One host thread + one context + its streams per GPU, frames in contiguous blocks, no collective: N of the reference's
+// one-frame-per-callback nodes (alfa_node.cpp:298-319) on N GPUs.  Results are identical to one GPU's, frame by frame.
+class MultiGpu {
+public:
+    explicit MultiGpu(const gs_params& params, const std::vector<int>& devices = std::vector<int>()) {
+        const int rc = gs_multi_create(&params, devices.empty() ? nullptr : devices.data(), static_cast<int>(devices.size()), &m_);
+        if (rc != GS_OK) throw std::runtime_error(rc == GS_ECUDA ? "gs::MultiGpu: no usable CUDA device" : "gs::MultiGpu: invalid parameters or devices");
+    }
+    ~MultiGpu() { gs_multi_destroy(m_); }
+    MultiGpu(const MultiGpu&) = delete;
+    MultiGpu& operator=(const MultiGpu&) = delete;
+    int n_gpus() const { return gs_multi_n_gpus(m_); }
+    // page-locked memory first touched shard by shard (NUMA-local to the GPU that copies it)
+    void* host_alloc(size_t bytes) {
+        void* p = nullptr;
+        if (gs_multi_host_alloc(m_, bytes, &p) != GS_OK) throw std::bad_alloc();
+        return p;
+    }
+    void host_free(void* p, size_t bytes) { gs_multi_host_free(m_, p, bytes); }
+    // shard g of G processes frames [g * F / G, (g + 1) * F / G); frame f's cloud is records [first[f], first[f] + count[f]) of xyz4_out
+    void process_batch_host(const void* points, size_t stride_bytes, const int64_t* offsets, int n_frames, uint16_t* no_ground_out, float* xyz4_out,
+                            uint64_t xyz4_capacity, int64_t* first, uint32_t* count) {
+        if (gs_multi_process_batch_host(m_, points, stride_bytes, offsets, n_frames, no_ground_out, xyz4_out, xyz4_capacity, first, count) != GS_OK)
+            throw std::runtime_error(std::string("gs::MultiGpu: ") + gs_multi_last_error(m_));
+    }
+
+private:
+    gs_multi* m_ = nullptr;
+};
+
 }  // namespace gs
 #endif  // GS_HOST_HPP

@@ -393,10 +393,11 @@ def test_union_stage_stress_frames(oracle, noise_sigma, dropout):
                     assert int(d_cnt[f]) == want[f % 3]["xyz"].shape[0]
 
 
-@pytest.mark.parametrize("preset", [P.GS_PRESET_CLOUD2RANGE_DEFAULT, P.GS_PRESET_HDL64E_2048])
+@pytest.mark.parametrize("preset", [P.GS_PRESET_CLOUD2RANGE_DEFAULT, P.GS_PRESET_HDL64E_2048, P.GS_PRESET_VLP16, P.GS_PRESET_OS1_128])
 def test_repair_gaps_in_the_pipeline(oracle, preset):
-    """N2: with repair_gaps on, RepairGaps(range, 5, 1.0f) feeds the angle image only (cloud2range_node.cpp:468-471, typed
-    version); such a configuration runs on the per-stage kernels.  Frame and batch entry points against the oracle."""
+    """N2 / O1': with repair_gaps on (the cloud2range default, as Cloud2RangeNode::CloudCb runs it), RepairGaps(range, 5, 1.0f)
+    feeds the angle image only (cloud2range_node.cpp:468-473, typed version).  The fused kernel in-paints its range slab in shared
+    memory; the per-stage kernels do the same in global memory.  Frame and batch entry points against the oracle."""
     import torch
 
     p = P.preset(preset).copy(repair_gaps=1)
@@ -405,11 +406,17 @@ def test_repair_gaps_in_the_pipeline(oracle, preset):
     want = [oracle.process_frame(p, f) for f in frames]
     assert not np.array_equal(want[0]["angle"], oracle.process_frame(p.copy(repair_gaps=0), frames[0])["angle"]), "RepairGaps had no effect"
     with capi.Context(p) as ctx:
-        for f, w in zip(frames, want):
-            got = ctx.process_frame(f)
-            for k in ("range", "angle", "no_ground"):
-                assert np.array_equal(got[k], w[k]), k
-            assert np.array_equal(got["xyz"], w["xyz"])
+        for stats, staged in ((1, 0), (0, 0), (0, 1)):
+            ctx.set_option(capi.GS_OPT_COLLECT_STATS, stats)
+            ctx.set_option(capi.GS_OPT_FORCE_STAGED, staged)
+            for f, w in zip(frames, want):
+                l0 = ctx.stats().kernel_launches
+                got = ctx.process_frame(f)
+                assert (ctx.stats().kernel_launches - l0 == 1) == (not staged), "RepairGaps runs inside the fused kernel"
+                for k in ("range", "angle", "no_ground"):
+                    assert np.array_equal(got[k], w[k]), (stats, staged, k)
+                assert np.array_equal(got["xyz"], w["xyz"])
+        ctx.set_option(capi.GS_OPT_FORCE_STAGED, 0)
         offs = np.concatenate([[0], np.cumsum([f.shape[0] for f in frames])]).astype(np.int64)
         d_pts = torch.from_numpy(np.concatenate(frames)).cuda()
         d_res = torch.zeros((3, H, W), dtype=torch.int16, device="cuda")
@@ -687,3 +694,84 @@ def test_host_batch_record_strides_and_error_exits(ctxs, oracle):
     h_res, h_xyz, out_offs = run(pts)  # and the context still works
     assert np.array_equal(h_res[F - 1], want[(F - 1) % 4]["no_ground"])
     ctx.set_chunk_frames(0)
+
+
+@pytest.mark.parametrize("beta_deg", [5, 10, 15, 20])
+@pytest.mark.parametrize("name", ["C3_os1_128", "cloud2range_sg7", "C1_vlp16"])
+def test_batch_labels_match_oracle(oracle, name, beta_deg):
+    """gs_process_batch_device_labels: the Labeler as an all-components CCL on every frame of a batch (BASELINE configs C3 / C5),
+    labels in canonical min-index form against the oracle's serial raster-scan driver of the BFS."""
+    import torch
+
+    if name != "C3_os1_128" and beta_deg not in (5, 20):
+        pytest.skip("the full sweep runs on the C3 / C5 shape")
+    p = P.preset(CONFIGS[name])
+    H, W = p.shape
+    beta = math.radians(beta_deg)
+    pool, offs = synth.make_pool(p, 3, seed0=synth.SEED0 + 300 + beta_deg)
+    F = 7 if name == "C3_os1_128" else 45
+    pts, offsets = synth.tile_pool(pool, offs, F)
+    want = []
+    for i in range(3):
+        w = oracle.process_frame(p, pool[offs[i]:offs[i + 1]])
+        lab, n = oracle.label_components(p, w["no_ground"], w["angle"], beta)
+        want.append((w, lab, n))
+    d_pts = torch.from_numpy(pts).cuda()
+    d_res = torch.zeros((F, H, W), dtype=torch.int16, device="cuda")
+    d_lab = torch.full((F, H, W), -7, dtype=torch.int32, device="cuda")
+    d_n = torch.zeros(F, dtype=torch.int32, device="cuda")
+    d_cnt = torch.zeros(F, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    with capi.Context(p) as ctx:
+        # with and without caller-provided image buffers (wave scratch)
+        for give_res in (True, False):
+            d_lab.fill_(-7)
+            torch.cuda.synchronize()
+            ctx.process_batch_device_labels(d_pts.data_ptr(), offsets, F, d_res.data_ptr() if give_res else 0, 0, d_cnt.data_ptr(), d_lab.data_ptr(), beta,
+                                            d_n_components=d_n.data_ptr())
+            ctx.synchronize()
+            lab = d_lab.cpu().numpy()
+            nn = d_n.cpu().numpy()
+            for f in range(F):
+                w, wl, wn = want[f % 3]
+                assert np.array_equal(lab[f], wl), (give_res, f)
+                assert nn[f] == wn
+                if give_res:
+                    assert np.array_equal(d_res[f].cpu().numpy().view(np.uint16), w["no_ground"])
+
+
+def test_native_multi_gpu_driver_shards_equal_one_gpu(oracle):
+    """gs_multi (one host thread + context per GPU, contiguous frame blocks, no collective): N shards == 1 shard, bit for bit.
+    With one GPU visible the two shards share it (two contexts); with more, every GPU takes a shard as well."""
+    import torch
+
+    p = P.preset(P.GS_PRESET_VLP16)
+    H, W = p.shape
+    pool, offs = synth.make_pool(p, 5, seed0=synth.SEED0 + 1500)
+    F = 23
+    pts, offsets = synth.tile_pool(pool, offs, F)
+    want = [oracle.process_frame(p, pool[offs[i]:offs[i + 1]]) for i in range(5)]
+    n_dev = torch.cuda.device_count()
+    layouts = [[0, 0], [0, 0, 0]] + ([list(range(n_dev))] if n_dev > 1 else [])
+    for devices in layouts:
+        with capi.MultiGpu(p, devices) as mg:
+            assert mg.n_gpus == len(devices)
+            assert [w["device"] for w in mg.workers()] == devices
+            h_pts = mg.host_array(pts.shape, np.float32)
+            h_pts[:] = pts
+            h_res = mg.host_array((F, H, W), np.uint16)
+            h_xyz = mg.host_array((F * H * W, 4), np.float32)
+            for points in (h_pts, np.ascontiguousarray(pts[:, :3])):  # pinned XYZI, pageable 12-byte XYZ
+                h_res[:] = 0
+                _, _, first, count = mg.process_batch_host(points, offsets, h_res, h_xyz)
+                for f in range(F):
+                    w = want[f % 5]
+                    assert np.array_equal(h_res[f], w["no_ground"]), (devices, f)
+                    assert count[f] == w["xyz"].shape[0]
+                    assert np.array_equal(h_xyz[first[f]:first[f] + count[f]], w["xyz"])
+            bad = offsets.copy()
+            bad[3] = bad[2] - 1
+            with pytest.raises(capi.GsError):
+                mg.process_batch_host(h_pts, bad, h_res, h_xyz)
+            _, _, first, count = mg.process_batch_host(h_pts, offsets, h_res, h_xyz)  # still usable
+            assert count[F - 1] == want[(F - 1) % 5]["xyz"].shape[0]
