@@ -27,6 +27,7 @@ EXPORTS = [
     "gs_label_one_component", "gs_label_components", "gs_backproject", "gs_process_frame", "gs_process_batch_device",
     "gs_process_batch_host", "gs_process_batch_host_strided", "gs_process_batch_device_labels", "gs_label_components_batch_device", "gs_backproject_camera_info", "gs_synchronize", "gs_unpack_points", "gs_process_cloud2", "gs_pack_cloud_xyzrgb",
     "gs_get_camera_info", "gs_create_labeled_range_image", "gs_evaluate",
+    "gs_fpga_store_pointcloud", "gs_fpga_read_range_image", "gs_fpga_read_angle_image", "gs_colored_angle_image",
     "gs_multi_create", "gs_multi_destroy", "gs_multi_n_gpus", "gs_multi_worker_info", "gs_multi_last_error", "gs_multi_host_alloc",
     "gs_multi_host_free", "gs_multi_process_batch_host",
 ]
@@ -96,6 +97,10 @@ def load(build_if_missing=False):
     L.gs_get_camera_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     L.gs_create_labeled_range_image.argtypes = [C.c_void_p, vp, C.c_size_t, u16p]
     L.gs_evaluate.argtypes = [C.c_void_p, u16p, u16p, u16p, C.POINTER(GsEval)]
+    L.gs_fpga_store_pointcloud.argtypes = [C.c_void_p, vp, C.c_size_t, C.c_size_t, vp]
+    L.gs_fpga_read_range_image.argtypes = [C.c_void_p, vp, C.c_uint32, C.c_uint32, u16p]
+    L.gs_fpga_read_angle_image.argtypes = [C.c_void_p, vp, C.c_uint32, C.c_uint32, u16p]
+    L.gs_colored_angle_image.argtypes = [C.c_void_p, u16p, C.c_int32, C.c_int32, vp]
     L.gs_multi_create.argtypes = [C.POINTER(GsParams), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
     L.gs_multi_destroy.argtypes = [C.c_void_p]
     L.gs_multi_destroy.restype = None
@@ -319,6 +324,31 @@ class Context:
         K = (C.c_double * 9)()
         self._ck(self._L.gs_get_camera_info(self._h, C.byref(h), C.byref(w), K))
         return h.value, w.value, [float(x) for x in K]
+
+    # ---- FPGA wire formats + coloured angle image
+    def fpga_store_pointcloud(self, points):
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        out = np.zeros(pts.shape[0], np.uint64)
+        self._ck(self._L.gs_fpga_store_pointcloud(self._h, _ptr(pts), pts.shape[0], pts.strides[0] if pts.shape[0] else 16, _ptr(out)))
+        return out
+
+    def fpga_read_range_image(self, words, rows, cols):
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        out = np.empty((64, 1800), np.uint16)
+        self._ck(self._L.gs_fpga_read_range_image(self._h, _ptr(w), rows, cols, _ptr(out)))
+        return out
+
+    def fpga_read_angle_image(self, words, rows, cols):
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        out = np.empty((rows, cols), np.uint16)
+        self._ck(self._L.gs_fpga_read_angle_image(self._h, _ptr(w), rows, cols, _ptr(out)))
+        return out
+
+    def colored_angle_image(self, angle):
+        a = np.ascontiguousarray(angle, dtype=np.uint16)
+        out = np.empty(a.shape + (3,), np.uint8)
+        self._ck(self._L.gs_colored_angle_image(self._h, _ptr(a), a.shape[0], a.shape[1], _ptr(out)))
+        return out
 
     # ---- evaluation
     def create_labeled_range_image(self, points32):

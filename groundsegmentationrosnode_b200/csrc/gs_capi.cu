@@ -997,6 +997,85 @@ int gs_pack_cloud_xyzrgb(gs_ctx* ctx, const float* xyz4, uint32_t n_points, void
     return GS_OK;
 }
 
+// ---- N4: AlfaNode's FPGA wire formats and the coloured angle image (host buffers; the context lends its stream and staging) ----
+namespace {
+int stage_bytes(gs_ctx* ctx, size_t bytes) { return ensure_points(ctx, bytes); }
+}  // namespace
+
+int gs_fpga_store_pointcloud(gs_ctx* ctx, const void* points, size_t n_points, size_t stride_bytes, uint64_t* words_out) {
+    if (!ctx || (n_points && (!points || !words_out)) || stride_bytes < 12 || (stride_bytes & 3)) return fail(ctx, GS_EINVAL, "gs_fpga_store_pointcloud: bad arguments");
+    if (n_points == 0) return GS_OK;
+    cudaSetDevice(ctx->device);
+    const size_t in_bytes = (n_points * stride_bytes + 255) & ~static_cast<size_t>(255);
+    int rc;
+    if ((rc = stage_bytes(ctx, in_bytes + n_points * 8))) return rc;
+    unsigned char* base = static_cast<unsigned char*>(ctx->d_points);
+    CU(cudaMemcpyAsync(base, points, n_points * stride_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    launch_fpga_store(launch_of(ctx), base, n_points, stride_bytes, reinterpret_cast<unsigned long long*>(base + in_bytes));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(words_out, base + in_bytes, n_points * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GS_OK;
+}
+
+int gs_fpga_read_range_image(gs_ctx* ctx, const uint64_t* words, uint32_t rows, uint32_t cols, uint16_t* image64x1800_out) {
+    if (!ctx || !words || !image64x1800_out) return fail(ctx, GS_EINVAL, "gs_fpga_read_range_image: bad arguments");
+    const size_t n = static_cast<size_t>(rows) * cols / 4 * 4;  // whole words only, like the reference's loop (alfa_node.cpp:165,170)
+    if (n > static_cast<size_t>(64) * 1800) return fail(ctx, GS_EINVAL, "gs_fpga_read_range_image: %u x %u pixels do not fit the 64 x 1800 image the reference hard-codes", rows, cols);
+    cudaSetDevice(ctx->device);
+    const size_t img_bytes = static_cast<size_t>(64) * 1800 * 2;
+    int rc;
+    if ((rc = stage_bytes(ctx, img_bytes + n * 2 + 256))) return rc;
+    unsigned char* base = static_cast<unsigned char*>(ctx->d_points);
+    CU(cudaMemsetAsync(base, 0, img_bytes, ctx->stream));  // Mat::zeros (:162)
+    if (n) {
+        CU(cudaMemcpyAsync(base + img_bytes, words, n * 2, cudaMemcpyHostToDevice, ctx->stream));
+        launch_fpga_read_range(launch_of(ctx), reinterpret_cast<const unsigned long long*>(base + img_bytes), static_cast<unsigned>(n),
+                               reinterpret_cast<uint16_t*>(base));
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(image64x1800_out, base, img_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GS_OK;
+}
+
+int gs_fpga_read_angle_image(gs_ctx* ctx, const uint64_t* words, uint32_t rows, uint32_t cols, uint16_t* image_out) {
+    if (!ctx || !words || !image_out) return fail(ctx, GS_EINVAL, "gs_fpga_read_angle_image: bad arguments");
+    if (rows != 64) return fail(ctx, GS_EINVAL, "gs_fpga_read_angle_image: the reference's unpacking counts 64 rows per column (alfa_node.cpp:219,240), got %u", rows);
+    const size_t n = static_cast<size_t>(rows) * cols;
+    if (n == 0) return GS_OK;
+    const size_t n_words = (n >> 8) * 43 + (((n & 255) < 252) ? ((n & 255) + 5) / 6 : 43);
+    cudaSetDevice(ctx->device);
+    const size_t img_bytes = (n * 2 + 255) & ~static_cast<size_t>(255);
+    int rc;
+    if ((rc = stage_bytes(ctx, img_bytes + n_words * 8))) return rc;
+    unsigned char* base = static_cast<unsigned char*>(ctx->d_points);
+    CU(cudaMemcpyAsync(base + img_bytes, words, n_words * 8, cudaMemcpyHostToDevice, ctx->stream));
+    launch_fpga_read_angle(launch_of(ctx), reinterpret_cast<const unsigned long long*>(base + img_bytes), static_cast<unsigned>(n), cols,
+                           reinterpret_cast<uint16_t*>(base));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(image_out, base, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GS_OK;
+}
+
+int gs_colored_angle_image(gs_ctx* ctx, const uint16_t* angle, int32_t rows, int32_t cols, uint8_t* rgb_out) {
+    if (!ctx || !angle || !rgb_out || rows < 0 || cols < 0) return fail(ctx, GS_EINVAL, "gs_colored_angle_image: bad arguments");
+    const size_t n = static_cast<size_t>(rows) * cols;
+    if (n == 0) return GS_OK;
+    cudaSetDevice(ctx->device);
+    const size_t in_bytes = (n * 2 + 255) & ~static_cast<size_t>(255);
+    int rc;
+    if ((rc = stage_bytes(ctx, in_bytes + n * 3))) return rc;
+    unsigned char* base = static_cast<unsigned char*>(ctx->d_points);
+    CU(cudaMemcpyAsync(base, angle, n * 2, cudaMemcpyHostToDevice, ctx->stream));
+    launch_colored_angle(launch_of(ctx), reinterpret_cast<const uint16_t*>(base), static_cast<unsigned>(n), base + in_bytes);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(rgb_out, base + in_bytes, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GS_OK;
+}
+
 int gs_get_camera_info(const gs_ctx* ctx, int32_t* height, int32_t* width, double* K9) {
     if (!ctx || !height || !width || !K9) return GS_EINVAL;
     *height = ctx->der.n_rows;

@@ -88,6 +88,11 @@ void launch_components(const Launch& L, const KParams& kp, int frames, const uin
 // n_components: [frames] or NULL, cnt->components accumulates the total when cnt is given
 void launch_components_batch(const Launch& L, const KParams& kp, int frames, const uint16_t* image, const uint16_t* angle, int k_edge,
                              int32_t* labels, unsigned* n_components, Counters* cnt);
+// N4: AlfaNode's FPGA wire formats and the coloured angle image
+void launch_fpga_store(const Launch& L, const void* points, size_t n, size_t stride, unsigned long long* words);
+void launch_fpga_read_range(const Launch& L, const unsigned long long* words, unsigned n_pixels, uint16_t* image64x1800);
+void launch_fpga_read_angle(const Launch& L, const unsigned long long* words, unsigned n_pixels, unsigned cols, uint16_t* image);
+void launch_colored_angle(const Launch& L, const uint16_t* angle, unsigned n_pixels, unsigned char* rgb);
 void launch_erase(const Launch& L, const KParams& kp, int frames, const uint16_t* range, const uint8_t* label, uint16_t* res,
                   unsigned* rowcount);
 void launch_backproject(const Launch& L, const KParams& kp, const Luts& lut, int frames, const uint16_t* image,

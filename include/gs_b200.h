@@ -217,6 +217,21 @@ int gs_pack_cloud_xyzrgb(gs_ctx* ctx, const float* xyz4, uint32_t n_points, void
  * the u16 row-major buffers of this API are the mono16 payload (step = 2 * width). */
 int gs_get_camera_info(const gs_ctx* ctx, int32_t* height, int32_t* width, double* K9);
 
+/* ---- FPGA wire formats and the coloured angle image.  HOST buffers. ----
+ * gs_fpga_store_pointcloud = AlfaNode::store_pointcloud_hardware (src/alfa_node.cpp:105-131): one 64-bit word per point, four u16
+ * {elevation, azimuth in centi-degrees, range in centimetres, 0}, in the reference's float arithmetic (atan2f / hypotf / sqrtf).
+ * gs_fpga_read_range_image = AlfaNode::read_hardware_pointcloud (:157-194): rows * cols / 4 words of four u16 pixels, column by
+ * column (64 rows each), into the 64 x 1800 image the reference hard-codes (:162); more pixels than that -> GS_EINVAL.
+ * gs_fpga_read_angle_image = AlfaNode::read_hardware_filtered_angle_image (:196-271): 10-bit fields, six per word and four in every
+ * 43rd word, column by column into a rows x cols image; rows must be 64 (the reference's row counter, :219,240).  The input words
+ * are left untouched (the reference shifts them while reading).
+ * gs_colored_angle_image = Alfa_GS::CreateColoredAngleImage (src/alfa_gs.cpp:768-829): rows x cols x 3 bytes; every angle is
+ * scaled by 255 / (largest angle seen so far in raster order) before it is coloured (:781-793) — kept literally. */
+int gs_fpga_store_pointcloud(gs_ctx* ctx, const void* points, size_t n_points, size_t stride_bytes, uint64_t* words_out);
+int gs_fpga_read_range_image(gs_ctx* ctx, const uint64_t* words, uint32_t rows, uint32_t cols, uint16_t* image64x1800_out);
+int gs_fpga_read_angle_image(gs_ctx* ctx, const uint64_t* words, uint32_t rows, uint32_t cols, uint16_t* image_out);
+int gs_colored_angle_image(gs_ctx* ctx, const uint16_t* angle, int32_t rows, int32_t cols, uint8_t* rgb_out);
+
 /* ---- evaluation against labelled data ----
  * gs_create_labeled_range_image = Alfa_GS::CreateLabeledRangeImage (src/alfa_gs.cpp:945-995): points are 32-byte
  * pcl::PointXYZRGB records (x y z pad | b g r a | pad); the image is 1 everywhere and 0 where a kept point lands while the

@@ -775,3 +775,71 @@ def test_native_multi_gpu_driver_shards_equal_one_gpu(oracle):
                 mg.process_batch_host(h_pts, bad, h_res, h_xyz)
             _, _, first, count = mg.process_batch_host(h_pts, offsets, h_res, h_xyz)  # still usable
             assert count[F - 1] == want[(F - 1) % 5]["xyz"].shape[0]
+
+
+def test_fpga_wire_formats_and_colored_angle_image(ctxs, oracle):
+    """N4: AlfaNode's FPGA codecs (src/alfa_node.cpp:105-271) and Alfa_GS::CreateColoredAngleImage (src/alfa_gs.cpp:768-829) against
+    the reference's OWN members (oracle/_ref, compiled verbatim) and against numpy restatements of the integer formats."""
+    p = P.preset(P.GS_PRESET_ALFA_GS_DEFAULT)
+    ctx = ctxs(p)
+    rng = np.random.default_rng(41)
+    pts = synth.make_frame(p, synth.SEED0 + 77)
+    extra = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [-1, 0, 0, 0], [0, -1, 0, 0], [0, 0, 1, 0], [0, 0, -1, 0], [3, -4, 12, 0], [-2.5, -0.0, 0.1, 0],
+                      [1e-3, 1e-3, 1e-3, 0], [100, -250, 30, 0]], np.float32)
+    pts = np.concatenate([pts, extra])
+    words = ctx.fpga_store_pointcloud(pts)
+    # numpy restatement of the packing (the float arithmetic is the reference's own, below)
+    assert np.all((words >> np.uint64(48)) == 0)
+    rng_cm = ((words >> np.uint64(32)) & np.uint64(0xffff)).astype(np.int64)
+    r = np.sqrt((pts[:, 0] * pts[:, 0] + pts[:, 1] * pts[:, 1] + pts[:, 2] * pts[:, 2]).astype(np.float32))
+    assert np.array_equal(rng_cm, (r * np.float32(100)).astype(np.int64) & 0xffff)
+    # read_hardware_pointcloud: 4 pixels per word, column-major, 64 rows per column, hard-coded 64 x 1800 image
+    for rows, cols in ((64, 1800), (64, 900), (16, 1800)):
+        px = rng.integers(0, 65536, size=rows * cols, dtype=np.uint64)
+        w = (px[0::4] | (px[1::4] << np.uint64(16)) | (px[2::4] << np.uint64(32)) | (px[3::4] << np.uint64(48))).astype(np.uint64)
+        got = ctx.fpga_read_range_image(w, rows, cols)
+        want = np.zeros((64, 1800), np.uint16)
+        k = np.arange(rows * cols)
+        want[k % 64, k // 64] = px.astype(np.uint16)
+        assert np.array_equal(got, want)
+    with pytest.raises(capi.GsError):
+        ctx.fpga_read_range_image(np.zeros(64 * 2048 // 4, np.uint64), 64, 2048)
+    # read_hardware_filtered_angle_image: 10-bit fields, 6 per word, every 43rd word 4
+    for cols in (1800, 50, 4):
+        n = 64 * cols
+        vals = rng.integers(0, 1024, size=n, dtype=np.uint64)
+        n_words = (n // 256) * 43 + (43 if n % 256 >= 252 else -(-(n % 256) // 6))
+        w = np.zeros(n_words + 1, np.uint64)
+        for i in range(n):
+            b, wi = divmod(i, 256)
+            word, field = (b * 43 + wi // 6, wi % 6) if wi < 252 else (b * 43 + 42, wi - 252)
+            w[word] |= vals[i] << np.uint64(10 * field)
+        got = ctx.fpga_read_angle_image(w, 64, cols)
+        want = np.zeros((64, cols), np.uint16)
+        k = np.arange(n)
+        want[k % 64, k // 64] = vals.astype(np.uint16)
+        assert np.array_equal(got, want), cols
+    with pytest.raises(capi.GsError):
+        ctx.fpga_read_angle_image(np.zeros(100, np.uint64), 32, 10)
+    # coloured angle image: running maximum in raster order
+    ang = np.clip(rng.integers(-30, 158, size=(64, 300)), 0, 157).astype(np.uint16)
+    ang[0, :5] = 0
+    got = ctx.colored_angle_image(ang)
+    flat = ang.reshape(-1).astype(np.float64)
+    mx = np.maximum.accumulate(flat)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        s = np.where(mx > 0, np.floor(255.0 / np.where(mx > 0, mx, 1) * flat), 0).astype(np.int64)
+    want = np.zeros((flat.size, 3), np.uint8)
+    hi, lo = s >= 128, (s > 0) & (s < 128)
+    want[hi, 0], want[hi, 1] = ((s[hi] - 128) * 2).astype(np.uint8), (255 - (s[hi] - 128) * 2).astype(np.uint8)
+    want[lo, 1], want[lo, 2] = (s[lo] * 2).astype(np.uint8), (255 - 2 * s[lo]).astype(np.uint8)
+    assert np.array_equal(got.reshape(-1, 3), want)
+    if oracle.ref() is not None:  # the reference's own members
+        node = oracle.RefAlfaGS(p)
+        assert np.array_equal(words, node.store_pointcloud_hardware(pts))
+        px = rng.integers(0, 65536, size=64 * 1800, dtype=np.uint64)
+        w = (px[0::4] | (px[1::4] << np.uint64(16)) | (px[2::4] << np.uint64(32)) | (px[3::4] << np.uint64(48))).astype(np.uint64)
+        assert np.array_equal(ctx.fpga_read_range_image(w, 64, 1800), node.read_hardware_pointcloud(w, 64, 1800))
+        wa = rng.integers(0, 1 << 62, size=(64 * 1800 // 256 + 1) * 43, dtype=np.uint64)
+        assert np.array_equal(ctx.fpga_read_angle_image(wa, 64, 1800), node.read_hardware_filtered_angle_image(wa, 64, 1800))
+        assert np.array_equal(got, node.colored_angle_image(ang))

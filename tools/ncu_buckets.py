@@ -47,8 +47,12 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "rege
 rows = list(csv.reader(raw))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 hdr = rows[hi]
-body = [dict(zip(hdr, r)) for r in rows[hi + 1:] if len(r) == len(hdr)]
-lines = T.sass_lines(sys.argv[3] if len(sys.argv) > 3 else "k_frameILi1ELi1024ELi64ELi512")
+body = []
+for r in rows[hi + 1:]:  # the first kernel of the report only (the cluster instantiation; its software-cluster twin follows)
+    if len(r) != len(hdr) or r[0] == "Address" or r[0] == "Kernel Name":
+        break
+    body.append(dict(zip(hdr, r)))
+lines = T.sass_lines(sys.argv[3] if len(sys.argv) > 3 else "k_frameILi1ELi1024ELi64ELi512ELi4ELb0")
 STALLS = ["stall_barrier", "stall_short_sb", "stall_wait", "stall_long_sb", "stall_not_selected", "stall_branch_resolving", "stall_math", "stall_mio"]
 agg = collections.defaultdict(lambda: [0, 0] + [0] * len(STALLS))
 for d, l in zip(body, lines):
