@@ -339,18 +339,23 @@ def parity_block(p, pool, offs, offsets, d_res, d_xyz, d_cnt, d_lab, k_frames, b
     return out
 
 
-def pcie_probe(torch, n_bytes=256 << 20):
-    """Raw pinned-host <-> device copy bandwidth of this rank, both directions at once: the ceiling of the e2e figure."""
+def pcie_probe(torch, barrier, in_per_frame, out_per_frame, n_bytes=256 << 20):
+    """Copy-only ceiling of the e2e figure: this rank moves pinned host -> device and device -> pinned host bytes in the
+    proportion of the workload (one frame = in_per_frame bytes in, out_per_frame bytes out), all ranks at the same time.
+    Returns (frames/s this rank could move, H2D GB/s, D2H GB/s) plus the H2D-alone rate."""
+    n_out = max(1 << 20, int(n_bytes * out_per_frame / max(in_per_frame, 1.0)))
     h_in = torch.empty(n_bytes, dtype=torch.uint8).pin_memory()
-    h_out = torch.empty(n_bytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(n_out, dtype=torch.uint8).pin_memory()
     d_a = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
-    d_b = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
+    d_b = torch.empty(n_out, dtype=torch.uint8, device="cuda")
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
     out = {}
-    for name, both in (("h2d_alone_gbs", False), ("both_directions", True)):
+    reps = 12
+    for both in (False, True):
         torch.cuda.synchronize()
+        barrier()  # buffers exist on every rank: the copies of all ranks overlap in time
         t0 = time.perf_counter()
-        for _ in range(4):
+        for _ in range(reps):
             with torch.cuda.stream(s1):
                 d_a.copy_(h_in, non_blocking=True)
             if both:
@@ -359,9 +364,11 @@ def pcie_probe(torch, n_bytes=256 << 20):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if both:
-            out["h2d_gbs"] = out["d2h_gbs"] = 4 * n_bytes / dt / 1e9
+            out["h2d_gbs"] = reps * n_bytes / dt / 1e9
+            out["d2h_gbs"] = reps * n_out / dt / 1e9
+            out["frames_per_s"] = reps * n_bytes / in_per_frame / dt
         else:
-            out[name] = 4 * n_bytes / dt / 1e9
+            out["h2d_alone_gbs"] = reps * n_bytes / dt / 1e9
     return out
 
 
@@ -521,13 +528,14 @@ def main():
     e_sec = time.perf_counter() - t0
     e_out_records = int(h_out_offs[-1])
     barrier()
-    pcie = pcie_probe(torch)  # every rank at the same time: the ceiling the ranks share
+    # every rank at the same time: the copy-only ceiling the ranks share
+    pcie = pcie_probe(torch, barrier, 16.0 * e_points / Fe, (2.0 * Pn * Fe + 16.0 * e_out_records + 4.0 * Fe) / Fe)
     barrier()
 
     # ---- max over ranks
     t = torch.tensor([ms_total, e_sec], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(F), float(n_points), float(n_ng), float(launches), float(Fe * calls), float(e_points * calls)], dtype=torch.float64, device="cuda")
-    pc = torch.tensor([pcie["h2d_alone_gbs"], pcie["h2d_gbs"]], dtype=torch.float64, device="cuda")
+    pc = torch.tensor([pcie["h2d_alone_gbs"], pcie["h2d_gbs"], pcie["d2h_gbs"], pcie["frames_per_s"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -573,10 +581,11 @@ def main():
                     "h2d_bytes_per_step": int(e_bytes_in), "d2h_bytes_per_step": int(e_bytes_out),
                     "frames_per_step": Fe * calls, "calls_per_step": calls,
                     "api": "gs_process_batch_host (pinned host buffers, waves of frames, copy-in / compute / copy-out on three streams)",
-                    "pcie": {"h2d_alone_gbs_all_ranks": float(pc[0]), "h2d_gbs_all_ranks_with_d2h": float(pc[1]),
-                             "ceiling_frames_per_s": float(pc[1]) * 1e9 / (e_bytes_in / (Fe * calls)),
-                             "note": "raw pinned-host -> device copy bandwidth measured in this run, all ranks copying at once; the ceiling is that "
-                                     "bandwidth over the input bytes of one frame"}},
+                    "pcie": {"ceiling_frames_per_s": float(pc[3]), "frac_of_ceiling": e_fps / max(float(pc[3]), 1e-9),
+                             "h2d_gbs_all_ranks": float(pc[1]), "d2h_gbs_all_ranks": float(pc[2]), "h2d_alone_gbs_all_ranks": float(pc[0]),
+                             "note": "copy-only ceiling measured in this run: every rank moves pinned host -> device and device -> pinned host bytes in the "
+                                     "proportion of one frame (input records in, image + cloud out), all ranks at once, no kernel; "
+                                     "profiles/r2_e2e_probe_8gpu.txt has the same at 1 / 2 / 4 / 8 GPUs from one process"}},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
         }
