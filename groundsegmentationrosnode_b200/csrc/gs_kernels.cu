@@ -468,37 +468,63 @@ __device__ __forceinline__ void ufs_unite(int* par, int a, int b) {  // shared o
 
 constexpr unsigned short CCL_EMPTY = 0xffffu;
 
-__global__ void __launch_bounds__(256) k_ccl_tile(const uint16_t* __restrict__ image, const uint16_t* __restrict__ angle, int k_edge, int TW,
+// TW = 1 << TWL columns per tile (a power of two: row / column of a tile-local index are a shift and a mask)
+__global__ void __launch_bounds__(256) k_ccl_tile(const uint16_t* __restrict__ image, const uint16_t* __restrict__ angle, int k_edge, int TWL,
                                                   int32_t* __restrict__ labels, KParams kp) {
     extern __shared__ __align__(16) unsigned char ccl_smem[];
-    const int H = kp.H, W = kp.W;
-    const int c0 = blockIdx.x * TW, tw = min(TW, W - c0);
+    const int H = kp.H, W = kp.W, TW = 1 << TWL, CM = TW - 1;
+    const int c0 = blockIdx.x << TWL, tw = min(TW, W - c0);
     const size_t base = static_cast<size_t>(blockIdx.y) * kp.P;
     int* par = reinterpret_cast<int*>(ccl_smem);                               // [H][TW] tile-local row-major index of the parent
     unsigned short* ang = reinterpret_cast<unsigned short*>(par + H * TW);     // [H][TW] angle, CCL_EMPTY for empty pixels
     const int n = H * TW;
-    for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        const int r = t / TW, c = t - r * TW;
-        unsigned short a = CCL_EMPTY;
-        if (c < tw) {
-            const size_t g = base + static_cast<size_t>(r) * W + c0 + c;
-            if (image[g] != 0) a = min(static_cast<unsigned>(angle[g]), 0xfffeu);
+    // both images are read unconditionally and four pixels ahead: the tile load is the one phase that waits for HBM / L2
+    for (int t0 = threadIdx.x; t0 < n; t0 += 4 * blockDim.x) {
+        unsigned img[4], an[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int t = t0 + j * blockDim.x;
+            const int r = t >> TWL, c = t & CM;
+            img[j] = 0;
+            an[j] = 0;
+            if (t < n && c < tw) {
+                const size_t g = base + static_cast<size_t>(r) * W + c0 + c;
+                img[j] = __ldg(image + g);
+                an[j] = __ldg(angle + g);
+            }
         }
-        ang[t] = a;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int t = t0 + j * blockDim.x;
+            if (t < n) ang[t] = img[j] ? static_cast<unsigned short>(min(an[j], 0xfffeu)) : CCL_EMPTY;
+        }
     }
     __syncthreads();
     auto linked = [&](int t, int u) -> bool {
         const int a = ang[t], b = ang[u];
         return a != CCL_EMPTY && b != CCL_EMPTY && abs(a - b) <= k_edge;
     };
-    // vertical runs: the top pixel of a run is its root
-    for (int c = threadIdx.x; c < tw; c += blockDim.x) {
-        int top = c;
-        for (int r = 0; r < H; ++r) {
-            const int t = r * TW + c;
-            if (r == 0 || !linked(t - TW, t)) top = t;
-            par[t] = top;
+    // vertical runs: the top pixel of a run is its root.  Every column is walked in segments of SEG rows by different threads (all
+    // threads of the CTA busy); a run that continues across a segment boundary is joined below like any other pair of runs.
+    const int n_seg = max(1, min(static_cast<int>(blockDim.x) >> TWL, H >> 3));
+    const int SEG = (H + n_seg - 1) / n_seg;
+    for (int job = threadIdx.x; job < (n_seg << TWL); job += blockDim.x) {
+        const int c = job & CM, r0 = (job >> TWL) * SEG, r1 = min(r0 + SEG, H);
+        if (c < tw) {
+            int top = r0 * TW + c;
+            for (int r = r0; r < r1; ++r) {
+                const int t = r * TW + c;
+                if (r == r0 || !linked(t - TW, t)) top = t;
+                par[t] = top;
+            }
         }
+    }
+    __syncthreads();
+    for (int job = threadIdx.x; job < (n_seg << TWL); job += blockDim.x) {
+        const int c = job & CM, r0 = (job >> TWL) * SEG;
+        const bool todo = c < tw && r0 > 0 && r0 < H && linked((r0 - 1) * TW + c, r0 * TW + c);
+        if (todo) ufs_unite(par, (r0 - 1) * TW + c, r0 * TW + c);
+        __syncwarp();
     }
     __syncthreads();
     // horizontal links: one union per pair of runs.  The loops keep whole warps together (no early `continue`, a __syncwarp per
@@ -506,7 +532,7 @@ __global__ void __launch_bounds__(256) k_ccl_tile(const uint16_t* __restrict__ i
     // its own and the loop header is issued an order of magnitude more often (measured: 363 instead of 32 issues per warp).
     for (int t0 = 0; t0 < n; t0 += blockDim.x) {
         const int t = t0 + threadIdx.x;
-        const int r = t / TW, c = t - r * TW;
+        const int r = t >> TWL, c = t & CM;
         bool todo = t < n && c + 1 < tw && linked(t, t + 1);
         if (todo && r > 0 && linked(t - TW, t - TW + 1) && linked(t - TW, t) && linked(t - TW + 1, t + 1)) todo = false;  // row r-1 joins the same runs
         if (todo) ufs_unite(par, t, t + 1);
@@ -515,13 +541,12 @@ __global__ void __launch_bounds__(256) k_ccl_tile(const uint16_t* __restrict__ i
     __syncthreads();
     for (int t0 = 0; t0 < n; t0 += blockDim.x) {
         const int t = t0 + threadIdx.x;
-        const int r = t / TW, c = t - r * TW;
+        const int r = t >> TWL, c = t & CM;
         const bool in = t < n && c < tw;
         int out = -1;
         if (in && ang[t] != CCL_EMPTY) {
             const int root = ufs_find(par, t);
-            const int rr = root / TW;
-            out = rr * W + c0 + (root - rr * TW);
+            out = (root >> TWL) * W + c0 + (root & CM);
         }
         __syncwarp();
         if (in) labels[base + static_cast<size_t>(r) * W + c0 + c] = out;
@@ -1044,7 +1069,9 @@ void launch_components_batch(const Launch& L, const KParams& kp, int frames, con
     const size_t smem = static_cast<size_t>(kp.H) * TW * 6;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_ccl_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));  // per device
     if (n_components) cudaMemsetAsync(n_components, 0, static_cast<size_t>(frames) * sizeof(unsigned), L.stream);
-    k_ccl_tile<<<dim3(n_tiles, frames), 256, smem, L.stream>>>(image, angle, k_edge, TW, labels, kp);
+    int TWL = 0;
+    while ((1 << TWL) < TW) ++TWL;
+    k_ccl_tile<<<dim3(n_tiles, frames), 256, smem, L.stream>>>(image, angle, k_edge, TWL, labels, kp);
     GS_COUNT(L);
     k_ccl_seams<<<dim3((kp.H * n_tiles + 255) / 256, frames), 256, 0, L.stream>>>(image, angle, k_edge, TW, n_tiles, labels, kp);
     GS_COUNT(L);
