@@ -21,6 +21,7 @@ max-over-ranks time only).
              the node, one node per host core, on a bounded sample of the same workload
   --latency  one frame at a time through gs_process_frame (the reference's real execution model, alfa_node.cpp:298-319)
   --config   C4 (default, the headline: 64x2048 batch) | C3 (128x2048 with the Labeler CCL labels as an output)
+  --native   in-process multi-GPU mode: the native driver (gs_multi) over --gpus N devices, end to end from host buffers
 """
 import argparse
 import json
@@ -412,6 +413,42 @@ def run_latency(args):
     return 0
 
 
+def run_native(args):
+    """In-process multi-GPU mode: the native driver (gs_multi: one host thread + context per GPU, NUMA-local pinned buffers) over
+    --gpus N devices of this box, end to end from host buffers.  No torchrun, no torch.distributed."""
+    import torch
+
+    from groundsegmentationrosnode_b200 import capi
+
+    G = min(args.gpus, torch.cuda.device_count())
+    preset, _, frames_default, _ = CONFIGS[args.config]
+    Fg = min(args.e2e_frames, args.frames or frames_default)
+    F = Fg * G
+    p, pool, offs = make_workload(64, preset=preset)
+    H, W = p.shape
+    pts, offsets = synth.tile_pool(pool, offs, F)
+    with capi.MultiGpu(p, list(range(G))) as mg:
+        h_pts = mg.host_array(pts.shape, np.float32)
+        h_pts[:] = pts
+        h_res = mg.host_array((F, H, W), np.uint16)
+        h_xyz = mg.host_array((F * (H * W // 2 + 4096), 4), np.float32)
+        for _ in range(max(1, args.warmup // 2)):
+            _, _, first, count = mg.process_batch_host(h_pts, offsets, h_res, h_xyz)
+        steps = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            _, _, first, count = mg.process_batch_host(h_pts, offsets, h_res, h_xyz)
+        dt = (time.perf_counter() - t0) / steps
+        workers = mg.workers()
+    print(json.dumps({
+        "metric": METRIC, "mode": "native multi-GPU driver, one process (gs_multi_process_batch_host)", "n_gpus": G, "unit": "frames/s",
+        "higher_is_better": True, "scaling": "weak", "data": "synthetic", "config": config_dict(args.config, Fg),
+        "e2e": {"value": F / dt, "unit": "frames/s", "h2d_bytes_per_step": int(pts.nbytes), "d2h_bytes_per_step": int(h_res.nbytes + int(count.sum()) * 16),
+                "frames_per_step": F, "ms_per_step": 1e3 * dt},
+        "workers": workers}), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -426,12 +463,15 @@ def main():
     ap.add_argument("--latency", action="store_true", help="single-frame latency of gs_process_frame instead of batch throughput")
     ap.add_argument("--latency-frames", type=int, default=300)
     ap.add_argument("--staged", action="store_true", help="force the per-stage kernels instead of the fused kernel")
+    ap.add_argument("--native", action="store_true", help="in-process multi-GPU mode: the native driver over --gpus N devices, end to end (no torchrun)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
     if args.latency:
         return run_latency(args)
+    if args.native:
+        return run_native(args)
 
     rank, local_rank, world = rank_info()
     affinity = bind_near_gpu(local_rank)  # before torch allocates pinned memory

@@ -1042,25 +1042,50 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                 for (int i = tid; i < n16; i += NT) dst[i] = src[i];
             }
             __syncthreads();
-            constexpr int STEP = 5;
-            for (int c = tid; c < myCW; c += NT) {
-                for (int r = 0; r < H; ++r) {
-                    if (s_rep[r * S16 + c] != 0) continue;  // curr_depth < 0.001f
-                    int counter = 0;
-                    float sum = 0.0f;
-                    for (int i = 1; i < STEP; ++i) {
-                        if (r - i < 0) continue;
-                        const float prev = static_cast<float>(s_rep[(r - i) * S16 + c]);
-                        for (int j = 1; j < STEP; ++j) {
-                            if (r + j > H - 1) continue;
-                            const float next = static_cast<float>(s_rep[(r + j) * S16 + c]);
-                            if (prev > 0.001f && next > 0.001f && fabsf(__fsub_rn(prev, next)) < 1.0f) {
-                                sum = __fadd_rn(sum, __fadd_rn(prev, next));
-                                counter += 2;
-                            }
+            // One thread per column: it first collects the rows of its empty pixels (a 128-bit mask), then visits only those, top
+            // to bottom (repaired pixels feed later ones, alfa_gs.cpp:304-305: rows above are read in their current state, rows below
+            // are still original when a pixel is visited).  A pair (prev, next) counts when both are non-empty and
+            // |prev - next| < 1.0f, i.e. when the two encoded values are EQUAL; sums of at most 32 u16 values are exact in float, so
+            // the reference's float accumulation is the integer sum, divided and truncated as there (:326-328).  Warps reconverge
+            // after every visit (a lane subset left alone in a data-dependent loop re-issues the whole loop on its own).
+            for (int c0w = 0; c0w < myCW; c0w += NT) {  // uniform trip count
+                const int c = c0w + tid;
+                const bool col_ok = c < myCW;
+                uint16_t* col = s_rep + (col_ok ? c : 0);
+                unsigned long long e_lo = 0, e_hi = 0;
+                for (int r = 0; r < min(H, 64); ++r)
+                    if (col[r * S16] == 0) e_lo |= 1ull << r;
+                for (int r = 64; r < H; ++r)
+                    if (col[r * S16] == 0) e_hi |= 1ull << (r - 64);
+                if (!col_ok) e_lo = e_hi = 0;
+                while (__any_sync(0xffffffffu, (e_lo | e_hi) != 0ull)) {
+                    if ((e_lo | e_hi) != 0ull) {
+                        int r;
+                        if (e_lo) {
+                            r = __ffsll(static_cast<long long>(e_lo)) - 1;
+                            e_lo &= e_lo - 1ull;
+                        } else {
+                            r = 63 + __ffsll(static_cast<long long>(e_hi));
+                            e_hi &= e_hi - 1ull;
                         }
+                        unsigned av[4], bv[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            av[i] = (r - 1 - i >= 0) ? col[(r - 1 - i) * S16] : 0u;
+                            bv[i] = (r + 1 + i < H) ? col[(r + 1 + i) * S16] : 0u;
+                        }
+                        unsigned cnt = 0, sum = 0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const bool m = av[i] == bv[j] && av[i] != 0u;
+                                cnt += m ? 1u : 0u;
+                                sum += m ? av[i] : 0u;
+                            }
+                        if (cnt) col[r * S16] = static_cast<uint16_t>(__float2int_rz(__fdiv_rn(static_cast<float>(2u * sum), static_cast<float>(2u * cnt))));
                     }
-                    if (counter > 0) s_rep[r * S16 + c] = static_cast<uint16_t>(__float2int_rz(__fdiv_rn(sum, static_cast<float>(counter))));
+                    __syncwarp();
                 }
             }
             __syncthreads();
