@@ -161,14 +161,62 @@ int main() {
         gs::Range2CloudNode r2c;
         std::vector<gs::PointXYZ> out = r2c.CameraCb(img, c2r.cinfo());
         bool ok = out.size() == w_n;
-        for (size_t i = 0; ok && i < out.size(); ++i) {
-            // K carries max_angle only through d_altitude: allow 1e-6 relative (north-star tolerance for XYZ)
-            for (int k = 0; k < 3; ++k) {
-                const float a = (&out[i].x)[k], b = w_xyz[4 * i + k];
-                ok = ok && std::fabs(a - b) <= 1e-6f * std::max(std::fabs(b), 1e-3f);
-            }
-        }
+        for (size_t i = 0; ok && i < out.size(); ++i)  // K[4] / K[5] are used as published (range2cloud_node.cpp:51-58): bit-exact
+            for (int k = 0; k < 3; ++k) ok = ok && (&out[i].x)[k] == w_xyz[4 * i + k];
         CHECK(ok, "Range2CloudNode::CameraCb");
+        // a foreign CameraInfo: d_azimuth / d_altitude that this library would not derive itself must be honoured
+        gs::CameraInfo foreign = c2r.cinfo();
+        foreign.K[4] *= 1.0 + 3e-16;
+        foreign.K[5] *= 1.0 - 2e-16;
+        std::vector<gs::PointXYZ> out2 = r2c.CameraCb(img, foreign);
+        bool ok2 = out2.size() == out.size();
+        size_t k_img = 0;
+        for (int r = 0; ok2 && r < img.rows; ++r)
+            for (int c = 0; ok2 && c < img.cols; ++c) {
+                const uint16_t e = img.at(r, c);
+                if (!e) continue;
+                const double range = (static_cast<double>(e - 1) / 65534) * (foreign.K[3] - foreign.K[2]) + foreign.K[2];
+                const double alt = (img.rows - r) * foreign.K[5] + foreign.K[0], az = c * foreign.K[4];
+                ok2 = out2[k_img].x == static_cast<float>(std::cos(alt) * std::cos(az) * range) &&
+                      out2[k_img].y == static_cast<float>(std::cos(alt) * std::sin(az) * range) &&
+                      out2[k_img].z == static_cast<float>(std::sin(alt) * range);
+                ++k_img;
+            }
+        CHECK(ok2, "Range2CloudNode::CameraCb with a foreign CameraInfo");
+        bool threw = false;
+        try {
+            gs::Image<uint16_t> small(img.rows - 1, img.cols);
+            r2c.CameraCb(small, c2r.cinfo());
+        } catch (const std::logic_error&) {
+            threw = true;
+        }
+        CHECK(threw, "Range2CloudNode::CameraCb rejects an image that is not height x width");
+
+        // ---- gs::MultiGpu: two shards (on one GPU when only one is visible) == one context, frame by frame
+        std::vector<gs::PointXYZI> batch;
+        std::vector<int64_t> offs(1, 0);
+        const int F = 5;
+        for (int f = 0; f < F; ++f) {
+            const std::vector<gs::PointXYZI> fr = make_cloud<gs::PointXYZI>(q, 100 + f);
+            batch.insert(batch.end(), fr.begin(), fr.end());
+            offs.push_back(static_cast<int64_t>(batch.size()));
+        }
+        const size_t P = static_cast<size_t>(d.n_rows) * d.n_cols;
+        gs::MultiGpu gpus(q, std::vector<int>{0, 0});
+        CHECK(gpus.n_gpus() == 2, "gs::MultiGpu shard count");
+        std::vector<uint16_t> m_res(F * P);
+        std::vector<float> m_xyz(F * P * 4);
+        std::vector<int64_t> first(F);
+        std::vector<uint32_t> count(F);
+        gpus.process_batch_host(batch.data(), sizeof(gs::PointXYZI), offs.data(), F, m_res.data(), m_xyz.data(), F * P, first.data(), count.data());
+        bool okm = true;
+        for (int f = 0; okm && f < F; ++f) {
+            gso_process_frame(&q, batch.data() + offs[f], static_cast<size_t>(offs[f + 1] - offs[f]), sizeof(gs::PointXYZI), nullptr, nullptr, w_res.data(),
+                              w_xyz.data(), &w_n, nullptr);
+            okm = std::equal(w_res.begin(), w_res.end(), m_res.begin() + f * P) && count[f] == w_n &&
+                  std::equal(w_xyz.begin(), w_xyz.begin() + 4 * static_cast<size_t>(w_n), m_xyz.begin() + 4 * first[f]);
+        }
+        CHECK(okm, "gs::MultiGpu::process_batch_host");
     }
     if (failures == 0) std::printf("host api ok\n");
     return failures ? 1 : 0;

@@ -54,11 +54,15 @@ for r in rows[hi + 1:]:  # the first kernel of the report only (the cluster inst
     body.append(dict(zip(hdr, r)))
 lines = T.sass_lines(sys.argv[3] if len(sys.argv) > 3 else "k_frameILi1ELi1024ELi64ELi512ELi4ELb0")
 STALLS = ["stall_barrier", "stall_short_sb", "stall_wait", "stall_long_sb", "stall_not_selected", "stall_branch_resolving", "stall_math", "stall_mio"]
+if len(lines) != len(body):
+    print("warning: %d SASS rows in the report, %d instructions in the library on disk: the capture is of another build, the attribution below is off" % (len(body), len(lines)))
 agg = collections.defaultdict(lambda: [0, 0] + [0] * len(STALLS))
+thr = collections.defaultdict(int)
 for d, l in zip(body, lines):
     b = bucket(l)
     agg[b][0] += int(d["Instructions Executed"] or 0)
     agg[b][1] += int(d["# Samples"] or 0)
+    thr[b] += int(d.get("Thread Instructions Executed") or 0)
     for k, st in enumerate(STALLS):
         agg[b][2 + k] += int(d.get(st) or 0)
 ti = sum(v[0] for v in agg.values())
@@ -68,5 +72,5 @@ print("%-28s %-26s %-9s | share of all samples by stall reason: %s" % ("phase", 
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     if v[1] * 200 < ts:
         continue
-    print("%-28s inst %5.1f%% (%7.1fk/frame)   samples %5.1f%% | %s" % (k, 100 * v[0] / ti, v[0] / frames / 1e3, 100 * v[1] / ts,
-                                                                     " ".join("%8.1f" % (100.0 * x / ts) for x in v[2:])))
+    print("%-28s inst %5.1f%% (%7.1fk/frame, %4.1f lanes)   samples %5.1f%% | %s" % (k, 100 * v[0] / ti, v[0] / frames / 1e3, thr[k] / max(v[0], 1),
+                                                                                  100 * v[1] / ts, " ".join("%8.1f" % (100.0 * x / ts) for x in v[2:])))

@@ -2,8 +2,8 @@
 """BASELINE config C5: angle-threshold sweep on 128 x 2048 frames (needs a GPU).
 
 Ground threshold 2..10 degrees: device-resident throughput of the whole path (fused kernel) and mask parity with the oracle
-on one frame; Labeler threshold beta 5..20 degrees: the all-components CCL (gs_label_components, stage API with host buffers)
-per-frame time and label parity with the oracle.
+on one frame; Labeler threshold beta 5..20 degrees: the whole path plus the all-components CCL on every frame of the batch
+(gs_process_batch_device_labels), throughput and label parity with the oracle.
 
     python tools/sweep_c5.py
 """
@@ -52,16 +52,34 @@ for deg in (2, 3, 4, 5, 6, 7, 8, 9, 10):
         same = np.array_equal(d_res[0].cpu().numpy().view(np.uint16), want["no_ground"]) and int(d_cnt[0]) == want["xyz"].shape[0]
         print("  ground %2d deg (cut-off K = %2d): %8.0f frames/s, %.3e points/s, mask parity with the oracle: %s" % (
             deg, capi.derive(p).k_ground, F / ms * 1e3, int(offsets[-1]) / ms * 1e3, "exact" if same else "MISMATCH"), flush=True)
-print("Labeler beta sweep (gs_label_components on the no-ground image of one frame, host buffers)")
-o = O.process_frame(base, frame0)
+print("Labeler beta sweep: the whole path plus the all-components CCL on every frame (gs_process_batch_device_labels), %d frames per batch" % F)
+d_lab = torch.empty((F, H, W), dtype=torch.int32, device="cuda")
+d_n = torch.zeros(F, dtype=torch.int32, device="cuda")
+n_distinct = len(offs) - 1
+o = [O.process_frame(base, pool[offs[i]:offs[i + 1]]) for i in range(2)]
 with capi.Context(base) as ctx:
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
     for deg in (5, 10, 15, 20):
         beta = math.radians(deg)
-        want, n_want = O.label_components(base, o["no_ground"], o["angle"], beta)
-        ctx.label_components(o["no_ground"], o["angle"], beta)
-        t0 = time.perf_counter()
-        for _ in range(10):
-            got, n_got = ctx.label_components(o["no_ground"], o["angle"], beta)
-        dt = (time.perf_counter() - t0) / 10
-        print("  beta %2d deg: %d components, %.3f ms per frame (copies included), labels equal to the oracle's canonical labels: %s" % (
-            deg, n_got, dt * 1e3, "yes" if (n_got == n_want and np.array_equal(got, want)) else "NO"), flush=True)
+        want = [O.label_components(base, x["no_ground"], x["angle"], beta) for x in o]
+
+        def step():
+            ctx.process_batch_device_labels(d_pts.data_ptr(), offsets, F, d_res.data_ptr(), d_xyz.data_ptr(), d_cnt.data_ptr(), d_lab.data_ptr(), beta,
+                                            d_n_components=d_n.data_ptr())
+        for _ in range(2):
+            step()
+        ctx.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(3):
+                step()
+            e1.record(stream)
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        same = all(np.array_equal(d_lab[i].cpu().numpy(), want[i][0]) and int(d_n[i]) == want[i][1] and
+                   np.array_equal(d_lab[i + n_distinct].cpu().numpy(), want[i][0]) for i in range(2))
+        print("  beta %2d deg (cut-off K = %2d): %6d components per frame, %8.0f frames/s, %.3e points/s, labels equal to the oracle's canonical labels: %s" % (
+            deg, capi.derive(base.copy(ground_angle_threshold=beta)).k_ground, want[0][1], F / ms * 1e3, int(offsets[-1]) / ms * 1e3, "yes" if same else "NO"), flush=True)
