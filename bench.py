@@ -390,19 +390,39 @@ def run_latency(args):
         frames = [torch.from_numpy(pool[offs[i]:offs[i + 1]].copy()).pin_memory() for i in range(8)]
         h_res = torch.empty((H, W), dtype=torch.int16).pin_memory()
         h_xyz = torch.empty((H * W, 4), dtype=torch.float32).pin_memory()
+        p_res = np.empty((H, W), np.uint16)  # pageable outputs: the copying path of gs_process_frame
+        p_xyz = np.empty((H * W, 4), np.float32)
+        row = {}
         with capi.Context(p, device=local_rank) as ctx:
-            def one(i):
+            def pinned(i):
                 return ctx.process_frame_into(frames[i % 8].numpy(), h_res.numpy().view(np.uint16), h_xyz.numpy())
-            for i in range(20):
-                one(i)
-            ts = []
-            for i in range(args.latency_frames):
-                t0 = time.perf_counter()
-                one(i)
-                ts.append(time.perf_counter() - t0)
-        ts = np.array(ts) * 1e6
-        row = {"p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99)), "mean_us": float(ts.mean()),
-               "frames": len(ts), "points_per_frame": float(np.mean([f.shape[0] for f in frames]))}
+
+            def copying(i):
+                return ctx.process_frame_into(frames[i % 8].numpy(), p_res, p_xyz)
+
+            # four variants measured in alternating blocks (the GPU's clocks ramp with load: variants measured one after the other
+            # would not see the same clocks); the first block of every variant is warm-up
+            variants = [("p50_us", pinned, 0), ("p50_us_outputs_copied_back", copying, 0),
+                        ("p50_us_batch_plan_cluster", pinned, 1), ("p50_us_batch_plan_cluster_outputs_copied_back", copying, 1)]
+            samples = {k: [] for k, _, _ in variants}
+            block = max(25, args.latency_frames // 6)
+            for rnd in range(7):
+                for key, fn, no_lone in variants:
+                    ctx.set_option(capi.GS_OPT_NO_LONE_PLAN, no_lone)
+                    for i in range(block):
+                        t0 = time.perf_counter()
+                        fn(i)
+                        dt = time.perf_counter() - t0
+                        if rnd:
+                            samples[key].append(dt * 1e6)
+            ts = np.array(samples["p50_us"])
+            row.update({"p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99)), "mean_us": float(ts.mean()),
+                        "frames": len(ts), "points_per_frame": float(np.mean([f.shape[0] for f in frames])),
+                        "path": "page-locked output buffers: the kernel stores image, cloud and count straight into host memory; "
+                                "one frame spread over the widest cluster that fits"})
+            # where the latency comes from: the same call with the outputs copied back after the kernel, and on the batch plan's cluster
+            for key, _, _ in variants[1:]:
+                row[key] = float(np.percentile(np.array(samples[key]), 50))
         if not args.no_cpu_baseline:
             cpu = reference_run(p, pool, offs, 2.0, 1) if have_reference() else port_run(p, pool, offs, 2.0, 1)
             row["cpu_one_thread_us"] = 1e6 / cpu["fps"]

@@ -18,6 +18,7 @@ GS_OPT_COLLECT_STATS = 1
 GS_OPT_FORCE_STAGED = 2
 GS_OPT_PHASE_TIMING = 3
 GS_OPT_CAS_UNIONS = 4
+GS_OPT_NO_LONE_PLAN = 5
 
 # every symbol include/gs_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [

@@ -168,6 +168,8 @@ struct gs_ctx {
     int slot_frames = 0;
     long long* d_offsets = nullptr;
     size_t d_offsets_cap = 0;
+    unsigned* h_count_mapped = nullptr;  // zero-copy word the fused kernel writes a lone frame's point count into
+    unsigned* d_count_mapped = nullptr;  // its device alias
     // wave scratch of gs_process_batch_device_labels: no-ground and angle images the CCL kernels read
     uint16_t *lab_res = nullptr, *lab_ang = nullptr;
     int lab_frames = 0;
@@ -522,6 +524,7 @@ void gs_destroy(gs_ctx* ctx) {
     fused_release(ctx->fused);
     cudaFree(ctx->lut_block);
     cudaFree(ctx->ci_block);
+    if (ctx->h_count_mapped) cudaFreeHost(ctx->h_count_mapped);
     cudaFree(ctx->d_cnt);
     cudaFree(ctx->d_offsets);
     if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
@@ -577,6 +580,7 @@ int gs_set_option(gs_ctx* ctx, int option, int value) {
         case GS_OPT_FORCE_STAGED: ctx->fused.disabled = value != 0; return GS_OK;
         case GS_OPT_PHASE_TIMING: ctx->phase_timing = value != 0; return GS_OK;
         case GS_OPT_CAS_UNIONS: ctx->cas_unions = value != 0; return GS_OK;
+        case GS_OPT_NO_LONE_PLAN: ctx->fused.no_lone = value != 0; return GS_OK;
         default: return fail(ctx, GS_EINVAL, "unknown option %d", option);
     }
 }
@@ -900,6 +904,35 @@ int gs_process_frame(gs_ctx* ctx, const void* points, size_t n_points, size_t st
     const long long offs[2] = {0, static_cast<long long>(n_points)};
     CU(cudaMemcpyAsync(ctx->d_offsets, offs, sizeof(offs), cudaMemcpyHostToDevice, ctx->stream));
     if (n_points) CU(cudaMemcpyAsync(ctx->d_points, points, n_points * stride_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    // Latency path (the reference's execution model is one frame per callback, alfa_node.cpp:298-319): when the caller's output
+    // buffers are page-locked host memory the device can address, the fused kernel stores the image, the cloud and the point
+    // count straight into them while it computes — no device-to-host copies behind the kernel and ONE synchronisation.
+    {
+        auto visible = [](const void* p, void** d) -> bool {
+            if (!p) { *d = nullptr; return true; }
+            cudaPointerAttributes a;
+            if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+            if (a.type != cudaMemoryTypeHost || !a.devicePointer) return false;
+            *d = a.devicePointer;
+            return true;
+        };
+        void *d_rng = nullptr, *d_ang = nullptr, *d_res = nullptr, *d_xyz = nullptr;
+        const bool fused_ok = fused_supported(ctx->fused) && static_cast<long long>(n_points) <= fused_max_points();
+        if (fused_ok && (no_ground_out || xyz4_out) && visible(range_out, &d_rng) && visible(angle_out, &d_ang) && visible(no_ground_out, &d_res) &&
+            visible(xyz4_out, &d_xyz)) {
+            if (!ctx->h_count_mapped) {
+                CU(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_count_mapped), 64, cudaHostAllocMapped));
+                CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->d_count_mapped), ctx->h_count_mapped, 0));
+            }
+            *ctx->h_count_mapped = 0;
+            if ((rc = run_wave(ctx, ctx->d_points, stride_bytes, ctx->d_offsets, 1, static_cast<long long>(n_points), static_cast<uint16_t*>(d_rng),
+                               static_cast<uint16_t*>(d_ang), static_cast<uint16_t*>(d_res), static_cast<float*>(d_xyz), ctx->d_count_mapped)))
+                return rc;
+            CU(cudaStreamSynchronize(ctx->stream));
+            if (n_out) *n_out = *ctx->h_count_mapped;
+            return GS_OK;
+        }
+    }
     if ((rc = ensure_scratch(ctx, 1))) return rc;
     if ((rc = run_wave(ctx, ctx->d_points, stride_bytes, ctx->d_offsets, 1, static_cast<long long>(n_points), ctx->d_a, ctx->d_b, ctx->d_c,
                        ctx->d_xyz, ctx->sc.counts)))

@@ -40,6 +40,11 @@ namespace gs {
 
 namespace {
 
+#ifndef GS_READOUT_COMPRESS
+#define GS_READOUT_COMPRESS 1
+#endif
+constexpr bool READOUT_COMPRESS = GS_READOUT_COMPRESS != 0;
+
 constexpr int BLK = 256;        // points per dealt block
 constexpr int MAX_BLOCKS = 4096;  // per frame: up to 1 Mi points
 constexpr int MAX_CL = 8;
@@ -119,6 +124,7 @@ struct SoftMail {
 };
 
 constexpr int FB = 18;  // fractional bits of the fixed-point cell coordinates
+
 
 // Shared-memory layout of one CTA: a pure function of (H, CW, NW) so that it can be evaluated at compile time for the
 // specialised instantiations of k_frame (constant strides and offsets fold into the addressing) and at run time otherwise.
@@ -1711,6 +1717,13 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                     uf16s_root_entries2(a_par, n0, n1, e0, e1);
                     if (e0 & 0x8000u) g |= m0;
                     if (e1 & 0x8000u) g |= m1;
+                    // nothing unites any more: hang both runs directly under their roots, which shortens the walks of the runs
+                    // below them that other lanes still have to do (a reader sees the old parent or the root: both are ancestors)
+                    if (READOUT_COMPRESS) {
+                        const unsigned r0 = e0 & 0x7fffu, r1 = e1 & 0x7fffu;
+                        if (r0 != static_cast<unsigned>(n0)) sts_u16(a_par + 2 * n0, r0);
+                        if (r1 != static_cast<unsigned>(n1)) sts_u16(a_par + 2 * n1, r1);
+                    }
                 }
                 MW(MK_G, w, c) = g;
             }
@@ -2025,6 +2038,40 @@ int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const Sg
     fs.smem_bytes = lay.total;
     fs.n_sms = n_sms;
     fs.max_clusters = max_clusters;
+    // A lone frame (gs_process_frame: the reference's one-callback-per-cloud model) has nothing to share the GPU with: it is spread
+    // over the widest cluster that fits (8 CTAs x 256 columns for 64 x 2048) instead of the batch plan's cluster.
+    fs.lone_cluster = 0;
+    fs.lone_kernel = nullptr;
+    if (nt == 1024 && !force_cl && !getenv("GS_NO_LONE_PLAN")) {
+        for (int CL = MAX_CL; CL > lay.CL; --CL) {
+            Layout l;
+            if (!layout_for(kp, CL, NW, &l) || l.total > smem_cap || l.CW < 64) continue;
+            const void* kern = select_kernel(NW, nt, kp.H, l.CW, CL, kp.W, false);
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess) {
+                cudaGetLastError();
+                continue;
+            }
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(static_cast<unsigned>(CL));
+            cfg.blockDim = dim3(nt);
+            cfg.dynamicSmemBytes = l.total;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = static_cast<unsigned>(CL);
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) {
+                cudaGetLastError();
+                continue;
+            }
+            fs.lone_cluster = CL;
+            fs.lone_kernel = kern;
+            break;
+        }
+    }
     if (!fs.d_const) {
         e = cudaMalloc(&fs.d_const, sizeof(KParams) + sizeof(GateConsts));
         if (e != cudaSuccess) return static_cast<int>(e);
@@ -2074,12 +2121,14 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
     if (max_points > fused_max_points()) return static_cast<int>(cudaErrorInvalidValue);
     const KParams& kp = fs.kp;
     const int NW = kp.H <= 64 ? 1 : 2;
+    const bool lone = frames == 1 && fs.lone_cluster > 0 && fs.lone_kernel && !fs.no_lone;  // one frame: the widest cluster that fits
     Layout lay;
-    if (!layout_for(kp, fs.cluster, NW, &lay)) return static_cast<int>(cudaErrorInvalidConfiguration);
+    if (!layout_for(kp, lone ? fs.lone_cluster : fs.cluster, NW, &lay)) return static_cast<int>(cudaErrorInvalidConfiguration);
     // how the frames are shared out: clusters of the cluster kernel first, software clusters for what is left
-    const int n_hw = fs.mode == FUSED_MODE_SOFT ? 0 : std::min(frames, fs.max_clusters);
-    const int n_soft = fs.mode == FUSED_MODE_HW ? 0 : std::min(frames - n_hw, fs.soft_clusters);
-    const int slots = fs.max_clusters + fs.soft_clusters;
+    const int n_hw = lone ? 1 : (fs.mode == FUSED_MODE_SOFT ? 0 : std::min(frames, fs.max_clusters));
+    const int n_soft = (lone || fs.mode == FUSED_MODE_HW) ? 0 : std::min(frames - n_hw, fs.soft_clusters);
+    const int slots_all = fs.max_clusters + fs.soft_clusters;  // mailboxes / queue: sized once for the batch plan
+    const int slots = lone ? 1 : slots_all;
     // remote-record scratch: every point of a frame may be remote in the worst case (shuffled clouds)
     const unsigned rcap = static_cast<unsigned>(std::max<long long>((max_points + 1023) / 1024 * 1024, 1024));
     const size_t need = static_cast<size_t>(slots) * lay.CL * (static_cast<size_t>(rcap) * sizeof(uint2) + sizeof(unsigned));
@@ -2092,7 +2141,7 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
         fs.rowbase_cap = need;
     }
     // frame queue + the mailboxes of the software clusters: one allocation, zeroed before every batch
-    const size_t mail_bytes = 128 + static_cast<size_t>(slots) * sizeof(SoftMail);
+    const size_t mail_bytes = 128 + static_cast<size_t>(std::max(slots_all, 1)) * sizeof(SoftMail);
     if (!fs.d_mail) {
         cudaError_t e = cudaMalloc(&fs.d_mail, mail_bytes);
         if (e != cudaSuccess) return static_cast<int>(e);
@@ -2107,7 +2156,7 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
         }
     }
     {
-        const cudaError_t e = cudaMemsetAsync(fs.d_mail, 0, mail_bytes, L.stream);
+        const cudaError_t e = cudaMemsetAsync(fs.d_mail, 0, lone ? 128 : mail_bytes, L.stream);  // a lone frame only needs the queue word
         if (e != cudaSuccess) return static_cast<int>(e);
     }
     FusedArgs a;
@@ -2208,7 +2257,7 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         void* kargs[] = {&a};
-        const cudaError_t e = cudaLaunchKernelExC(&cfg, fs.kernel, kargs);
+        const cudaError_t e = cudaLaunchKernelExC(&cfg, lone ? fs.lone_kernel : fs.kernel, kargs);
         if (e != cudaSuccess) return static_cast<int>(e);
         ++*L.n_launches;
     }
@@ -2216,7 +2265,7 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
         cudaStream_t st = two ? fs.stream2 : L.stream;
         cudaError_t e;
         a.first_frame = n_hw;
-        a.slot_base = fs.max_clusters;
+        a.slot_base = n_hw > 0 ? fs.max_clusters : 0;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(static_cast<unsigned>(n_soft * lay.CL));
         cfg.blockDim = dim3(fs.threads);

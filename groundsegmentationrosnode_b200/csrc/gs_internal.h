@@ -124,6 +124,9 @@ struct FusedState {
     int mode = 0;            // FUSED_MODE_*
     const void* kernel_soft = nullptr;  // the software-cluster instantiation of the same shape
     int soft_clusters = 0;   // software clusters launched beside (hybrid) or instead of (soft) the cluster kernel
+    int lone_cluster = 0;    // CTAs per frame when a call brings ONE frame (the widest cluster that fits), 0 = none
+    const void* lone_kernel = nullptr;
+    bool no_lone = false;    // GS_OPT_NO_LONE_PLAN: single frames take the batch plan's cluster (tests)
     void* d_mail = nullptr;  // frame queue + software-cluster mailboxes
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;

@@ -143,6 +143,8 @@ int gs_set_chunk_frames(gs_ctx* ctx, int frames);
 #define GS_OPT_PHASE_TIMING 3 /* fused kernel accumulates clock64() cycles per internal phase (gs_get_phase_cycles) */
 #define GS_OPT_CAS_UNIONS 4   /* fused kernel: take the compare-and-swap union path (the one used by frames whose link list
                                * does not fit in shared memory) for every frame; a test aid */
+#define GS_OPT_NO_LONE_PLAN 5 /* fused kernel: a call that brings ONE frame normally spreads it over the widest cluster that fits
+                               * (lowest latency); 1 = use the batch plan's cluster for single frames too.  A test aid. */
 int gs_set_option(gs_ctx* ctx, int option, int value);
 int gs_get_stats(gs_ctx* ctx, gs_stats* out);
 int gs_reset_stats(gs_ctx* ctx);

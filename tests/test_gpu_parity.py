@@ -36,13 +36,17 @@ def ctxs():
     def get(p, staged=False, stats=True):
         # stats=True: GS_OPT_COLLECT_STATS selects the CHECKED instantiations of the fused kernel (the exact arithmetic is evaluated
         # beside every fast result and disagreements are counted); stats=False is the PRODUCTION instantiation bench.py times.
-        if staged == "production":
+        # A call that brings one frame spreads it over the widest cluster that fits (the generic instantiation, lowest latency):
+        # mode "lone".  The other fused modes pin single frames to the batch plan's cluster, i.e. to the instantiation batches run.
+        lone = staged == "lone"
+        if staged in ("production", "lone"):
             staged, stats = False, False
-        key = (bytes(p), staged, stats)
+        key = (bytes(p), staged, stats, lone)
         if key not in cache:
             c = capi.Context(p)
             c.set_option(capi.GS_OPT_COLLECT_STATS, int(stats))
             c.set_option(capi.GS_OPT_FORCE_STAGED, int(staged))
+            c.set_option(capi.GS_OPT_NO_LONE_PLAN, int(not lone))
             cache[key] = c
         return cache[key]
 
@@ -73,8 +77,8 @@ def _xyz_close(got, want):
     assert float((num / den).max()) <= TOL_XYZ
 
 
-MODES = [False, True, "production"]
-MODE_IDS = ["fused_checked", "staged", "fused_production"]
+MODES = [False, True, "production", "lone"]
+MODE_IDS = ["fused_checked", "staged", "fused_production", "fused_lone_frame_plan"]
 
 
 @pytest.mark.parametrize("name", list(CONFIGS))
@@ -82,7 +86,7 @@ MODE_IDS = ["fused_checked", "staged", "fused_production"]
 def test_full_pipeline_matches_oracle(ctxs, oracle, name, staged):
     p = P.preset(CONFIGS[name])
     ctx = ctxs(p, staged)
-    production = staged == "production"
+    production = staged in ("production", "lone")
     for seed in range(2):
         pts = synth.make_frame(p, synth.SEED0 + seed, shuffle=(seed == 1))
         want = oracle.process_frame(p, pts)
@@ -187,7 +191,7 @@ def test_adversarial_frames(ctxs, oracle, name, kind, staged):
     ctx.reset_stats()
     got = ctx.process_frame(pts)
     st = ctx.stats()
-    if staged != "production":
+    if staged not in ("production", "lone"):
         assert st.dropped_points == dropped
     assert st.fast_path_mismatches == 0
     budget = ne_p if kind == "edges" else 0
@@ -579,8 +583,9 @@ def test_random_sensor_configurations(oracle, seed):
                            jitter=float(rng.choice([0.3, 0.45])))
     want = oracle.process_frame(p, pts)
     with capi.Context(p) as ctx:
-        for stats in (1, 0):  # the checked and the production instantiation of the fused kernel
+        for stats in (1, 0):  # the checked instantiation on the batch plan's cluster, the production one on the lone-frame plan
             ctx.set_option(capi.GS_OPT_COLLECT_STATS, stats)
+            ctx.set_option(capi.GS_OPT_NO_LONE_PLAN, stats)
             l0 = ctx.stats().kernel_launches
             got = ctx.process_frame(pts)
             st = ctx.stats()
@@ -843,3 +848,36 @@ def test_fpga_wire_formats_and_colored_angle_image(ctxs, oracle):
         wa = rng.integers(0, 1 << 62, size=(64 * 1800 // 256 + 1) * 43, dtype=np.uint64)
         assert np.array_equal(ctx.fpga_read_angle_image(wa, 64, 1800), node.read_hardware_filtered_angle_image(wa, 64, 1800))
         assert np.array_equal(got, node.colored_angle_image(ang))
+
+
+@pytest.mark.parametrize("name", ["C1_vlp16", "C2_hdl64_2048", "C3_os1_128", "cloud2range_sg7"])
+def test_lone_frame_into_pinned_buffers(oracle, name):
+    """The latency path of gs_process_frame: with page-locked output buffers the fused kernel stores image, cloud and count straight
+    into host memory (no device-to-host copies, one synchronisation).  Same bits as the copying path and the oracle."""
+    import torch
+
+    p = P.preset(CONFIGS[name])
+    H, W = p.shape
+    frames = [synth.make_frame(p, synth.SEED0 + 1700 + k) for k in range(3)]
+    frames.append(np.zeros((0, 4), np.float32))
+    h_res = torch.zeros((H, W), dtype=torch.int16).pin_memory()
+    h_xyz = torch.zeros((H * W, 4), dtype=torch.float32).pin_memory()
+    with capi.Context(p) as ctx:
+        for pts in frames:
+            want = oracle.process_frame(p, pts)
+            h_in = torch.from_numpy(pts.copy()).pin_memory() if pts.shape[0] else torch.zeros((0, 4), dtype=torch.float32)
+            h_res.fill_(-1)
+            l0 = ctx.stats().kernel_launches
+            n = ctx.process_frame_into(h_in.numpy(), h_res.numpy().view(np.uint16), h_xyz.numpy())
+            assert ctx.stats().kernel_launches - l0 == 1
+            assert n == want["xyz"].shape[0]
+            assert np.array_equal(h_res.numpy().view(np.uint16), want["no_ground"])
+            assert np.array_equal(h_xyz.numpy()[:n], want["xyz"])
+            # image only, and pageable buffers (the copying path)
+            h_res.fill_(-1)
+            assert ctx.process_frame_into(h_in.numpy(), h_res.numpy().view(np.uint16), None) == n
+            assert np.array_equal(h_res.numpy().view(np.uint16), want["no_ground"])
+            res2 = np.zeros((H, W), np.uint16)
+            xyz2 = np.zeros((H * W, 4), np.float32)
+            assert ctx.process_frame_into(pts, res2, xyz2) == n
+            assert np.array_equal(res2, want["no_ground"]) and np.array_equal(xyz2[:n], want["xyz"])
