@@ -884,8 +884,12 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             // every point; the production instantiation keeps the hot path to the certified pixel, the key and one atomic,
             // with everything else (padding lanes, uncertified points, the alias column) in one cold branch
             const unsigned a_key = smem_base32 + off_range;  // shared-window address of the key slab
-            auto place = [&](auto checked_tag, const float4 p4, const int i, const Lean& L) {
+            auto place = [&](auto checked_tag, auto nearest_tag, const float4 p4, const int i, const Lean& L) {
                 constexpr bool CHECKED = decltype(checked_tag)::value;
+                // pixel_policy: the reference keeps the LAST point in input order (key = order tag << 16 | range, the later
+                // point has the larger key); the north-star variant keeps the NEAREST return, ties to the lowest index (key =
+                // (65536 - range) << 16 | ~order tag: the smaller range, then the earlier point, has the larger key).  Both are one atomicMax.
+                constexpr bool NEAREST = decltype(nearest_tag)::value;
                 unsigned k = 0x80000000u | lane;  // owner << 16 | slab address; this value is unique per lane: never matches
                 unsigned val = 0;                 // g << 16 | encoded range
                 int row = L.row, col = L.col;
@@ -921,19 +925,30 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                     const int owner = SPEC ? col / CW : min(static_cast<int>(__umulhi(static_cast<unsigned>(col), A.cw_magic)), CL - 1);
                     const int lc = col - owner * CW;
                     k = (static_cast<unsigned>(owner) << 16) | static_cast<unsigned>(row * S16 + lc);
-                    val = ((static_cast<unsigned>(i >> tag_shift) + 1u) << 16) | enc;
+                    const unsigned tagv = static_cast<unsigned>(i >> tag_shift) + 1u;
+                    val = NEAREST ? (((65536u - enc) << 16) | (65535u - tagv)) : ((tagv << 16) | enc);  // 65536 - enc is in [1, 65535]: never 0 = empty
                 }
                 // points that share an order tag are 2^tag_shift consecutive lanes: the highest lane among those that hit the
                 // same pixel holds the latest point (xor-shuffles over the group; __match_any_sync would do the same for a
                 // whole warp but costs ~100 cycles of the address-divergence unit per call when all keys differ)
                 bool winner = have;
                 if (tag_shift) {  // uniform; 1 for frames of 64 Ki .. 128 Ki points
-                    const unsigned o1 = __shfl_xor_sync(0xffffffffu, k, 1);
-                    if (o1 == k && !(lane & 1)) winner = false;
+                    if constexpr (NEAREST) {
+                        // same pixel, same order tag: the larger key (smaller range) wins, equal ranges go to the lower lane (earlier point)
 #pragma unroll 1
-                    for (int d = 2; d < (1 << tag_shift); ++d) {
-                        const unsigned other = __shfl_xor_sync(0xffffffffu, k, d);
-                        if (other == k && (lane ^ d) > lane) winner = false;
+                        for (int d = 1; d < (1 << tag_shift); ++d) {
+                            const unsigned other = __shfl_xor_sync(0xffffffffu, k, d);
+                            const unsigned oval = __shfl_xor_sync(0xffffffffu, val, d);
+                            if (other == k && (oval > val || (oval == val && (lane ^ d) < lane))) winner = false;
+                        }
+                    } else {
+                        const unsigned o1 = __shfl_xor_sync(0xffffffffu, k, 1);
+                        if (o1 == k && !(lane & 1)) winner = false;
+#pragma unroll 1
+                        for (int d = 2; d < (1 << tag_shift); ++d) {
+                            const unsigned other = __shfl_xor_sync(0xffffffffu, k, d);
+                            if (other == k && (lane ^ d) > lane) winner = false;
+                        }
                     }
                 }
                 const bool local = winner && static_cast<int>(k >> 16) == rank;
@@ -952,7 +967,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                     }
                 }
             };
-            auto rounds = [&](auto checked_tag) {
+            auto rounds = [&](auto checked_tag, auto nearest_tag) {
                 float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb4 = na;
                 int ni = 0;
                 if (warp < n_punits) ni = load_unit(warp, na, nb4);
@@ -961,12 +976,17 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                     const int i0 = ni;
                     if (u + NT / 32 < n_punits) ni = load_unit(u + NT / 32, na, nb4);
                     const Lean La = project_lean(A, pa.x, pa.y, pa.z), Lb = project_lean(A, pb.x, pb.y, pb.z);  // straight-line: the two interleave
-                    place(checked_tag, pa, i0, La);
-                    place(checked_tag, pb, i0 + 32, Lb);
+                    place(checked_tag, nearest_tag, pa, i0, La);
+                    place(checked_tag, nearest_tag, pb, i0 + 32, Lb);
                 }
             };
-            if (stats1 || !A.use_fast) rounds(std::true_type{});
-            else rounds(std::false_type{});
+            if (kp.pixel_policy == GS_PIXEL_NEAREST) {  // uniform
+                if (stats1 || !A.use_fast) rounds(std::true_type{}, std::true_type{});
+                else rounds(std::false_type{}, std::true_type{});
+            } else {
+                if (stats1 || !A.use_fast) rounds(std::true_type{}, std::false_type{});
+                else rounds(std::false_type{}, std::false_type{});
+            }
         }
         GS_PHASE(2);
         // remote records and counts: barrier.cluster arrives with release and waits with acquire semantics at cluster scope,
@@ -1007,6 +1027,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             const uint4* k4 = reinterpret_cast<const uint4*>(s_key);
             uint2* r2 = reinterpret_cast<uint2*>(s_range);
             constexpr int CQ = 3;  // quads per thread between two barriers (12 registers)
+            const bool nearest_keys = kp.pixel_policy == GS_PIXEL_NEAREST;
             for (int base = 0; base < n_quads; base += CQ * NT) {
                 uint4 v[CQ];
 #pragma unroll
@@ -1019,7 +1040,15 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
 #pragma unroll
                 for (int j = 0; j < CQ; ++j) {
                     const int i = base + j * NT + tid;
-                    if (i < n_quads) r2[i] = make_uint2((v[j].x & 0xffffu) | (v[j].y << 16), (v[j].z & 0xffffu) | (v[j].w << 16));
+                    if (i < n_quads) {
+                        if (nearest_keys) {  // the range sits complemented in the upper half of a key; an untouched key is an empty pixel
+                            const unsigned e0 = v[j].x ? 65536u - (v[j].x >> 16) : 0u, e1 = v[j].y ? 65536u - (v[j].y >> 16) : 0u;
+                            const unsigned e2 = v[j].z ? 65536u - (v[j].z >> 16) : 0u, e3 = v[j].w ? 65536u - (v[j].w >> 16) : 0u;
+                            r2[i] = make_uint2(e0 | (e1 << 16), e2 | (e3 << 16));
+                        } else {
+                            r2[i] = make_uint2((v[j].x & 0xffffu) | (v[j].y << 16), (v[j].z & 0xffffu) | (v[j].w << 16));
+                        }
+                    }
                 }
             }
             __syncthreads();
@@ -1953,7 +1982,7 @@ int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const Sg
     fs.repair = repair;
     fs.configured = false;
     // what the fused kernel covers; everything else runs on the staged kernels
-    if (kp.pixel_policy != GS_PIXEL_LAST) return 0;
+    if (kp.pixel_policy != GS_PIXEL_LAST && kp.pixel_policy != GS_PIXEL_NEAREST) return 0;
     if (kp.H > MAX_H || kp.W < 2 || (kp.H & (kp.H - 1)) != 0) return 0;  // beam counts that are powers of two (16 / 32 / 64 / 128)
     const int NW = kp.H <= 64 ? 1 : 2;
     int max_smem = 0, n_sms = 0;

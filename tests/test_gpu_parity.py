@@ -881,3 +881,43 @@ def test_lone_frame_into_pinned_buffers(oracle, name):
             xyz2 = np.zeros((H * W, 4), np.float32)
             assert ctx.process_frame_into(pts, res2, xyz2) == n
             assert np.array_equal(res2, want["no_ground"]) and np.array_equal(xyz2[:n], want["xyz"])
+
+
+@pytest.mark.parametrize("name", ["C1_vlp16", "C2_hdl64_2048", "C3_os1_128", "cloud2range_sg7"])
+def test_nearest_return_policy_in_the_fused_kernel(ctxs, oracle, name):
+    """pixel_policy = nearest (the north-star variant: smallest range wins a pixel, ties to the lowest index) runs in the fused kernel
+    like the reference's last-writer rule: one launch, every instantiation, several returns per pixel in random order, ranges
+    on the gates, and a batch."""
+    import torch
+
+    p = P.preset(CONFIGS[name]).copy(pixel_policy=P.GS_PIXEL_NEAREST)
+    H, W = p.shape
+    frames = [synth.make_adversarial_frame(p, synth.SEED0 + 21, "collisions"), synth.make_adversarial_frame(p, synth.SEED0 + 22, "edges"),
+              synth.make_frame(p, synth.SEED0 + 23, shuffle=True)]
+    want = [oracle.process_frame(p, f) for f in frames]
+    assert not np.array_equal(want[0]["range"], oracle.process_frame(p.copy(pixel_policy=P.GS_PIXEL_LAST), frames[0])["range"])
+    for mode in MODES:
+        ctx = ctxs(p, mode)
+        for f, w in zip(frames, want):
+            l0 = ctx.stats().kernel_launches
+            got = ctx.process_frame(f)
+            assert (ctx.stats().kernel_launches - l0 == 1) == (mode is not True)
+            _, ne_p, _ = oracle.create_range_image(p, f, with_counts=True)
+            bad = _assert_images_equal(got["range"], w["range"], "range image", ne_p)
+            if bad == 0:
+                assert np.array_equal(got["angle"], w["angle"])
+                assert np.array_equal(got["no_ground"], w["no_ground"])
+                assert np.array_equal(got["xyz"], w["xyz"])
+    offs = np.concatenate([[0], np.cumsum([f.shape[0] for f in frames])]).astype(np.int64)
+    pts, offsets = synth.tile_pool(np.concatenate(frames), offs, 40)
+    d_pts = torch.from_numpy(pts).cuda()
+    d_rng = torch.zeros((40, H, W), dtype=torch.int16, device="cuda")
+    d_cnt = torch.zeros(40, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx = ctxs(p, "production")
+    ctx.process_batch_device(d_pts.data_ptr(), offsets, 40, d_rng.data_ptr(), 0, 0, 0, d_cnt.data_ptr())
+    ctx.synchronize()
+    rng_img = d_rng.cpu().numpy().view(np.uint16)
+    for f in (0, 2, 3, 39):  # the collision frame and the shuffled one (no cell-edge points), early and late in the queue
+        assert np.array_equal(rng_img[f], want[f % 3]["range"])
+        assert int(d_cnt[f]) == want[f % 3]["xyz"].shape[0]

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Throughput of the paths beside the headline one, 64x2048 frames, device-resident batches (needs a GPU):
   ordered (firing order, the headline)  |  row-major organised clouds  |  shuffled clouds (every point through the remote list)
-  pixel_policy = nearest (per-stage kernels)  |  the per-stage kernels on the default configuration
+  pixel_policy = nearest (fused kernel)  |  the per-stage kernels on the default configuration
 
     python tools/slow_paths.py [frames]
 """
@@ -72,5 +72,5 @@ rm, rmo = reorder("row-major")
 run("row-major organised cloud, fused kernel", base, rm, rmo)
 sh, sho = reorder("shuffled")
 run("shuffled cloud (remote-list path), fused kernel", base, sh, sho)
-run("pixel_policy = nearest (per-stage kernels)", base.copy(pixel_policy=P.GS_PIXEL_NEAREST), pool, offs)
+run("pixel_policy = nearest (north-star variant), fused kernel", base.copy(pixel_policy=P.GS_PIXEL_NEAREST), pool, offs)
 run("default configuration forced onto the per-stage kernels", base, pool, offs, staged=True)
