@@ -12,7 +12,7 @@ import numpy as np
 from .params import (GS_ECUDA, GS_EINVAL, GS_OK, GsDerived, GsEval, GsParams, GsStats)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgs_b200.so")
+LIB_PATH = os.environ.get("GS_B200_LIB") or os.path.join(HERE, "libgs_b200.so")  # GS_B200_LIB: another build of the same ABI (A/B runs)
 
 GS_OPT_COLLECT_STATS = 1
 GS_OPT_FORCE_STAGED = 2

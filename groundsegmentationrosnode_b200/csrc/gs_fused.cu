@@ -40,6 +40,9 @@ namespace gs {
 
 namespace {
 
+#ifndef GS_EXP_DOUBLE
+#define GS_EXP_DOUBLE 0  // timing experiments: 1 / 2 / 3 run the projection / the angle walk / the output loop twice (idempotent)
+#endif
 #ifndef GS_READOUT_COMPRESS
 #define GS_READOUT_COMPRESS 1
 #endif
@@ -78,7 +81,7 @@ struct FusedArgs {
     uint2* rlist;        // [clusters][CL][rcap] remote records
     unsigned* rcount;    // [clusters][CL]
     unsigned rcap;
-    // ---- fast (float / fixed-point) projection, certified by margins (see project_lean)
+    // ---- fast (float / fixed-point) projection, certified by margins (see project_lean2)
     double enc_scale;          // 65534 / (max_range - min_range)
     float alt_to_fix;          // altitude (rad) -> row cells * 2^FB
     float az_to_fix;           // angle (rad)    -> column cells * 2^FB
@@ -93,7 +96,7 @@ struct FusedArgs {
     const GateConsts* gates_dev;  // device-memory constants of project_undecided
     int col_limit, col_wrap;   // largest column the fast path may return; GS_COL_WRAP
     double range_lo_in, range_hi_in, range_lo_out, range_hi_out;  // range gates -/+ 1e-9 m
-    // lean fast path (project_lean): encoded range in 2^-UB fixed point, altitude gates in cell fixed point
+    // lean fast path (project_lean2): encoded range in 2^-UB fixed point, altitude gates in cell fixed point
     double u_scale, u_c0;      // ufix = trunc(range * u_scale + u_c0) = ((range - min_range) * 65534 / span + 1) * 2^UB
     int alt_gate_lo, alt_gate_span;  // rn(altitude * alt_to_fix) - alt_gate_lo <= alt_gate_span (unsigned): certainly inside the altitude gates
     float sg_t[11];            // Savitzky-Golay taps (cloud2range_node.cpp:470), sg_ws = 0: no smoothing
@@ -149,9 +152,9 @@ __host__ __device__ constexpr Layout layout_hcw(int H, int CW, int NW) {
     L.ok = static_cast<size_t>(H) * L.S16 <= 65535   // slab addresses are 16-bit
            && static_cast<size_t>(H) * CW <= 32768;  // run indices are 15-bit
     const size_t range_bytes = align_up(static_cast<size_t>(H) * L.S16 * 2, 16);
-    const size_t masks_bytes = align_up(static_cast<size_t>(MK_KINDS) * NW * CW * 8 + static_cast<size_t>(2) * H * L.NG * 4, 16);
     const size_t tag_bytes = align_up(max_sz(range_bytes, static_cast<size_t>(H) * CW * 2), 16);
     const size_t angle_bytes = align_up(max_sz(static_cast<size_t>(H) * L.S8, static_cast<size_t>(4096) * 3), 16);  // 4096 = MAX_BLOCKS
+    const size_t masks_bytes = align_up(static_cast<size_t>(MK_KINDS) * NW * CW * 8 + static_cast<size_t>(2) * H * L.NG * 4, 16);
     const size_t Hp = (static_cast<size_t>(H) + 7) & ~static_cast<size_t>(7);
     const size_t misc_bytes = align_up(14 * 8 + static_cast<size_t>(8) * Hp * 4 + Hp * 4 + Hp + 2 * 8 * 4 + (8 + 20 + 64) * 4 + 64 + Hp + 16, 16);  // 8 = MAX_CL
     L.off_range = 0;
@@ -203,6 +206,50 @@ __device__ __forceinline__ float atan01(float a) {
     return __fmaf_rn(__fmul_rn(a, s), q, a);
 }
 
+// ---- sm_100 packed binary32 arithmetic (FFMA2 / FMUL2 / FADD2): one instruction, two independent IEEE operations — each half
+// rounds exactly like the scalar fma.rn / mul.rn / add.rn, so a packed evaluation is bit-identical to two scalar ones and the
+// certified margins carry over unchanged.  The kernel is bound by instruction issue, not by the FP32 pipe: pairing the two
+// points of a projection unit (and two rows of an angle walk) halves the issue slots of their float chains.
+__device__ __forceinline__ unsigned long long f2_bits(float2 v) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
+    return r;
+}
+__device__ __forceinline__ float2 f2_from(unsigned long long r) {
+    float2 v;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(r));
+    return v;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+    return f2_from(r);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return f2_from(r);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return f2_from(r);
+}
+__device__ __forceinline__ float2 splat2(float c) { return make_float2(c, c); }
+// atan01 of two arguments at once (the same operations in the same order as atan01: bit-identical per half)
+__device__ __forceinline__ float2 atan01x2(float2 a) {
+    const float2 s = mul2(a, a);
+    float2 q = splat2(0.0021047850605100393f);
+    q = fma2(q, s, splat2(-0.012938526459038258f));
+    q = fma2(q, s, splat2(0.03731348365545273f));
+    q = fma2(q, s, splat2(-0.07019482553005219f));
+    q = fma2(q, s, splat2(0.1039692610502243f));
+    q = fma2(q, s, splat2(-0.14136579632759094f));
+    q = fma2(q, s, splat2(0.19983631372451782f));
+    q = fma2(q, s, splat2(-0.3333265483379364f));
+    return fma2(mul2(a, s), q, a);
+}
+
 // Union-find over vertical runs, 16-bit parents in shared memory: bits 0..14 = parent index, bit 15 = "ground" flag
 // (meaningful on roots).  A root is always hung under a root of higher priority, priority = a multiplicative hash of the
 // index (ties impossible: the hash is a bijection on 16 bits), so the forest is acyclic and — unlike linking by index,
@@ -233,6 +280,16 @@ __device__ __forceinline__ unsigned lds_u16(unsigned a) {
 __device__ __forceinline__ unsigned lds_u32(unsigned a) {
     unsigned v;
     asm volatile("ld.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds_f32(unsigned a) {
+    float v;
+    asm volatile("ld.shared::cta.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ double lds_f64(unsigned a) {
+    double v;
+    asm volatile("ld.shared::cta.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
     return v;
 }
 __device__ __forceinline__ void sts_u16(unsigned a, unsigned v) {
@@ -537,10 +594,11 @@ __device__ __forceinline__ float rcp_ftz(float a) {
 //    (alfa_gs.cpp:288-291) is taken in 2^-14 fixed point from one DFMA + F2I; a fractional part of 0 or 16383 (within
 //    6.1e-5 of an integer) or a value outside (1, 65535) — the range gates of alfa_gs.cpp:261 map to exactly 1 and 65535 —
 //    is not certified.
-//  * altitude / azimuth (utils.h:8-28): float atan on [0, 1] (atan01, error 6.6e-8 rad) after octant reduction with the
-//    raw MUFU rcp / rsqrt (flush-to-zero forms; operands below 1e-15 are not certified), reflections in exact 18-bit fixed
-//    point; the altitude gates (alfa_gs.cpp:269) and the cell edges (:275, :277) are tested on the fixed-point cell
-//    coordinates with margins of 1e-6 rad / 7.5e-7 rad.
+//  * altitude / azimuth (utils.h:8-28): float atan on [0, 1] (atan01, error 6.6e-8 rad); the azimuth after octant reduction
+//    with the raw MUFU rcp (flush-to-zero form; operands below 1e-15 are not certified) and reflections in exact 18-bit fixed
+//    point, the altitude from |z| * rsqrt(x^2 + y^2) for |altitude| <= 45 degrees (steeper points are not certified); the
+//    altitude gates (alfa_gs.cpp:269) and the cell edges (:275, :277) are tested on the fixed-point cell coordinates with
+//    margins of 1e-6 rad / 7.5e-7 rad.
 // ok = pixel (row, col, enc) certified.  Everything else — outside a gate, within a margin of a gate or an edge, the
 // flat-index alias column W, y == 0, non-finite — is classified by project_undecided / project_point_d.
 struct Lean {
@@ -548,49 +606,57 @@ struct Lean {
     unsigned enc;
     bool ok;
 };
-__device__ __forceinline__ Lean project_lean(const FusedArgs& A, float fx, float fy, float fz) {
+// project_lean2 evaluates the two points a warp lane handles per iteration together: their float chains (sums of squares,
+// quotients, both polynomial atans, scalings) run as packed f32x2 instructions, bit-identical to two scalar evaluations.
+__device__ __forceinline__ void project_lean2(const FusedArgs& A, const float4& pa, const float4& pb, Lean& oa, Lean& ob) {
     const KParams& kp = A.kp;
-    Lean o;
-    const double x = fx, y = fy, z = fz;
-    const double s2 = __fma_rn(x, x, __fma_rn(y, y, __dmul_rn(z, z)));
-    const float h2 = __fmaf_rn(fx, fx, __fmul_rn(fy, fy));
-    const double rd = static_cast<double>(rsqrt_ftz(__fmaf_rn(fz, fz, h2)));
-    const double r0 = __dmul_rn(s2, rd);
-    const double range = __fma_rn(__fma_rn(-r0, r0, s2), __dmul_rn(0.5, rd), r0);
-    const int ufix = __double2int_rz(__fma_rn(range, A.u_scale, A.u_c0));  // NaN -> 0, overflow saturates: both fail the test below
-    const unsigned ufrac = static_cast<unsigned>(ufix) & ((1u << UB) - 1u);
-    const bool range_ok = static_cast<unsigned>(ufix - ((1 << UB) + 1)) <= static_cast<unsigned>((65534 << UB) - 2) && ufrac - 1u <= (1u << UB) - 3u;
-    const bool xy_ok = fy != 0.0f && h2 > 1e-30f;  // atan2(-0.0, x < 0) = -pi in the reference (Q3); the flush-to-zero forms need h2 > 0
-    // altitude = atan2(z, hypot(x, y))
-    const float az = fabsf(fz);
-    const float h = __fmul_rn(h2, rsqrt_ftz(h2));
-    float t = atan01(__fmul_rn(fminf(az, h), rcp_ftz(fmaxf(az, h))));
-    if (az > h) t = 1.57079632679489662f - t;
-    const float alt = __uint_as_float(__float_as_uint(t) | (__float_as_uint(fz) & 0x80000000u));
-    const int altfix = __float2int_rn(__fmul_rn(alt, A.alt_to_fix));
-    const int rowfix = A.row0_fix - altfix;
-    const unsigned rfrac = static_cast<unsigned>(rowfix) & ((1u << FB) - 1u);
-    // azimuth in [0, 2 pi): octant reduction, reflections in exact fixed point
-    const float ax = fabsf(fx), ay = fabsf(fy);
-    int c = __float2int_rn(__fmul_rn(atan01(__fmul_rn(fminf(ax, ay), rcp_ftz(fmaxf(ax, ay)))), A.az_to_fix));
-    if (ay > ax) c = A.quarter_fix - c;
-    if (fx < 0.0f) c = 2 * A.quarter_fix - c;
-    if (fy < 0.0f) c = 4 * A.quarter_fix - c;
-    const int colfix = c + A.col_half_fix;
-    const unsigned cfrac = static_cast<unsigned>(colfix) & ((1u << FB) - 1u);
-    o.row = rowfix >> FB;
-    o.col = colfix >> FB;
-    o.enc = static_cast<unsigned>(ufix) >> UB;
+    const float2 fx = make_float2(pa.x, pb.x), fy = make_float2(pa.y, pb.y), fz = make_float2(pa.z, pb.z);
+    const float2 h2 = fma2(fx, fx, mul2(fy, fy));
+    const float2 s2f = fma2(fz, fz, h2);
+    const float2 hr = make_float2(rsqrt_ftz(h2.x), rsqrt_ftz(h2.y));
+    // altitude = atan2(z, hypot(x, y)) for |altitude| <= 45 degrees: tan = |z| / hypot = |z| * rsqrt(x^2 + y^2), no reciprocal and
+    // no octant reflection (relative error of the quotient: rsqrt.approx 2^-22.4 + the rounding of h2 and of one product, below
+    // the reciprocal form's).  Steeper points are left to the exact path — lidar beams beyond +-45 degrees sit outside every
+    // preset's altitude gates.  The azimuth octant and both points' polynomial chains run packed.
+    const float2 az = make_float2(fabsf(fz.x), fabsf(fz.y));
+    const float2 alt_q = mul2(az, hr);
+    const float2 ax = make_float2(fabsf(fx.x), fabsf(fx.y)), ay = make_float2(fabsf(fy.x), fabsf(fy.y));
+    const float2 azi_q = make_float2(__fmul_rn(fminf(ax.x, ay.x), rcp_ftz(fmaxf(ax.x, ay.x))), __fmul_rn(fminf(ax.y, ay.y), rcp_ftz(fmaxf(ax.y, ay.y))));
+    const float2 tf = mul2(atan01x2(alt_q), splat2(A.alt_to_fix));  // |altitude| in cell fixed point; the sign is applied to the product (exact either way)
+    const float2 ta = mul2(atan01x2(azi_q), splat2(A.az_to_fix));
     const unsigned rm = static_cast<unsigned>(A.row_margin), cm = static_cast<unsigned>(A.col_margin);
-    const bool gate_ok = static_cast<unsigned>(altfix - A.alt_gate_lo) <= static_cast<unsigned>(A.alt_gate_span);
-    const bool edges_ok = rfrac - rm <= (1u << FB) - 2u * rm && cfrac - cm <= (1u << FB) - 2u * cm;
-    // col < W: the alias column W of the alfa_gs variant (Q2) is left to the exact path
-    const bool box_ok = static_cast<unsigned>(o.row) < static_cast<unsigned>(kp.H) && static_cast<unsigned>(o.col) < static_cast<unsigned>(kp.W);
-    o.ok = range_ok && xy_ok && gate_ok && edges_ok && box_ok;
-    return o;
+    auto finish = [&](float x, float y, float z, float h2v, float s2fv, float altq, float tfv, float tav, Lean& o) {
+        const double xd = x, yd = y, zd = z;
+        const double s2 = __fma_rn(xd, xd, __fma_rn(yd, yd, __dmul_rn(zd, zd)));
+        const double rd = static_cast<double>(rsqrt_ftz(s2fv));
+        const double r0 = __dmul_rn(s2, rd);
+        const double range = __fma_rn(__fma_rn(-r0, r0, s2), __dmul_rn(0.5, rd), r0);
+        const int ufix = __double2int_rz(__fma_rn(range, A.u_scale, A.u_c0));  // NaN -> 0, overflow saturates: both fail the test below
+        const unsigned ufrac = static_cast<unsigned>(ufix) & ((1u << UB) - 1u);
+        const bool range_ok = static_cast<unsigned>(ufix - ((1 << UB) + 1)) <= static_cast<unsigned>((65534 << UB) - 2) && ufrac - 1u <= (1u << UB) - 3u;
+        const bool xy_ok = y != 0.0f && h2v > 1e-30f && altq <= 1.0f;  // false for NaN
+        const int altfix = __float2int_rn(__uint_as_float(__float_as_uint(tfv) | (__float_as_uint(z) & 0x80000000u)));
+        const int rowfix = A.row0_fix - altfix;
+        const unsigned rfrac = static_cast<unsigned>(rowfix) & ((1u << FB) - 1u);
+        int c = __float2int_rn(tav);
+        if (fabsf(y) > fabsf(x)) c = A.quarter_fix - c;
+        if (x < 0.0f) c = 2 * A.quarter_fix - c;
+        if (y < 0.0f) c = 4 * A.quarter_fix - c;
+        const int colfix = c + A.col_half_fix;
+        const unsigned cfrac = static_cast<unsigned>(colfix) & ((1u << FB) - 1u);
+        o.row = rowfix >> FB;
+        o.col = colfix >> FB;
+        o.enc = static_cast<unsigned>(ufix) >> UB;
+        const bool gate_ok = static_cast<unsigned>(altfix - A.alt_gate_lo) <= static_cast<unsigned>(A.alt_gate_span);
+        const bool edges_ok = rfrac - rm <= (1u << FB) - 2u * rm && cfrac - cm <= (1u << FB) - 2u * cm;
+        const bool box_ok = static_cast<unsigned>(o.row) < static_cast<unsigned>(kp.H) && static_cast<unsigned>(o.col) < static_cast<unsigned>(kp.W);
+        o.ok = range_ok && xy_ok && gate_ok && edges_ok && box_ok;
+    };
+    finish(pa.x, pa.y, pa.z, h2.x, s2f.x, alt_q.x, tf.x, ta.x, oa);
+    finish(pb.x, pb.y, pb.z, h2.y, s2f.y, alt_q.y, tf.y, ta.y, ob);
 }
-// a point project_lean did not certify: 1 = certainly dropped by a gate (alfa_gs.cpp:261, :269), 2 = exact evaluation.
-// Cold path: the range and the altitude are recomputed here (the same arithmetic as in project_lean) rather than kept
+// a point project_lean2 did not certify: 1 = certainly dropped by a gate (alfa_gs.cpp:261, :269), 2 = exact evaluation.
+// Cold path: the range and the altitude are recomputed here (the same arithmetic as in project_lean2) rather than kept
 // alive across the hot loop.
 __device__ __noinline__ int project_undecided(const GateConsts* __restrict__ Ap, float fx, float fy, float fz) {
     const GateConsts& A = *Ap;
@@ -614,7 +680,7 @@ __device__ __noinline__ int project_undecided(const GateConsts* __restrict__ Ap,
 
 // cheap column estimate used only to deal point blocks to CTAs (any answer is correct, a good one is fast)
 __device__ __forceinline__ int approx_col(const FusedArgs& A, float x, float y) {
-    // the azimuth of project_lean (octant reduction, polynomial atan, reflections in fixed point) without its certificates
+    // the azimuth of project_lean2 (octant reduction, polynomial atan, reflections in fixed point) without its certificates
     const float ax = fabsf(x), ay = fabsf(y);
     int c = __float2int_rn(__fmul_rn(atan01(__fmul_rn(fminf(ax, ay), rcp_ftz(fmaxf(fmaxf(ax, ay), 1e-30f)))), A.az_to_fix));
     if (ay > ax) c = A.quarter_fix - c;
@@ -623,6 +689,18 @@ __device__ __forceinline__ int approx_col(const FusedArgs& A, float x, float y) 
     return min(max((c + A.col_half_fix) >> FB, 0), A.kp.W - 1);
 }
 
+// true when lane + d exists and holds the same value (SHFL.DOWN's in-range predicate: no lane arithmetic)
+__device__ __forceinline__ bool shfl_down_eq(unsigned v, int d) {
+    unsigned r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b32 o;\n\t"
+        "shfl.sync.down.b32 o|p, %1, %2, 31, 0xffffffff;\n\t"
+        "setp.eq.and.b32 q, o, %1, p;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(r)
+        : "r"(v), "r"(d));
+    return r != 0;
+}
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -641,22 +719,6 @@ __device__ __forceinline__ void soft_cluster_sync(unsigned* bar, unsigned& epoch
     }
     __syncthreads();
 }
-
-struct Smem {
-    uint16_t* range;
-    uint16_t* tag;
-    uint8_t* angle;
-    unsigned long long* masks;  // aliases tag (dead after the projection)
-    unsigned* rowmask;          // [H][NG]   after masks
-    unsigned* grp_prefix;       // [H][NG]
-    unsigned* rowcnt_all;       // [MAX_CL][H]  written by every CTA of the cluster
-    unsigned* rowbase;          // [H]
-    uint8_t* assign;            // aliases angle (dead during the projection)
-    uint16_t* mylist;           // after assign
-    unsigned char* halo;        // fixed area: halo angle column [H]
-    unsigned long long* halo_masks;  // [4][NW]: right neighbour VALID, right neighbour G, left neighbour G, left neighbour HM, left neighbour HA
-    unsigned* flags;            // [MAX_CL] + misc counters
-};
 
 }  // namespace
 
@@ -864,18 +926,21 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             const int n_punits = nmine * (BLK / 64);
             // x, y, z are loaded as 8 + 4 bytes, not as one 16-byte record: the register of the unused intensity word would be
             // handed out as a temporary while the prefetch is in flight, and the first write to it waits for the load (WAW)
+            const float4* pts_r;  // the frame's base address as a register pair (one IMAD.WIDE per point address)
+            asm volatile("mov.u64 %0, %1;" : "=l"(pts_r) : "l"(pts));
+            const unsigned a_mylist = smem_base32 + off_angle + MAX_BLOCKS;  // s_mylist through the shared window (no SR_CgaCtaId per access)
             auto load_point = [&](int i) -> float4 {
                 float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (i < N) {
-                    const float2 xy = __ldcs(reinterpret_cast<const float2*>(pts + i));
+                    const float2 xy = __ldcs(reinterpret_cast<const float2*>(pts_r + i));
                     q.x = xy.x;
                     q.y = xy.y;
-                    q.z = __ldcs(reinterpret_cast<const float*>(pts + i) + 2);
+                    q.z = __ldcs(reinterpret_cast<const float*>(pts_r + i) + 2);
                 }
                 return q;
             };
             auto load_unit = [&](int u, float4& pa, float4& pb) -> int {
-                const int i0 = static_cast<int>(s_mylist[u >> 2]) * BLK + (u & 3) * 64 + lane;
+                const int i0 = static_cast<int>(lds_u16(a_mylist + 2 * (u >> 2))) * BLK + (u & 3) * 64 + lane;
                 pa = load_point(i0);
                 pb = load_point(i0 + 32);
                 return i0;
@@ -884,7 +949,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             // every point; the production instantiation keeps the hot path to the certified pixel, the key and one atomic,
             // with everything else (padding lanes, uncertified points, the alias column) in one cold branch
             const unsigned a_key = smem_base32 + off_range;  // shared-window address of the key slab
-            auto place = [&](auto checked_tag, auto nearest_tag, const float4 p4, const int i, const Lean& L) {
+            auto place = [&](auto checked_tag, auto nearest_tag, auto ts_tag, const int i, const Lean& L) {
                 constexpr bool CHECKED = decltype(checked_tag)::value;
                 // pixel_policy: the reference keeps the LAST point in input order (key = order tag << 16 | range, the later
                 // point has the larger key); the north-star variant keeps the NEAREST return, ties to the lowest index (key =
@@ -897,7 +962,11 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                 bool have = L.ok && i < N;
                 if (CHECKED || !have) {
                     if (i < N) {
-                        // not certified: a gate drop, or the exact evaluation (every point when statistics are collected)
+                        // not certified: a gate drop, or the exact evaluation (every point when statistics are collected).  The
+                        // coordinates are read again here (a cache hit, ~0.5 % of the points) instead of being kept in registers
+                        // through the hot path: the loop sits at its 64 registers, and what the compiler spills otherwise is a
+                        // register of the prefetched next unit — a store that waits for the load it was meant to overlap
+                        const float4 p4 = load_point(i);
                         int st = A.use_fast ? (L.ok ? 0 : project_undecided(A.gates_dev, p4.x, p4.y, p4.z)) : 2;
                         if (st == 2 || (CHECKED && stats1)) {
                             const Proj pr = project_point_d(A.kp_dev, p4.x, p4.y, p4.z);
@@ -931,43 +1000,41 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                 // points that share an order tag are 2^tag_shift consecutive lanes: the highest lane among those that hit the
                 // same pixel holds the latest point (xor-shuffles over the group; __match_any_sync would do the same for a
                 // whole warp but costs ~100 cycles of the address-divergence unit per call when all keys differ)
-                bool winner = have;
-                if (tag_shift) {  // uniform; 1 for frames of 64 Ki .. 128 Ki points
-                    if constexpr (NEAREST) {
+                // TS: 0 = every point has its own tag (no dedupe), 1 = pairs of lanes share a tag (frames of 64 Ki .. 128 Ki points),
+                // 2 = the run-time general case
+                constexpr int TS = decltype(ts_tag)::value;
+                bool lose = false;
+                if constexpr (NEAREST) {
+                    if (tag_shift) {  // uniform
                         // same pixel, same order tag: the larger key (smaller range) wins, equal ranges go to the lower lane (earlier point)
 #pragma unroll 1
                         for (int d = 1; d < (1 << tag_shift); ++d) {
                             const unsigned other = __shfl_xor_sync(0xffffffffu, k, d);
                             const unsigned oval = __shfl_xor_sync(0xffffffffu, val, d);
-                            if (other == k && (oval > val || (oval == val && (lane ^ d) < lane))) winner = false;
-                        }
-                    } else {
-                        const unsigned o1 = __shfl_xor_sync(0xffffffffu, k, 1);
-                        if (o1 == k && !(lane & 1)) winner = false;
-#pragma unroll 1
-                        for (int d = 2; d < (1 << tag_shift); ++d) {
-                            const unsigned other = __shfl_xor_sync(0xffffffffu, k, d);
-                            if (other == k && (lane ^ d) > lane) winner = false;
+                            if (other == k && (oval > val || (oval == val && (lane ^ d) < lane))) lose = true;
                         }
                     }
+                } else if constexpr (TS == 1) {
+                    // a lane loses when a HIGHER lane of the warp hits the same pixel: inside its tag group that is the rule, beyond
+                    // the group the higher lane carries a larger tag and would win the atomicMax anyway
+                    lose = shfl_down_eq(k, 1);
+                } else if constexpr (TS == 2) {
+                    if (tag_shift) {  // uniform
+#pragma unroll 1
+                        for (int d = 1; d < (1 << tag_shift); ++d) lose |= shfl_down_eq(k, d);
+                    }
                 }
+                const bool winner = have && !lose;
                 const bool local = winner && static_cast<int>(k >> 16) == rank;
                 if (local) asm volatile("red.shared::cta.max.u32 [%0], %1;" ::"r"(a_key + 4u * (k & 0xffffu)), "r"(val) : "memory");
-                // remote pixels: queue the record (warp-aggregated slot claim)
-                const bool remote = winner && !local;
-                const unsigned rm = __ballot_sync(0xffffffffu, remote);
-                if (rm) {
-                    unsigned base = 0;
-                    if (lane == 0) base = atomicAdd(&rcount[rank], __popc(rm));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (remote) {
-                        const unsigned slot = base + __popc(rm & ((1u << lane) - 1u));
-                        if (slot < A.rcap) rlist[slot] = make_uint2(k, val);
-                        if (CHECKED && stats1) GS_STAT(ST_REMOTE);
-                    }
+                // remote pixels: queue the record (the compiler aggregates the slot claim over the lanes of the branch)
+                if (winner && !local) {
+                    const unsigned slot = atomicAdd(&rcount[rank], 1u);
+                    if (slot < A.rcap) rlist[slot] = make_uint2(k, val);
+                    if (CHECKED && stats1) GS_STAT(ST_REMOTE);
                 }
             };
-            auto rounds = [&](auto checked_tag, auto nearest_tag) {
+            auto rounds = [&](auto checked_tag, auto nearest_tag, auto ts_tag) {
                 float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb4 = na;
                 int ni = 0;
                 if (warp < n_punits) ni = load_unit(warp, na, nb4);
@@ -975,17 +1042,27 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                     const float4 pa = na, pb = nb4;
                     const int i0 = ni;
                     if (u + NT / 32 < n_punits) ni = load_unit(u + NT / 32, na, nb4);
-                    const Lean La = project_lean(A, pa.x, pa.y, pa.z), Lb = project_lean(A, pb.x, pb.y, pb.z);  // straight-line: the two interleave
-                    place(checked_tag, nearest_tag, pa, i0, La);
-                    place(checked_tag, nearest_tag, pb, i0 + 32, Lb);
+                    Lean La, Lb;
+                    project_lean2(A, pa, pb, La, Lb);  // straight-line, the float chains of the two points packed (f32x2)
+                    place(checked_tag, nearest_tag, ts_tag, i0, La);
+                    place(checked_tag, nearest_tag, ts_tag, i0 + 32, Lb);
                 }
             };
+            using ts_any = std::integral_constant<int, 2>;
             if (kp.pixel_policy == GS_PIXEL_NEAREST) {  // uniform
-                if (stats1 || !A.use_fast) rounds(std::true_type{}, std::true_type{});
-                else rounds(std::false_type{}, std::true_type{});
+                if (stats1 || !A.use_fast) rounds(std::true_type{}, std::true_type{}, ts_any{});
+                else rounds(std::false_type{}, std::true_type{}, ts_any{});
+            } else if (stats1 || !A.use_fast) {
+                rounds(std::true_type{}, std::false_type{}, ts_any{});
+            } else if (tag_shift == 0) {  // the production instantiations: the dedupe of a frame's tag shift is compiled in
+                rounds(std::false_type{}, std::false_type{}, std::integral_constant<int, 0>{});
+            } else if (tag_shift == 1) {
+                rounds(std::false_type{}, std::false_type{}, std::integral_constant<int, 1>{});
+#if GS_EXP_DOUBLE == 1
+                rounds(std::false_type{}, std::false_type{}, std::integral_constant<int, 1>{});
+#endif
             } else {
-                if (stats1 || !A.use_fast) rounds(std::true_type{}, std::false_type{});
-                else rounds(std::false_type{}, std::false_type{});
+                rounds(std::false_type{}, std::false_type{}, ts_any{});
             }
         }
         GS_PHASE(2);
@@ -1162,51 +1239,67 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                         p_x = __fmul_rn(0.0f, 1.0f);  // 0 * cosf(0)
                     }
                 }
-                unsigned vbits = 0;
+                unsigned vbits = 0;  // shifted in row by row: the first row walked (hi) ends up at bit hi - lo
                 const uint16_t* p_rng = s_walk + hi * S16 + c;
                 uint8_t* p_ang = s_angle + hi * S8 + c;
-#pragma unroll 4
-                for (int r = hi; r >= lo; --r, p_rng -= S16, p_ang -= S8) {
-                    const unsigned e = *p_rng;
-                    unsigned a_out = 0;
-                    if (e) {
-                        vbits |= 1u << (r - lo);
-                        const double rng = decode_range_d(kp, e);
-                        const float sy = s_sin_y[r], cy = s_cos_y[r];
-                        if (has_prev) {
-                            const float dz = __double2float_rn(fabs(__dsub_rn(static_cast<double>(p_z), __dmul_rn(rng, s_sin_y_d[r]))));  // :366
-                            const float dx = __double2float_rn(fabs(__dsub_rn(static_cast<double>(p_x), __dmul_rn(rng, s_cos_y_d[r]))));  // :367
-                            // fast: float atan with a 2e-7 rad error budget; results within 4e-6 rad of a centi-radian edge
-                            // (and 0/0) are recomputed with the bit-exact clone of the host's atan2f
-                            float t = atan01(__fmul_rn(fminf(dz, dx), rcp_ftz(fmaxf(dz, dx))));
-                            if (dz > dx) t = 1.57079632679489662f - t;
-                            const float sc = __fmul_rn(t, 100.0f);  // 0 .. 157.1 (NaN for 0/0 and flushed operands: not sure)
-                            // floor and distance to the nearest integer with the 1.5 * 2^23 trick (FP32 adds instead of two
-                            // conversions on the XU pipe): bits(sc + M) - bits(M) = rn(sc)
-                            const float tm = __fadd_rn(sc, 12582912.0f);
-                            const float diff = __fsub_rn(sc, __fsub_rn(tm, 12582912.0f));  // sc - rn(sc), exact
-                            const int kk = (__float_as_int(tm) - 0x4B400000) - (diff < 0.0f ? 1 : 0);
-                            const bool sure = (!CHECKED || A.use_fast) && fabsf(diff) > 4e-4f;  // false for NaN
-                            a_out = static_cast<unsigned>(kk);
-                            if (!sure || (CHECKED && (A.stats & 1))) {
-                                const float alfa = atan2f_exact(dz, dx);       // :368
-                                const float scaled = __fmul_rn(alfa, 100.0f);  // :370
-                                const unsigned exact = static_cast<unsigned>(__float2int_rz(scaled));
-                                if ((CHECKED && (A.stats & 1))) {
-                                    const float fe = scaled - floorf(scaled);
-                                    if (fminf(fe, 1.0f - fe) < 1e-3f) GS_STAT(ST_NEAR_ANGLE);
-                                    if (!sure) GS_STAT(ST_FALLBACK);
-                                    else if (exact != a_out) GS_STAT(ST_MISMATCH);
-                                }
-                                if (!sure) a_out = exact;
-                            }
+                // the per-row tables through shared-window addresses that walk along with the row (no address arithmetic per pixel)
+                unsigned a_f = smem_base32 + off_lut + static_cast<unsigned>(reinterpret_cast<unsigned char*>(s_sin_y) - reinterpret_cast<unsigned char*>(s_cos_az)) + 4u * hi;
+                unsigned a_d = smem_base32 + off_lut + static_cast<unsigned>(reinterpret_cast<unsigned char*>(s_sin_y_d) - reinterpret_cast<unsigned char*>(s_cos_az)) + 8u * hi;
+                // Two rows per iteration: the differences (dz, dx) of a row depend on the previous non-empty pixel only through two
+                // products, so both rows' float chains (quotient, polynomial, scaling, rounding trick) run packed as f32x2.
+                // fast: float atan with a 2e-7 rad error budget; results within 4e-6 rad of a centi-radian edge (and 0/0) are
+                // recomputed with the bit-exact clone of the host's atan2f
+                // branch-free: an empty pixel (8 % of them) is evaluated like any other and its results are dropped by selects
+                auto row_in = [&](unsigned e, unsigned af, unsigned ad, bool& live, float& dz, float& dx) {
+                    const bool valid = e != 0u;
+                    const double rng = decode_range_d(kp, e);
+                    const float sy = lds_f32(af), cy = lds_f32(af + 4u * H);  // s_sin_y[r], s_cos_y[r]
+                    dz = __double2float_rn(fabs(__dsub_rn(static_cast<double>(p_z), __dmul_rn(rng, lds_f64(ad)))));           // :366  s_sin_y_d[r]
+                    dx = __double2float_rn(fabs(__dsub_rn(static_cast<double>(p_x), __dmul_rn(rng, lds_f64(ad + 8u * H)))));  // :367  s_cos_y_d[r]
+                    live = valid && has_prev;
+                    const float rf = __double2float_rn(rng);  // prev_r = range (:379)
+                    p_z = valid ? __fmul_rn(rf, sy) : p_z;
+                    p_x = valid ? __fmul_rn(rf, cy) : p_x;
+                    has_prev = has_prev || valid;
+                };
+                auto row_out = [&](bool live, float dz, float dx, float tm, float diff) -> unsigned {
+                    // bits(sc + M) - bits(M) = rn(sc), M = 1.5 * 2^23; diff = sc - rn(sc), exact
+                    const int kk = (__float_as_int(tm) - 0x4B400000) - (diff < 0.0f ? 1 : 0);
+                    const bool sure = (!CHECKED || A.use_fast) && fabsf(diff) > 4e-4f;  // false for NaN
+                    unsigned a_out = live ? static_cast<unsigned>(kk) : 0u;
+                    if (live && (!sure || (CHECKED && (A.stats & 1)))) {
+                        const float alfa = atan2f_exact(dz, dx);       // :368
+                        const float scaled = __fmul_rn(alfa, 100.0f);  // :370
+                        const unsigned exact = static_cast<unsigned>(__float2int_rz(scaled));
+                        if ((CHECKED && (A.stats & 1))) {
+                            const float fe = scaled - floorf(scaled);
+                            if (fminf(fe, 1.0f - fe) < 1e-3f) GS_STAT(ST_NEAR_ANGLE);
+                            if (!sure) GS_STAT(ST_FALLBACK);
+                            else if (exact != a_out) GS_STAT(ST_MISMATCH);
                         }
-                        const float rf = __double2float_rn(rng);
-                        p_z = __fmul_rn(rf, sy);
-                        p_x = __fmul_rn(rf, cy);
-                        has_prev = true;
+                        if (!sure) a_out = exact;
                     }
-                    *p_ang = static_cast<uint8_t>(a_out);
+                    return a_out;
+                };
+#pragma unroll 2
+                for (int r = hi; r >= lo; r -= 2, p_rng -= 2 * S16, p_ang -= 2 * S8, a_f -= 8u, a_d -= 16u) {
+                    // (a segment has 32 rows, or H rows for H = 2 .. 16: an even number — H is a power of two, checked on the host)
+                    const unsigned e0 = *p_rng;
+                    const unsigned e1 = *(p_rng - S16);
+                    vbits = (vbits << 2) | (e0 ? 2u : 0u) | (e1 ? 1u : 0u);
+                    bool live0, live1;
+                    float dz0, dx0, dz1, dx1;
+                    row_in(e0, a_f, a_d, live0, dz0, dx0);
+                    row_in(e1, a_f - 4u, a_d - 8u, live1, dz1, dx1);
+                    const float2 q = make_float2(__fmul_rn(fminf(dz0, dx0), rcp_ftz(fmaxf(dz0, dx0))), __fmul_rn(fminf(dz1, dx1), rcp_ftz(fmaxf(dz1, dx1))));
+                    float2 t = atan01x2(q);
+                    if (dz0 > dx0) t.x = 1.57079632679489662f - t.x;
+                    if (dz1 > dx1) t.y = 1.57079632679489662f - t.y;
+                    const float2 sc = mul2(t, splat2(100.0f));  // 0 .. 157.1 (NaN for 0/0 and flushed operands: not sure)
+                    const float2 tm = add2(sc, splat2(12582912.0f));
+                    const float2 diff = fma2(add2(tm, splat2(-12582912.0f)), splat2(-1.0f), sc);  // sc - (tm - M): the product is exact, one rounding
+                    *p_ang = static_cast<uint8_t>(row_out(live0, dz0, dx0, tm.x, diff.x));
+                    *(p_ang - S8) = static_cast<uint8_t>(row_out(live1, dz1, dx1, tm.y, diff.y));
                 }
                 // valid bits of this segment -> the column's VALID mask word
                 s_m32[(MK_VALID * NWD + wseg) * CW + c] = vbits;
@@ -1214,6 +1307,10 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         };
         if ((A.stats & 1) || !A.use_fast) angle_walk(std::true_type{});
         else angle_walk(std::false_type{});
+#if GS_EXP_DOUBLE == 2
+        __syncthreads();
+        angle_walk(std::false_type{});
+#endif
         if (A.repair) {
             // the ground search sees the ORIGINAL range image (cloud2range_node.cpp:473): VALID words from it, not from the repaired one
             const int nword = (H + 31) / 32;
@@ -1880,11 +1977,14 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             uint16_t* res = A.res_out ? A.res_out + static_cast<size_t>(f) * kp.P : nullptr;
             float4* cloud = A.xyz_out ? A.xyz_out + static_cast<size_t>(f) * kp.P : nullptr;
             const bool range_as_double = kp.variant == GS_VARIANT_CLOUD2RANGE;
+#if GS_EXP_DOUBLE == 3
+            for (int rep_ = 0; rep_ < 2; ++rep_)
+#endif
             for (int pair = warp; pair < H * NG; pair += NT / 32) {  // one warp per (row, 32-column group)
-                const int r = static_cast<int>(__umulhi(static_cast<unsigned>(pair), A.ng_magic));
+                const int r = SPEC ? pair / LC.NG : static_cast<int>(__umulhi(static_cast<unsigned>(pair), A.ng_magic));
                 const int gidx = pair - r * NG;
                 const int cc = gidx * 32 + lane;
-                if (cc < myCW) {
+                if ((SPEC && CWT % 32 == 0) || cc < myCW) {
                     const unsigned m = s_rowmask[pair];
                     const bool keep = (m >> lane) & 1u;
                     const unsigned enc = s_range[r * S16 + cc];
@@ -1983,7 +2083,7 @@ int fused_configure(FusedState& fs, const KParams& kp, const Luts& lut, const Sg
     fs.configured = false;
     // what the fused kernel covers; everything else runs on the staged kernels
     if (kp.pixel_policy != GS_PIXEL_LAST && kp.pixel_policy != GS_PIXEL_NEAREST) return 0;
-    if (kp.H > MAX_H || kp.W < 2 || (kp.H & (kp.H - 1)) != 0) return 0;  // beam counts that are powers of two (16 / 32 / 64 / 128)
+    if (kp.H > MAX_H || kp.H < 2 || kp.W < 2 || (kp.H & (kp.H - 1)) != 0) return 0;  // beam counts that are powers of two (16 / 32 / 64 / 128)
     const int NW = kp.H <= 64 ? 1 : 2;
     int max_smem = 0, n_sms = 0;
     cudaError_t e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -2213,7 +2313,7 @@ int fused_run(FusedState& fs, const Launch& L, const float4* points, const long 
     a.cnt = cnt;
     a.stats = stats;  // bit 0: verification + counters, bit 1: phase timing
     a.rcap = rcap;
-    // fast-path constants (see project_lean)
+    // fast-path constants (see project_lean2)
     {
         const double two_fb = static_cast<double>(1 << FB);
         const bool c2r = kp.variant == GS_VARIANT_CLOUD2RANGE;

@@ -1,5 +1,5 @@
 set -x
 D=gpurun_out/quick; mkdir -p $D
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "nearest or policy or full_pipeline or batch_device" > $D/pytest.log 2>&1; echo "pytest rc=$?" >> $D/pytest.log
-python tools/slow_paths.py > $D/slow_paths.txt 2>&1
-python bench.py --steps 5 --warmup 3 --frames 2048 --no-cpu-baseline > $D/bench.log 2> $D/bench.err
+timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "nearest or policy or full_pipeline or batch_device or adversarial or shuffl or large_batch or union or random_sensor or lone or beyond" > $D/pytest.log 2>&1; echo "pytest rc=$?" >> $D/pytest.log
+bash tools/ab_bench.sh > $D/ab.log 2>&1
+python tools/phase_profile.py > $D/phase.log 2>&1
