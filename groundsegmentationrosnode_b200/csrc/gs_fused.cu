@@ -41,8 +41,11 @@ namespace gs {
 namespace {
 
 #ifndef GS_EXP_DOUBLE
-#define GS_EXP_DOUBLE 0  // timing experiments: 1 / 2 / 3 run the projection / the angle walk / the output loop twice (idempotent)
+#define GS_EXP_DOUBLE 0  // timing experiments: run one (idempotent) phase twice — 1 projection, 2 angle walk, 3 output loop, 4 forest
+                         // read-out, 5 links + runs + seeds, 6 label / dilate / transposes / row counts, 7 link scan; the difference to the
+                         // normal build, timed on the same box (tools/ab_bench.sh), is what the phase costs in situ
 #endif
+#define GS_REPEAT(k) for (int rep_ = 0; rep_ < (GS_EXP_DOUBLE == (k) ? 2 : 1); ++rep_)
 #ifndef GS_READOUT_COMPRESS
 #define GS_READOUT_COMPRESS 1
 #endif
@@ -1440,6 +1443,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         // VABSDIFF4 the four differences, and "d <= K" is bit 7 of ((K | 0x80) - (d & 0x7f)) & ~d per byte (K < 128);
         // eight rows of those bits shifted together are the bytes of the four columns' mask words.
         const bool simd_links = (myCW & 3) == 0 && (H & 7) == 0 && kp.k_ground < 128;  // uniform
+        GS_REPEAT(5) {
         if (simd_links) {
             const int n_c4 = myCW >> 2;
             const unsigned k4 = (static_cast<unsigned>(kp.k_ground) * 0x01010101u) | 0x80808080u;
@@ -1537,6 +1541,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                 s_halo32[3 * 4 + w] = ha & s_haloL_valid[w] & MW(MK_VALID, w, 0);
             }
         }
+        }
         GS_PHASE(7);
         __syncthreads();  // the angle slab is free from here on (the link scan reuses it)
         GS_PHASE(8);
@@ -1575,7 +1580,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                 p -= nk;
             }
         };
-        {
+        GS_REPEAT(7) {
             unsigned carry = 0;
             for (int q0 = 0; q0 < n_q; q0 += NT) {
                 const int q = q0 + tid;
@@ -1801,7 +1806,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         }
         GS_PHASE(10);
         // read the ground mask of every unit out of the forest, two runs at a time (lock-step walks)
-        {
+        GS_REPEAT(4) {
             auto at = [&](const void* ptr) -> unsigned { return smem_base32 + static_cast<unsigned>(reinterpret_cast<const unsigned char*>(ptr) - smem_raw); };
             const unsigned a_par = at(s_par);
             const unsigned a_runs = at(s_m32 + static_cast<size_t>(MK_S) * NWD * CW), a_valid = at(s_m32 + static_cast<size_t>(MK_VALID) * NWD * CW);
@@ -1860,6 +1865,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         // ================================================================================ D: label image, dilation, erase
         // L = G | accepted empty seeds | empty pixels 4-adjacent to a ground pixel u with |angle(u) - angle(p)| <= K
         const Mask<NW> Hmask = Mask<NW>::low(H);
+        GS_REPEAT(6) {
         for (int c = tid; c < myCW; c += NT) {
             const Mask<NW> valid = ld_mask32<NW>(s_m32, MK_VALID, NWD, CW, c);
             const Mask<NW> g = ld_mask32<NW>(s_m32, MK_G, NWD, CW, c);
@@ -1917,6 +1923,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             } else {
                 for (int k = 0; k < CL; ++k) cluster.map_shared_rank(s_rowcnt_all, k)[rank * Hp + r] = run;
             }
+        }
         }
         // the frame this cluster takes next: rank 0 draws it from the queue all launches of the batch share and publishes it
         if (rank == 0 && tid == NT - 1) {
