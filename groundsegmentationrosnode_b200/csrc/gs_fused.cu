@@ -42,7 +42,7 @@ namespace {
 
 #ifndef GS_EXP_DOUBLE
 #define GS_EXP_DOUBLE 0  // timing experiments: run one (idempotent) phase twice — 1 projection, 2 angle walk, 3 output loop, 4 forest
-                         // read-out, 5 links + runs + seeds, 6 label / dilate / transposes / row counts, 7 link scan; the difference to the
+                         // read-out, 5 links + runs + seeds, 7 link scan (the label stage is NOT idempotent: it rewrites its seed mask); the difference to the
                          // normal build, timed on the same box (tools/ab_bench.sh), is what the phase costs in situ
 #endif
 #define GS_REPEAT(k) for (int rep_ = 0; rep_ < (GS_EXP_DOUBLE == (k) ? 2 : 1); ++rep_)
@@ -1865,7 +1865,6 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
         // ================================================================================ D: label image, dilation, erase
         // L = G | accepted empty seeds | empty pixels 4-adjacent to a ground pixel u with |angle(u) - angle(p)| <= K
         const Mask<NW> Hmask = Mask<NW>::low(H);
-        GS_REPEAT(6) {
         for (int c = tid; c < myCW; c += NT) {
             const Mask<NW> valid = ld_mask32<NW>(s_m32, MK_VALID, NWD, CW, c);
             const Mask<NW> g = ld_mask32<NW>(s_m32, MK_G, NWD, CW, c);
@@ -1923,7 +1922,6 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
             } else {
                 for (int k = 0; k < CL; ++k) cluster.map_shared_rank(s_rowcnt_all, k)[rank * Hp + r] = run;
             }
-        }
         }
         // the frame this cluster takes next: rank 0 draws it from the queue all launches of the batch share and publishes it
         if (rank == 0 && tid == NT - 1) {

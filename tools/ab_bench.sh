@@ -3,7 +3,7 @@
 D=gpurun_out/ab; mkdir -p $D; : > $D/ab.txt
 for round in 1 2; do
   for lib in groundsegmentationrosnode_b200/libgs_b200.so groundsegmentationrosnode_b200/variants/*.so; do
-    v=$(GS_B200_LIB=$PWD/$lib python bench.py --steps 5 --warmup 3 --frames 2048 --no-cpu-baseline --no-parity --e2e-frames 64 2>/dev/null | python -c "import sys,json; print(json.loads(sys.stdin.read().strip().splitlines()[-1])['value'])")
+    v=$(GS_B200_LIB=$PWD/$lib python bench.py --steps 5 --warmup 3 --frames ${AB_FRAMES:-2048} --no-cpu-baseline --no-parity --e2e-frames 64 2>/dev/null | python -c "import sys,json; print(json.loads(sys.stdin.read().strip().splitlines()[-1])['value'])")
     echo "$round $lib $v" >> $D/ab.txt
   done
 done
