@@ -1001,7 +1001,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_frame(const FusedArgs
                     val = NEAREST ? (((65536u - enc) << 16) | (65535u - tagv)) : ((tagv << 16) | enc);  // 65536 - enc is in [1, 65535]: never 0 = empty
                 }
                 // points that share an order tag are 2^tag_shift consecutive lanes: the highest lane among those that hit the
-                // same pixel holds the latest point (xor-shuffles over the group; __match_any_sync would do the same for a
+                // same pixel holds the latest point (down-shuffles over the group; __match_any_sync would do the same for a
                 // whole warp but costs ~100 cycles of the address-divergence unit per call when all keys differ)
                 // TS: 0 = every point has its own tag (no dedupe), 1 = pairs of lanes share a tag (frames of 64 Ki .. 128 Ki points),
                 // 2 = the run-time general case
